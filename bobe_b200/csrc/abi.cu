@@ -1,0 +1,473 @@
+// extern "C" entry points declared in include/bobe_b200.h (except bobe_mll_grad_batched, see mll_grad.cu).
+#include <cmath>
+
+#include "gemm_nt.cuh"
+#include "kernels.cuh"
+
+using namespace bobe;
+
+namespace {
+
+constexpr int64_t QCHUNK = 148 * 128;  // queries per predict chunk: one 128-query tile per SM
+
+inline double* align256(void* p) { return (double*)(((uintptr_t)p + 255) & ~(uintptr_t)255); }
+inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+struct Carver {
+    double* base;
+    int64_t off = 0;
+    explicit Carver(void* ws) : base(ws ? align256(ws) : nullptr) {}
+    double* take(int64_t doubles) {
+        double* p = base ? base + off : nullptr;
+        off += round_up(doubles, 32);
+        return p;
+    }
+    int64_t bytes() const { return off * 8 + 256; }
+    bool fits(void* ws, int64_t ws_bytes) const { return (char*)(base + off) <= (char*)ws + ws_bytes; }
+};
+
+// one warp per row: out[r] = c0 - sum_k M[r][k]^2
+__global__ void __launch_bounds__(256) row_sumsq_kernel(const double* __restrict__ Mtx, int64_t ld, int64_t rows,
+                                                        int64_t cols, double c0, double* __restrict__ out) {
+    int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const double* m = Mtx + r * ld;
+    double s = 0.0;
+    for (int64_t k = lane; k < cols; k += 32) s = fma(m[k], m[k], s);
+    s = warp_sum(s);
+    if (lane == 0) out[r] = c0 - s;
+}
+
+// var[c][j] = base[j] - (kc[c][j] - G[c][j])^2 / delta2[c]  with the reference's NaN / floor handling
+// (BOBE/gp.py:572-576); optional mean / mean-sqrt reduction over j accumulated into acc[c] chunk by chunk.
+__global__ void __launch_bounds__(256) fantasy_combine_kernel(const double* __restrict__ base, const double* __restrict__ kc,
+                                                              const double* __restrict__ G, int64_t ldg,
+                                                              const double* __restrict__ delta2, int64_t nj,
+                                                              double scale, int reduce, double* __restrict__ out,
+                                                              int64_t ldo, int64_t j_begin, double* __restrict__ acc) {
+    __shared__ double red[8];
+    const int64_t c = blockIdx.x;
+    double d2 = delta2[c];
+    if (d2 < 0.0) d2 = nan("");  // sqrt of a negative pivot in fast_update_cholesky (BOBE/gp.py:187)
+    double s = 0.0;
+    for (int64_t j = threadIdx.x; j < nj; j += 256) {
+        double t = kc[c * ldg + j] - G[c * ldg + j];
+        double var = base[j] - t * t / d2;
+        if (isnan(var)) var = SAFE_FLOOR;
+        if (var < SAFE_FLOOR) var = SAFE_FLOOR;
+        var *= scale;
+        if (reduce == BOBE_REDUCE_NONE)
+            out[c * ldo + j_begin + j] = var;
+        else
+            s += (reduce == BOBE_REDUCE_MEAN_SQRT) ? sqrt(var) : var;
+    }
+    if (reduce != BOBE_REDUCE_NONE) {
+        s = warp_sum(s);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += red[w];
+            acc[c] += t;  // chunks arrive in stream order: deterministic
+        }
+    }
+}
+
+__global__ void scale_out_kernel(const double* acc, int64_t C, double inv, double* out) {
+    int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (c < C) out[c] = acc[c] * inv;
+}
+
+// ---- rank-1 append ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) chol_append_solve_kernel(const double* __restrict__ L, int64_t n, int64_t ldl,
+                                                                 const double* __restrict__ k, double k_self,
+                                                                 double* __restrict__ last_row) {
+    extern __shared__ double v[];  // n
+    __shared__ double part[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t b = 0; b < n; b += 32) {
+        int64_t r = b + warp;
+        double s = 0.0;
+        if (r < n)
+            for (int64_t j = lane; j < b; j += 32) s = fma(L[r * ldl + j], v[j], s);
+        s = warp_sum(s);
+        if (lane == 0) part[warp] = s;
+        __syncthreads();
+        if (warp == 0) {
+            int64_t row = b + lane;
+            double rhs = (row < n) ? k[row] - part[lane] : 0.0;
+            double vl = 0.0;
+            for (int j = 0; j < 32 && b + j < n; ++j) {
+                double ljj = L[(b + j) * ldl + b + j];
+                double vj = __shfl_sync(0xffffffffu, rhs, j) / ljj;
+                if (lane == j) vl = vj;
+                if (lane > j && row < n) rhs = fma(-L[row * ldl + b + j], vj, rhs);
+            }
+            if (row < n) v[row] = vl;
+        }
+        __syncthreads();
+    }
+    double s = 0.0;
+    for (int64_t j = threadIdx.x; j < n; j += 1024) {
+        last_row[j] = v[j];
+        s = fma(v[j], v[j], s);
+    }
+    s = warp_sum(s);
+    __syncthreads();
+    if (lane == 0) part[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 32; ++w) t += part[w];
+        last_row[n] = sqrt(k_self - t);  // NaN if the fantasy point is numerically inside the span (BOBE/gp.py:187)
+    }
+}
+
+__global__ void chol_append_copy_kernel(const double* __restrict__ L, int64_t n, int64_t ldl, double* __restrict__ out,
+                                        int64_t ldo) {
+    int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x, r = blockIdx.y;
+    if (c <= n) out[r * ldo + c] = (c <= r && c < n) ? L[r * ldl + c] : 0.0;
+}
+
+// ---- EI / LogEI epilogue ---------------------------------------------------------------------------------------
+__device__ double log1mexp_dev(double x) {  // tfp.math.log1mexp: log(1 - exp(-|x|))
+    x = fabs(x);
+    return x < 0.6931471805599453 ? log(-expm1(-x)) : log1p(-exp(-x));
+}
+
+__global__ void acq_ei_kernel(int which, const double* __restrict__ mean, const double* __restrict__ var, int64_t M,
+                              double best_y, double zeta, double* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= M) return;
+    const double inv_sqrt_2pi = 0.39894228040143267794, log_2pi = 1.8378770664093454836;
+    double v = var[i];
+    if (which == BOBE_ACQ_EI) {
+        v = fmax(v, 1e-20);  // jnp.clip(var, a_min=1e-20), BOBE/acquisition.py:247
+        double sigma = sqrt(v);
+        double u = ((mean[i] - zeta) - best_y) / sigma;
+        double ei = (exp(-0.5 * u * u) * inv_sqrt_2pi + u * normcdf(u)) * sigma;
+        out[i] = -ei;
+    } else {
+        v = fmax(v, 1e-18);  // BOBE/acquisition.py:324
+        double sigma = sqrt(v);
+        double u = ((mean[i] - zeta) - best_y) / sigma;
+        double r;
+        if (u > -1.0) {  // BOBE/acquisition.py:57-59
+            r = log(exp(-0.5 * u * u) * inv_sqrt_2pi + u * normcdf(u));
+        } else {  // BOBE/acquisition.py:61-73
+            double ue = u < -1e6 ? -1e6 : u;
+            double w = log(fabs(ue) * erfcx(-0.70710678118654752440 * ue)) + 0.22579135264472743236;  // 1/2 log(pi/2)
+            double second = (u > -1e6) ? log1mexp_dev(w) : -2.0 * log(fabs(u));
+            r = -0.5 * (u * u + log_2pi) + second;
+        }
+        out[i] = -(r + log(sigma));
+    }
+}
+
+}  // namespace
+
+extern "C" const char* bobe_last_error_string(void) { return bobe::last_error(); }
+extern "C" int32_t bobe_abi_version(void) { return 1; }
+extern "C" int64_t bobe_npad(int64_t n) { return npad_of(n); }
+
+extern "C" int32_t bobe_kernel_matrix(void* stream, int32_t kind, const double* xa, int64_t n1, const double* xb,
+                                      int64_t n2, int64_t d, const double* ls, double kv, double noise,
+                                      int32_t add_noise, double* out, int64_t ldo) {
+    if (!xa || !xb || !ls || !out || n1 < 0 || n2 < 0 || d <= 0 || ldo < n2) {
+        set_error("kernel_matrix: bad arguments");
+        return BOBE_E_ARG;
+    }
+    if (add_noise && n1 != n2) {  // noise * eye(n1) only broadcasts for a square matrix (BOBE/gp.py:153)
+        set_error("kernel_matrix: add_noise needs a square matrix");
+        return BOBE_E_ARG;
+    }
+    if (n1 == 0 || n2 == 0) return BOBE_OK;
+    // rows are chunked so that grid.y stays small
+    const int64_t RCH = 64 * 32768;
+    for (int64_t r0 = 0; r0 < n1; r0 += RCH) {
+        int64_t rows = (n1 - r0 < RCH) ? n1 - r0 : RCH;
+        KmatArgs a{};
+        a.xa = xa + r0 * d; a.xb = xb; a.ls = ls; a.out = out + r0 * ldo;
+        a.n1 = rows; a.n2 = n2; a.d = d; a.ldo = ldo;
+        a.rows_pad = round_up(rows, 64); a.cols_pad = round_up(n2, 64);
+        a.store_rows = rows; a.store_cols = n2;
+        a.vec_ok = aligned16(out) && (ldo % 2 == 0);
+        a.kv = kv; a.noise = noise; a.add_noise = add_noise && r0 == 0 && rows == n1;
+        if (add_noise && rows != n1) {
+            set_error("kernel_matrix: add_noise with more than %lld rows unsupported", (long long)RCH);
+            return BOBE_E_ARG;
+        }
+        if (int32_t rc = launch_kmat((cudaStream_t)stream, kind, a, 1)) return rc;
+    }
+    return BOBE_OK;
+}
+
+// ---- factorize ------------------------------------------------------------------------------------------
+namespace {
+struct FactorLayout {
+    double *KB, *L, *Lt, *Linv, *U, *Q, *diag, *stat, *z, *alpha;
+    int64_t bytes;
+    bool fits;
+};
+FactorLayout factor_layout(void* ws, int64_t ws_bytes, int64_t n, int64_t batch, bool need_L, bool need_Linv) {
+    int64_t npad = npad_of(n), m2 = npad * npad;
+    Carver c(ws);
+    FactorLayout l{};
+    l.KB = c.take(batch * m2);
+    l.Lt = c.take(batch * m2);
+    l.U = c.take(batch * m2);
+    l.L = c.take(need_L ? batch * m2 : 0);
+    l.Linv = c.take(need_Linv ? batch * m2 : 0);
+    l.Q = c.take(batch * factor_q_elems(npad));
+    l.diag = c.take(batch * npad);
+    l.stat = c.take(3 * batch);
+    l.z = c.take(solve_ws_doubles(npad, batch));
+    l.alpha = c.take(batch * npad);
+    l.bytes = c.bytes();
+    l.fits = ws ? c.fits(ws, ws_bytes) : false;
+    return l;
+}
+}  // namespace
+
+extern "C" int64_t bobe_factorize_workspace_bytes(int64_t n, int64_t batch) {
+    if (n <= 0 || batch <= 0) return 0;
+    return factor_layout(nullptr, 0, n, batch, true, true).bytes;
+}
+
+extern "C" int32_t bobe_factorize(void* stream_, int32_t kind, const double* X, const double* y, int64_t n, int64_t d,
+                                  const double* ls, const double* kv, double noise, int64_t batch, double* L,
+                                  double* Linv, double* alpha, double* logdet, double* quad, int32_t* info, void* ws,
+                                  int64_t ws_bytes) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!X || !y || !ls || !kv || !ws || n <= 0 || d <= 0 || batch <= 0) {
+        set_error("factorize: bad arguments");
+        return BOBE_E_ARG;
+    }
+    FactorLayout l = factor_layout(ws, ws_bytes, n, batch, L == nullptr, Linv == nullptr);
+    if (!l.fits) {
+        set_error("factorize: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)l.bytes);
+        return BOBE_E_WORKSPACE;
+    }
+    if ((L && !aligned16(L)) || (Linv && !aligned16(Linv))) {
+        set_error("factorize: L / Linv must be 16-byte aligned");
+        return BOBE_E_ARG;
+    }
+    const int npad = (int)npad_of(n);
+    FactorBuffers fb{l.KB, L ? L : l.L, l.Lt, Linv ? Linv : l.Linv, l.U, l.Q, l.diag, l.stat, (int*)(l.stat + 2 * batch), 0};
+    KmatArgs ka{};
+    ka.xa = X; ka.xb = X; ka.ls = ls; ka.kv_ptr = kv; ka.out = fb.KB;
+    ka.n1 = n; ka.n2 = n; ka.d = d; ka.ldo = npad; ka.rows_pad = npad; ka.cols_pad = npad;
+    ka.store_rows = npad; ka.store_cols = npad; ka.vec_ok = 1;
+    ka.ls_stride = d; ka.out_stride = (int64_t)npad * npad; ka.noise = noise; ka.add_noise = 1; ka.pad_identity = 1;
+    if (int32_t rc = launch_kmat(stream, kind, ka, (int)batch)) return rc;
+    if (int32_t rc = factor_recursive(stream, fb, npad, (int)batch)) return rc;
+    SolveArgs sa{kind, X, ls, kv, d, noise};
+    return launch_solve_vectors(stream, fb, sa, y, n, npad, (int)batch, l.z, alpha ? alpha : l.alpha, logdet, quad,
+                                info);
+}
+
+// ---- predict --------------------------------------------------------------------------------------------
+extern "C" int64_t bobe_predict_workspace_bytes(int64_t n, int64_t d, int64_t M, int32_t mode) {
+    (void)d;
+    if (!(mode & BOBE_PREDICT_VAR) || M <= 0) return 256;
+    int64_t rows = round_up(M < QCHUNK ? M : QCHUNK, 128);
+    return rows * npad_of(n) * 8 + 512;
+}
+
+extern "C" int32_t bobe_predict(void* stream_, int32_t kind, const double* X, int64_t n, int64_t d, const double* ls,
+                                double kv, double noise, const double* Linv, const double* alpha, const double* Xq,
+                                int64_t M, double y_mean, double y_std, int32_t mode, double* mean_out,
+                                double* var_out, void* ws, int64_t ws_bytes) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool want_mean = mode & BOBE_PREDICT_MEAN, want_var = mode & BOBE_PREDICT_VAR;
+    const int standardised = (mode & BOBE_PREDICT_STANDARDISED) ? 1 : 0;
+    if (!X || !ls || !Xq || n <= 0 || d <= 0 || M < 0 || (want_mean && (!alpha || !mean_out)) ||
+        (want_var && (!Linv || !var_out)) || !(want_mean || want_var)) {
+        set_error("predict: bad arguments");
+        return BOBE_E_ARG;
+    }
+    if (M == 0) return BOBE_OK;
+    const int64_t npad = npad_of(n);
+    double* kstar = nullptr;
+    if (want_var) {
+        if (!ws || ws_bytes < bobe_predict_workspace_bytes(n, d, M, mode)) {
+            set_error("predict: workspace too small (%lld < %lld)", (long long)ws_bytes,
+                      (long long)bobe_predict_workspace_bytes(n, d, M, mode));
+            return BOBE_E_WORKSPACE;
+        }
+        if (!aligned16(Linv)) {
+            set_error("predict: Linv must be 16-byte aligned");
+            return BOBE_E_ARG;
+        }
+        kstar = align256(ws);
+    }
+    for (int64_t q0 = 0; q0 < M; q0 += QCHUNK) {
+        int64_t rows = (M - q0 < QCHUNK) ? M - q0 : QCHUNK;
+        int64_t rows_pad = round_up(rows, 128);
+        KmatArgs a{};
+        a.xa = Xq + q0 * d; a.xb = X; a.ls = ls; a.kv = kv; a.noise = noise;
+        a.alpha = want_mean ? alpha : nullptr;
+        a.mean_out = want_mean ? mean_out + q0 : nullptr;
+        a.out = kstar;
+        a.n1 = rows; a.n2 = n; a.d = d; a.ldo = npad; a.rows_pad = rows_pad; a.cols_pad = npad;
+        a.store_rows = rows_pad; a.store_cols = npad; a.vec_ok = 1;
+        a.y_mean = y_mean; a.y_std = y_std; a.mean_standardised = standardised;
+        if (int32_t rc = launch_kmat(stream, kind, a, 1)) return rc;
+        if (want_var) {
+            if (int32_t rc = launch_trmm_sumsq(stream, Linv, (int)npad, kstar, npad, rows_pad, q0, M, kv + noise,
+                                               y_std * y_std, standardised, var_out))
+                return rc;
+        }
+    }
+    return BOBE_OK;
+}
+
+// ---- fantasy variance ---------------------------------------------------------------------------------------
+namespace {
+constexpr int64_t MCCHUNK = 16384;
+struct FantasyLayout {
+    double *Kmc, *VT, *base, *Kc, *VcT, *delta2, *G, *kc, *acc;
+    int64_t chunk, cpad, bytes;
+    bool fits;
+};
+FantasyLayout fantasy_layout(void* ws, int64_t ws_bytes, int64_t n, int64_t n_mc, int64_t C, bool self) {
+    int64_t npad = npad_of(n);
+    FantasyLayout l{};
+    l.chunk = self ? round_up(n_mc, 64) : round_up(n_mc < MCCHUNK ? n_mc : MCCHUNK, 64);
+    l.cpad = self ? l.chunk : round_up(C, 64);
+    Carver c(ws);
+    l.Kmc = c.take(l.chunk * npad);
+    l.VT = c.take(l.chunk * npad);
+    l.base = c.take(l.chunk);
+    l.Kc = c.take(self ? 0 : l.cpad * npad);
+    l.VcT = c.take(self ? 0 : l.cpad * npad);
+    l.delta2 = c.take(self ? 0 : l.cpad);
+    l.G = c.take(l.cpad * l.chunk);
+    l.kc = c.take(l.cpad * l.chunk);
+    l.acc = c.take(l.cpad);
+    l.bytes = c.bytes();
+    l.fits = ws ? c.fits(ws, ws_bytes) : false;
+    return l;
+}
+}  // namespace
+
+extern "C" int64_t bobe_fantasy_var_workspace_bytes(int64_t n, int64_t d, int64_t n_mc, int64_t C) {
+    (void)d;
+    if (n <= 0 || n_mc <= 0) return 256;
+    // C <= 0 means "the MC points are the candidates"
+    return fantasy_layout(nullptr, 0, n, n_mc, C, C <= 0).bytes;
+}
+
+extern "C" int32_t bobe_fantasy_var(void* stream_, int32_t kind, const double* X, int64_t n, int64_t d,
+                                    const double* ls, double kv, double noise, const double* Linv, double y_std,
+                                    const double* Xmc, int64_t n_mc, const double* Xcand, int64_t C, int32_t reduce,
+                                    double* out, void* ws, int64_t ws_bytes) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool self = (Xcand == nullptr);
+    if (!X || !ls || !Linv || !Xmc || !out || !ws || n <= 0 || d <= 0 || n_mc <= 0 || (self ? C != n_mc : C <= 0)) {
+        set_error("fantasy_var: bad arguments");
+        return BOBE_E_ARG;
+    }
+    FantasyLayout l = fantasy_layout(ws, ws_bytes, n, n_mc, C, self);
+    if (!l.fits) {
+        set_error("fantasy_var: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)l.bytes);
+        return BOBE_E_WORKSPACE;
+    }
+    const int64_t npad = npad_of(n);
+    const double kk = kv + noise;  // kernel_diag(..., include_noise=True), BOBE/gp.py:561,570
+    auto kstar_panel = [&](const double* pts, int64_t rows, int64_t rows_pad, double* Kout) {
+        KmatArgs a{};
+        a.xa = pts; a.xb = X; a.ls = ls; a.kv = kv; a.noise = noise; a.out = Kout;
+        a.n1 = rows; a.n2 = n; a.d = d; a.ldo = npad; a.rows_pad = rows_pad; a.cols_pad = npad;
+        a.store_rows = rows_pad; a.store_cols = npad; a.vec_ok = 1;
+        return launch_kmat(stream, kind, a, 1);
+    };
+    auto apply_linv = [&](const double* Kin, int64_t rows_pad, double* Vout) {  // Vout[j][i] = sum_k Kin[j][k] Linv[i][k]
+        GemmArgs g{};
+        g.A = Kin; g.Bt = Linv; g.C = Vout; g.lda = g.ldb = g.ldc = npad;
+        g.M = (int)rows_pad; g.N = (int)npad; g.K = (int)npad; g.alpha = 1.0; g.flags = GEMM_B_LOWER;
+        return launch_gemm_nt(stream, g, 1);
+    };
+    auto rows_sumsq = [&](const double* Vin, int64_t rows, double* o) {
+        row_sumsq_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(Vin, npad, rows, npad, kk, o);
+        return check_launch("row_sumsq_kernel");
+    };
+    if (cudaMemsetAsync(l.acc, 0, l.cpad * 8, stream) != cudaSuccess) {
+        set_error("fantasy_var: memset failed");
+        return BOBE_E_CUDA;
+    }
+    const double* VcT = l.VcT;
+    const double* delta2 = l.delta2;
+    if (!self) {
+        if (int32_t rc = kstar_panel(Xcand, C, l.cpad, l.Kc)) return rc;
+        if (int32_t rc = apply_linv(l.Kc, l.cpad, l.VcT)) return rc;
+        if (int32_t rc = rows_sumsq(l.VcT, C, l.delta2)) return rc;
+    }
+    for (int64_t j0 = 0; j0 < n_mc; j0 += l.chunk) {
+        int64_t nj = (n_mc - j0 < l.chunk) ? n_mc - j0 : l.chunk;
+        int64_t nj_pad = round_up(nj, 64);
+        if (int32_t rc = kstar_panel(Xmc + j0 * d, nj, nj_pad, l.Kmc)) return rc;
+        if (int32_t rc = apply_linv(l.Kmc, nj_pad, l.VT)) return rc;
+        if (int32_t rc = rows_sumsq(l.VT, nj, l.base)) return rc;
+        if (self) {
+            VcT = l.VT;
+            delta2 = l.base;
+        }
+        {  // G[c][j] = sum_i VcT[c][i] VT[j][i]
+            GemmArgs g{};
+            g.A = VcT; g.Bt = l.VT; g.C = l.G; g.lda = g.ldb = npad; g.ldc = l.chunk;
+            g.M = (int)l.cpad; g.N = (int)nj_pad; g.K = (int)npad; g.alpha = 1.0;
+            if (int32_t rc = launch_gemm_nt(stream, g, 1)) return rc;
+        }
+        {  // kc[c][j] = k(x_c, mc_j)   (BOBE/gp.py:565-568)
+            KmatArgs a{};
+            a.xa = self ? Xmc : Xcand; a.xb = Xmc + j0 * d; a.ls = ls; a.kv = kv; a.noise = noise; a.out = l.kc;
+            a.n1 = C; a.n2 = nj; a.d = d; a.ldo = l.chunk; a.rows_pad = l.cpad; a.cols_pad = nj_pad;
+            a.store_rows = l.cpad; a.store_cols = nj_pad; a.vec_ok = 1;
+            if (int32_t rc = launch_kmat(stream, kind, a, 1)) return rc;
+        }
+        fantasy_combine_kernel<<<(unsigned)C, 256, 0, stream>>>(l.base, l.kc, l.G, l.chunk, delta2, nj, y_std * y_std,
+                                                              reduce, out, n_mc, j0, l.acc);
+        if (int32_t rc = check_launch("fantasy_combine_kernel")) return rc;
+    }
+    if (reduce != BOBE_REDUCE_NONE) {
+        scale_out_kernel<<<(unsigned)((C + 255) / 256), 256, 0, stream>>>(l.acc, C, 1.0 / (double)n_mc, out);
+        return check_launch("scale_out_kernel");
+    }
+    return BOBE_OK;
+}
+
+// ---- rank-1 append --------------------------------------------------------------------------------------
+extern "C" int32_t bobe_chol_append(void* stream_, const double* L, int64_t n, int64_t ldl, const double* k,
+                                    double k_self, double* L_out, int64_t ldo) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!L_out || n < 0 || ldo < n + 1 || (n > 0 && (!L || !k || ldl < n))) {
+        set_error("chol_append: bad arguments");
+        return BOBE_E_ARG;
+    }
+    if (n * 8 > 200 * 1024) {
+        set_error("chol_append: n=%lld too large for the single-CTA solve", (long long)n);
+        return BOBE_E_ARG;
+    }
+    if (n > 0) {
+        dim3 grid((unsigned)((n + 1 + 255) / 256), (unsigned)n);
+        chol_append_copy_kernel<<<grid, 256, 0, stream>>>(L, n, ldl, L_out, ldo);
+        if (int32_t rc = check_launch("chol_append_copy_kernel")) return rc;
+    }
+    int smem = (int)(n * 8 + 16);
+    cudaFuncSetAttribute(chol_append_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    chol_append_solve_kernel<<<1, 1024, smem, stream>>>(L, n, ldl, k, k_self, L_out + n * ldo);
+    return check_launch("chol_append_solve_kernel");
+}
+
+extern "C" int32_t bobe_acq_ei(void* stream, int32_t which, const double* mean, const double* var, int64_t M,
+                               double best_y, double zeta, double* out) {
+    if (!mean || !var || !out || M < 0 || (which != BOBE_ACQ_EI && which != BOBE_ACQ_LOGEI)) {
+        set_error("acq_ei: bad arguments");
+        return BOBE_E_ARG;
+    }
+    if (M == 0) return BOBE_OK;
+    acq_ei_kernel<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(which, mean, var, M, best_y, zeta, out);
+    return check_launch("acq_ei_kernel");
+}

@@ -1,0 +1,61 @@
+// Shared device/host helpers for the bobe_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+
+#include "../../include/bobe_b200.h"
+
+namespace bobe {
+
+constexpr int NB = 64;             // leaf block of the recursive factorisation; npad is a multiple of it
+constexpr double SAFE_FLOOR = 1e-12;  // BOBE/gp.py:16
+constexpr double SQRT5 = 2.23606797749978969641;
+
+inline int64_t npad_of(int64_t n) { return ((n + NB - 1) / NB) * NB; }
+inline int64_t round_up(int64_t a, int64_t b) { return ((a + b - 1) / b) * b; }
+
+void set_error(const char* fmt, ...);
+int32_t check_launch(const char* what);
+
+// ---- FP64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col).  SASS: DMMA.8x8x4 -------------------
+// lane = 4*g + t :  a = A[g][t],  b = B[t][g],  c0/c1 = C[g][2t], C[g][2t+1]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// ---- cp.async (LDGSTS) 16-byte copies with zero-fill predicate ---------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+    uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem_src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// kernel value from the squared scaled distance q (BOBE/gp.py:149-151 and :161-165)
+template <int KIND>
+__device__ __forceinline__ double kernel_from_q(double q, double kv) {
+    if (KIND == BOBE_KERNEL_RBF) {
+        return kv * exp(-0.5 * q);
+    } else {
+        double r = sqrt(q < 1e-30 ? 1e-30 : q);
+        double e = exp(-SQRT5 * r);
+        double poly = 1.0 + r * (SQRT5 + r * (5.0 / 3.0));
+        return kv * poly * e;
+    }
+}
+
+}  // namespace bobe

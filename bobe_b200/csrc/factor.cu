@@ -1,0 +1,347 @@
+// Recursive Cholesky + triangular inverse, batched over hyper-parameter sets (grid.z).
+//
+//   chol_inv([A11 . ; A21 A22]):  chol_inv(A11);  L21 = A21 Linv11^T;  A22 -= L21 L21^T;  chol_inv(A22);
+//                                 Linv21 = -(Linv22 L21) Linv11
+//
+// Every product is an NT GEMM on the FP64 tensor pipe (gemm_nt.cuh); each result is stored in both
+// orientations (L and Lt, Linv and U) so that the next product is again NT.  Leaves are NB x NB blocks
+// factorised and inverted by one CTA in shared memory.  Replaces jnp.linalg.cholesky + cho_solve +
+// solve_triangular at BOBE/gp.py:175-176,259-260,549-550 and supplies the L^-1 the predictive variance
+// (BOBE/gp.py:462,484) and the fantasy variance (:571) are built on.  A non-PD matrix yields NaN outputs
+// and info = 1 for that batch entry only, never an error.
+#include "gemm_nt.cuh"
+#include "kernels.cuh"
+
+namespace bobe {
+
+constexpr int LLD = NB + 1;
+constexpr double REFINE_RATIO = 1e3;
+
+__global__ void __launch_bounds__(256) leaf_chol_inv_kernel(const double* __restrict__ KB, double* __restrict__ L,
+                                                            double* __restrict__ Lt, double* __restrict__ Linv,
+                                                            double* __restrict__ U, double* __restrict__ diag,
+                                                            double* __restrict__ dstat, int* __restrict__ gate,
+                                                            int npad, int o) {
+    extern __shared__ __align__(16) double sm[];
+    double* A = sm;                  // [NB][LLD] lower factor being built
+    double* X = sm + NB * LLD;       // [NB][LLD] its inverse
+    double* dd = X + NB * LLD;       // [NB]
+    double* invd = dd + NB;          // [NB]
+    const int tid = threadIdx.x;
+    const int64_t zoff = (int64_t)blockIdx.z * npad * npad;
+    const double* Kz = KB + zoff + (int64_t)o * npad + o;
+
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        int r = idx >> 6, c = idx & 63;
+        A[r * LLD + c] = (c <= r) ? Kz[(int64_t)r * npad + c] : 0.0;
+        X[r * LLD + c] = 0.0;
+    }
+    // unblocked right-looking Cholesky
+    for (int j = 0; j < NB; ++j) {
+        __syncthreads();
+        double dj = sqrt(A[j * LLD + j]);
+        if (tid > j && tid < NB) A[tid * LLD + j] = A[tid * LLD + j] / dj;
+        if (tid == j) dd[j] = dj;
+        __syncthreads();
+        for (int i = j + 1 + (tid >> 4); i < NB; i += 16) {
+            double aij = A[i * LLD + j];
+            for (int k = j + 1 + (tid & 15); k <= i; k += 16) A[i * LLD + k] = fma(-aij, A[k * LLD + j], A[i * LLD + k]);
+        }
+    }
+    __syncthreads();
+    if (tid < NB) invd[tid] = 1.0 / dd[tid];
+    __syncthreads();
+    // inverse by forward substitution: 4 lanes per column
+    {
+        const int c = tid >> 2, l4 = tid & 3;
+        const int cmin = (tid >> 5) << 3;  // smallest column handled by this warp
+        if (l4 == 0) X[c * LLD + c] = invd[c];
+        __syncwarp();
+        for (int i = cmin + 1; i < NB; ++i) {
+            double s = 0.0;
+            if (i > c)
+                for (int k = c + l4; k < i; k += 4) s = fma(A[i * LLD + k], X[k * LLD + c], s);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (l4 == 0 && i > c) X[i * LLD + c] = -s * invd[i];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    double* Lz = L + zoff + (int64_t)o * npad + o;
+    double* Ltz = Lt + zoff + (int64_t)o * npad + o;
+    double* Liz = Linv + zoff + (int64_t)o * npad + o;
+    double* Uz = U + zoff + (int64_t)o * npad + o;
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        int r = idx >> 6, c = idx & 63;
+        int64_t off = (int64_t)r * npad + c;
+        double d = dd[r];
+        Lz[off] = (c < r) ? A[r * LLD + c] : (c == r ? d : 0.0);
+        Ltz[off] = (c > r) ? A[c * LLD + r] : (c == r ? d : 0.0);
+        Liz[off] = (c <= r) ? X[r * LLD + c] : 0.0;
+        Uz[off] = (c >= r) ? X[c * LLD + r] : 0.0;
+    }
+    if (tid < NB) diag[(int64_t)blockIdx.z * npad + o + tid] = dd[tid];
+    // running extreme pivots of this matrix (leaves of one matrix run in stream order: no atomics needed).
+    // max/min pivot is a lower bound on cond(L); beyond REFINE_RATIO the panel solves get a correction step.
+    if (tid == 0) {
+        double lo = dstat[blockIdx.z * 2], hi = dstat[blockIdx.z * 2 + 1];
+        for (int i = 0; i < NB; ++i) {
+            lo = fmin(lo, dd[i]);
+            hi = fmax(hi, dd[i]);
+        }
+        dstat[blockIdx.z * 2] = lo;
+        dstat[blockIdx.z * 2 + 1] = hi;
+        if (hi > REFINE_RATIO * lo) gate[blockIdx.z] = 1;
+    }
+}
+
+__global__ void init_stat_kernel(double* dstat, int* gate, int batch, int force) {
+    int z = blockIdx.x * blockDim.x + threadIdx.x;
+    if (z < batch) {
+        dstat[2 * z] = 1e300;
+        dstat[2 * z + 1] = 0.0;
+        gate[z] = force;
+    }
+}
+
+int64_t factor_q_elems(int64_t npad) {
+    int64_t m = ((npad / NB + 1) / 2) * NB;
+    return m * m;
+}
+
+namespace {
+struct Rec {
+    cudaStream_t stream;
+    const FactorBuffers& fb;
+    int npad, batch;
+    int64_t mstride, qstride;
+    int32_t rc = BOBE_OK;
+
+    double* at(double* base, int rb, int cb) const { return base + (int64_t)rb * NB * npad + (int64_t)cb * NB; }
+
+    void gemm(const GemmArgs& a) {
+        if (rc == BOBE_OK) rc = launch_gemm_nt(stream, a, batch);
+    }
+
+    void run(int b0, int b1) {
+        if (rc != BOBE_OK) return;
+        int nb = b1 - b0;
+        if (nb == 1) {
+            int smem = (2 * NB * LLD + 2 * NB) * (int)sizeof(double);
+            cudaFuncSetAttribute(leaf_chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            leaf_chol_inv_kernel<<<dim3(1, 1, batch), 256, smem, stream>>>(fb.KB, fb.L, fb.Lt, fb.Linv, fb.U, fb.diag,
+                                                                         fb.dstat, fb.gate, npad, b0 * NB);
+            rc = check_launch("leaf_chol_inv_kernel");
+            return;
+        }
+        int mid = b0 + (nb + 1) / 2;
+        int m1 = (mid - b0) * NB, m2 = (b1 - mid) * NB;
+        run(b0, mid);
+        auto base = [&]() {
+            GemmArgs g{};
+            g.lda = g.ldb = g.ldc = g.ldct = g.ldd = npad;
+            g.strideA = g.strideB = g.strideC = g.strideCt = g.strideD = mstride;
+            g.alpha = 1.0;
+            return g;
+        };
+        {   // L21 = A21 * Linv11^T   (stored as L21 and as its transpose)
+            GemmArgs g = base();
+            g.A = at(fb.KB, mid, b0); g.Bt = at(fb.Linv, b0, b0); g.C = at(fb.L, mid, b0); g.Ct = at(fb.Lt, b0, mid);
+            g.M = m2; g.N = m1; g.K = m1; g.flags = GEMM_B_LOWER;
+            gemm(g);
+        }
+        // Correction of the panel solve, only for ill-conditioned matrices (gate set by the leaves):
+        // a product with the explicit inverse is not backward stable (error ~ cond(L11) eps); one step of
+        //   R = A21 - L21 L11^T,   L21 += R Linv11^T
+        // restores an O(eps) residual (measured: profiles/r01/accuracy_probe.txt).
+        {
+            GemmArgs g = base();
+            g.A = at(fb.L, mid, b0); g.Bt = at(fb.L, b0, b0); g.C = fb.Q; g.D = at(fb.KB, mid, b0);
+            g.ldc = m1; g.strideC = qstride; g.gate = fb.gate;
+            g.M = m2; g.N = m1; g.K = m1; g.alpha = -1.0; g.flags = GEMM_B_LOWER;
+            gemm(g);
+            g = base();
+            g.A = fb.Q; g.lda = m1; g.strideA = qstride; g.Bt = at(fb.Linv, b0, b0);
+            g.C = at(fb.L, mid, b0); g.D = g.C; g.Ct = at(fb.Lt, b0, mid); g.gate = fb.gate;
+            g.M = m2; g.N = m1; g.K = m1; g.flags = GEMM_B_LOWER;
+            gemm(g);
+        }
+        {   // A22 -= L21 * L21^T   (lower tiles only)
+            GemmArgs g = base();
+            g.A = at(fb.L, mid, b0); g.Bt = at(fb.L, mid, b0); g.C = at(fb.KB, mid, mid); g.D = g.C;
+            g.M = m2; g.N = m2; g.K = m1; g.alpha = -1.0; g.flags = GEMM_C_LOWER;
+            gemm(g);
+        }
+        run(mid, b1);
+        {   // Q = Linv22 * L21
+            GemmArgs g = base();
+            g.A = at(fb.Linv, mid, mid); g.Bt = at(fb.Lt, b0, mid); g.C = fb.Q;
+            g.ldc = m1; g.strideC = qstride;
+            g.M = m2; g.N = m1; g.K = m2; g.flags = GEMM_A_LOWER;
+            gemm(g);
+        }
+        {   // Linv21 = -Q * Linv11   (stored as Linv21 and as U12 = Linv21^T)
+            GemmArgs g = base();
+            g.A = fb.Q; g.lda = m1; g.strideA = qstride;
+            g.Bt = at(fb.U, b0, b0); g.C = at(fb.Linv, mid, b0); g.Ct = at(fb.U, b0, mid);
+            g.M = m2; g.N = m1; g.K = m1; g.alpha = -1.0; g.flags = GEMM_B_UPPER;
+            gemm(g);
+        }
+    }
+};
+}  // namespace
+
+// zero the off-diagonal upper blocks of L/Linv and lower blocks of Lt/U (the GEMMs never write them)
+__global__ void zero_other_triangle_kernel(double* L, double* Lt, double* Linv, double* U, int npad) {
+    const int64_t zoff = (int64_t)blockIdx.z * npad * npad;
+    const int rb = blockIdx.y, cb = blockIdx.x;
+    if (rb == cb) return;
+    double* lo0 = (cb > rb) ? L : Lt;     // L, Linv: zero where col block > row block
+    double* lo1 = (cb > rb) ? Linv : U;   // Lt, U: zero where col block < row block
+    for (int idx = threadIdx.x; idx < NB * NB; idx += blockDim.x) {
+        int r = idx >> 6, c = idx & 63;
+        int64_t off = zoff + (int64_t)(rb * NB + r) * npad + cb * NB + c;
+        lo0[off] = 0.0;
+        lo1[off] = 0.0;
+    }
+}
+
+int32_t factor_recursive(cudaStream_t stream, const FactorBuffers& fb, int npad, int batch) {
+    if (npad % NB) {
+        set_error("factor: npad=%d not a multiple of %d", npad, NB);
+        return BOBE_E_ARG;
+    }
+    int nbk = npad / NB;
+    init_stat_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(fb.dstat, fb.gate, batch, fb.force_refine);
+    if (int32_t rc = check_launch("init_stat_kernel")) return rc;
+    if (nbk > 1) {
+        zero_other_triangle_kernel<<<dim3(nbk, nbk, batch), 256, 0, stream>>>(fb.L, fb.Lt, fb.Linv, fb.U, npad);
+        if (int32_t rc = check_launch("zero_other_triangle_kernel")) return rc;
+    }
+    Rec r{stream, fb, npad, batch, (int64_t)npad * npad, factor_q_elems(npad)};
+    r.run(0, nbk);
+    return r.rc;
+}
+
+int32_t launch_kinv(cudaStream_t stream, const FactorBuffers& fb, int npad, int batch) {
+    GemmArgs g{};
+    g.A = fb.U; g.Bt = fb.U; g.C = fb.KB; g.Ct = fb.KB;
+    g.lda = g.ldb = g.ldc = g.ldct = npad;
+    g.strideA = g.strideB = g.strideC = g.strideCt = (int64_t)npad * npad;
+    g.M = g.N = g.K = npad; g.alpha = 1.0;
+    g.flags = GEMM_A_UPPER | GEMM_B_UPPER | GEMM_C_LOWER;
+    return launch_gemm_nt(stream, g, batch);
+}
+
+// ---- vectors: alpha = U (Linv y) with one gated step of iterative refinement, logdet, quad, info -----------
+// one warp per row; fixed summation order (deterministic)
+__global__ void __launch_bounds__(256) matvec_tri_kernel(const double* __restrict__ Mtx, const double* __restrict__ x,
+                                                         int64_t xstride, double* __restrict__ out, int64_t ostride,
+                                                         int npad, int upper, int accumulate,
+                                                         const int* __restrict__ gate) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int64_t z = blockIdx.y;
+    if (row >= npad || (gate && gate[z] == 0)) return;
+    const double* m = Mtx + z * (int64_t)npad * npad + (int64_t)row * npad;
+    const double* xv = x + z * xstride;
+    int kb = upper ? row : 0, ke = upper ? npad : row + 1;
+    double s = 0.0;
+    for (int k = kb + lane; k < ke; k += 32) s = fma(m[k], xv[k], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+        if (accumulate) s += out[z * ostride + row];
+        out[z * ostride + row] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256) pad_y_kernel(const double* __restrict__ y, int64_t n, int npad, double* ypad) {
+    int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < npad) ypad[i] = i < n ? y[i] : 0.0;
+}
+
+// r = y - (K0 alpha) - noise * alpha   (K0 alpha comes from the kernel-matrix pass; rows >= n stay 0)
+__global__ void __launch_bounds__(256) residual_kernel(const double* __restrict__ ypad, const double* __restrict__ k0a,
+                                                       const double* __restrict__ alpha, double noise, int64_t n,
+                                                       int npad, double* __restrict__ r, const int* __restrict__ gate) {
+    int i = blockIdx.x * 256 + threadIdx.x;
+    const int64_t z = blockIdx.y;
+    if (i >= npad || (gate && gate[z] == 0)) return;
+    int64_t o = z * npad + i;
+    r[o] = i < n ? (ypad[i] - k0a[o]) - noise * alpha[o] : 0.0;
+}
+
+__global__ void __launch_bounds__(256) factor_scalars_kernel(const double* __restrict__ diag,
+                                                             const double* __restrict__ zv, int npad,
+                                                             double* logdet, double* quad, int32_t* info) {
+    __shared__ double s1[8], s2[8];
+    __shared__ int sbad[8];
+    const int64_t z = blockIdx.x;
+    double a = 0.0, b = 0.0;
+    int bad = 0;
+    for (int i = threadIdx.x; i < npad; i += 256) {
+        double d = diag[z * npad + i];
+        if (!(d > 0.0) || isinf(d)) bad = 1;
+        a += log(d);
+        double zz = zv[z * npad + i];
+        b = fma(zz, zz, b);
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    bad = __any_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+        s1[threadIdx.x >> 5] = a;
+        s2[threadIdx.x >> 5] = b;
+        sbad[threadIdx.x >> 5] = bad;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ta = 0.0, tb = 0.0;
+        int tbad = 0;
+        for (int w = 0; w < 8; ++w) {
+            ta += s1[w];
+            tb += s2[w];
+            tbad |= sbad[w];
+        }
+        if (tbad) ta = tb = nan("");
+        if (logdet) logdet[z] = ta;
+        if (quad) quad[z] = tb;
+        if (info) info[z] = tbad;
+    }
+}
+
+// scratch: padded y (npad) + three (batch, npad) vectors
+int64_t solve_ws_doubles(int64_t npad, int64_t batch) { return (3 * batch + 1) * npad; }
+
+// alpha must be (batch, npad).  For ill-conditioned matrices (gate set during the factorisation) alpha gets
+// one step of iterative refinement against a freshly rebuilt K:  alpha += K^-1 (y - K alpha).
+int32_t launch_solve_vectors(cudaStream_t stream, const FactorBuffers& fb, const SolveArgs& sa, const double* y,
+                             int64_t n, int npad, int batch, double* z_ws, double* alpha, double* logdet,
+                             double* quad, int32_t* info) {
+    double* ypad = z_ws;                               // (npad) shared by all batch entries
+    double* zv = z_ws + npad;                          // (batch, npad)
+    double* k0a = zv + (int64_t)batch * npad;          // (batch, npad)
+    double* rv = k0a + (int64_t)batch * npad;          // (batch, npad)
+    pad_y_kernel<<<(npad + 255) / 256, 256, 0, stream>>>(y, n, npad, ypad);
+    dim3 grid((npad + 7) / 8, batch);
+    matvec_tri_kernel<<<grid, 256, 0, stream>>>(fb.Linv, ypad, 0, zv, npad, npad, 0, 0, nullptr);
+    matvec_tri_kernel<<<grid, 256, 0, stream>>>(fb.U, zv, npad, alpha, npad, npad, 1, 0, nullptr);
+    if (int32_t rc = check_launch("solve_vectors")) return rc;
+    {
+        KmatArgs ka{};
+        ka.xa = sa.X; ka.xb = sa.X; ka.ls = sa.ls; ka.kv_ptr = sa.kv; ka.alpha = alpha; ka.mean_out = k0a;
+        ka.n1 = n; ka.n2 = n; ka.d = sa.d; ka.rows_pad = npad; ka.cols_pad = npad;
+        ka.ls_stride = sa.d; ka.alpha_stride = npad; ka.mean_stride = npad; ka.mean_standardised = 1;
+        ka.gate = fb.gate;
+        if (int32_t rc = launch_kmat(stream, sa.kind, ka, batch)) return rc;
+        residual_kernel<<<dim3((npad + 255) / 256, batch), 256, 0, stream>>>(ypad, k0a, alpha, sa.noise, n, npad, rv,
+                                                                           fb.gate);
+        // z of the first solve is kept: quad = z^T z is a sum of squares (no cancellation), unlike y^T alpha
+        matvec_tri_kernel<<<grid, 256, 0, stream>>>(fb.Linv, rv, npad, k0a, npad, npad, 0, 0, fb.gate);
+        matvec_tri_kernel<<<grid, 256, 0, stream>>>(fb.U, k0a, npad, alpha, npad, npad, 1, 1, fb.gate);
+    }
+    factor_scalars_kernel<<<batch, 256, 0, stream>>>(fb.diag, zv, npad, logdet, quad, info);
+    return check_launch("solve_vectors");
+}
+
+}  // namespace bobe

@@ -1,0 +1,65 @@
+// Internal launcher declarations shared between translation units.
+#pragma once
+#include "common.cuh"
+
+namespace bobe {
+
+const char* last_error();
+
+// kernel-matrix family (kernel_matrix.cu) ---------------------------------------------------------------
+struct KmatArgs {
+    const double* xa;      // (n1, d) rows of the output
+    const double* xb;      // (n2, d) columns of the output
+    const double* ls;      // (batch, d) lengthscales, stride ls_stride
+    const double* kv_ptr;  // (batch) kernel variances or null -> kv
+    const double* alpha;   // (cols_pad) optional: mean_out[i] = sum_j alpha[j] K[i][j]   (needs col_splits == 1)
+    double* out;           // (rows_pad, ldo) or null (mean only)
+    double* mean_out;      // (n1) optional
+    int64_t n1, n2, d, ldo;
+    int64_t rows_pad, cols_pad;  // extent computed (multiples of 64); outside (n1, n2): identity if pad_identity else 0
+    int64_t store_rows, store_cols;  // extent actually stored to `out`
+    int vec_ok;                  // out base 16-byte aligned, ldo and out_stride even -> 16-byte stores
+    int64_t ls_stride, out_stride, alpha_stride, mean_stride;
+    const int* gate;             // optional per-batch switch (no-op where gate[z] == 0)
+    double kv, noise, y_mean, y_std;
+    int add_noise;     // + noise on the diagonal (square case)
+    int pad_identity;  // 1: padded part is the identity (factorisation input), 0: zeros (K* panels)
+    int mean_standardised;
+};
+int32_t launch_kmat(cudaStream_t stream, int kind, const KmatArgs& a, int batch);
+
+// trmm + sumsq (gemm.cu) ---------------------------------------------------------------------------------
+int32_t launch_trmm_sumsq(cudaStream_t stream, const double* Linv, int npad, const double* Kstar, int64_t ldk,
+                          int64_t rows_pad, int64_t q_begin, int64_t M, double kk, double scale, int standardised,
+                          double* var_out);
+
+// factorisation (factor.cu) -----------------------------------------------------------------------------
+struct FactorBuffers {
+    double* KB;    // (batch, npad, npad) in: K (lower used); out: scratch / K^-1 if requested
+    double* L;     // (batch, npad, npad) lower factor, zero upper
+    double* Lt;    // (batch, npad, npad) its transpose
+    double* Linv;  // (batch, npad, npad) L^-1 lower
+    double* U;     // (batch, npad, npad) (L^-1)^T upper
+    double* Q;     // (batch, npad/2+NB, npad/2+NB) scratch
+    double* diag;  // (batch, npad) diagonal of L
+    double* dstat; // (batch, 2) running min / max pivot
+    int* gate;     // (batch) 1 once max/min pivot exceeds the refinement ratio
+    int force_refine;
+};
+int64_t factor_q_elems(int64_t npad);
+int32_t factor_recursive(cudaStream_t stream, const FactorBuffers& fb, int npad, int batch);
+int32_t launch_kinv(cudaStream_t stream, const FactorBuffers& fb, int npad, int batch);  // KB <- U U^T (full symmetric)
+struct SolveArgs {  // what the alpha refinement needs to rebuild K alpha
+    int kind;
+    const double* X;
+    const double* ls;  // (batch, d)
+    const double* kv;  // (batch)
+    int64_t d;
+    double noise;
+};
+int64_t solve_ws_doubles(int64_t npad, int64_t batch);
+int32_t launch_solve_vectors(cudaStream_t stream, const FactorBuffers& fb, const SolveArgs& sa, const double* y,
+                             int64_t n, int npad, int batch, double* z_ws, double* alpha, double* logdet,
+                             double* quad, int32_t* info);
+
+}  // namespace bobe

@@ -1,0 +1,273 @@
+// Log marginal likelihood + analytic gradient for R hyper-parameter restarts in lock step.
+// Replaces jax.value_and_grad(GP.neg_mll) (BOBE/gp.py:385-398, gp_mll :170-178; called from
+// BOBE/optim.py:118,211,309) for the data term; priors are O(d) and stay on the host.
+//
+//   log p = -1/2 y^T K^-1 y - sum log L_ii - n/2 log 2 pi
+//   d log p / d theta = 1/2 sum_ik W_ik dK_ik/d theta,   W = alpha alpha^T - K^-1
+//   dK_ik/d log l_j = G_ik s_ikj,  s_ikj = ((x_ij - x_kj)/l_j)^2,
+//       G = K0 (RBF);  G = kv 5/3 (1 + sqrt5 r) exp(-sqrt5 r), 0 where the 1e-30 clamp is active (Matern-5/2)
+//   dK/d log kv = K0 (the noise-free kernel);  noise is never optimised;  tausq has no kernel gradient.
+#include <cmath>
+
+#include "gemm_nt.cuh"
+#include "kernels.cuh"
+
+namespace bobe {
+
+__global__ void exp_params_kernel(const double* __restrict__ lp, int64_t R, int64_t P, int64_t d, int has_kv,
+                                  double fixed_kv, double* __restrict__ ls, double* __restrict__ kv) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < R * d) {
+        int64_t r = i / d, k = i - r * d;
+        ls[i] = exp(lp[r * P + k]);
+    }
+    if (i < R) kv[i] = has_kv ? exp(lp[i * P + d]) : fixed_kv;
+}
+
+constexpr int GT = 64, GLD = 66;
+
+template <int KIND>
+__global__ void __launch_bounds__(256) mll_grad_tile_kernel(const double* __restrict__ X, int64_t n, int d,
+                                                            const double* __restrict__ ls_all,
+                                                            const double* __restrict__ kv_all,
+                                                            const double* __restrict__ Kinv, int npad,
+                                                            const double* __restrict__ alpha_all, int has_kv,
+                                                            int P, double* __restrict__ partial, int ntiles) {
+    extern __shared__ __align__(16) double sm[];
+    double* sa = sm;                // [d][GLD]
+    double* sb = sa + d * GLD;      // [d][GLD]
+    double* sai = sb + d * GLD;     // [GT] alpha rows
+    double* sak = sai + GT;         // [GT] alpha cols
+    double* wred = sak + GT;        // [8][d+1] per-warp partial sums
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
+    const int64_t z = blockIdx.y;
+    // lower-triangular tile index -> (ti, tj), ti >= tj
+    int x = blockIdx.x;
+    int ti = (int)((sqrt(8.0 * x + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= x) ++ti;
+    while (ti * (ti + 1) / 2 > x) --ti;
+    const int tj = x - ti * (ti + 1) / 2;
+    const int64_t i0 = (int64_t)ti * GT, k0 = (int64_t)tj * GT;
+    const double* ls = ls_all + z * d;
+    const double kv = kv_all[z];
+    const double* alpha = alpha_all + z * npad;
+    const double* Ki = Kinv + z * (int64_t)npad * npad;
+
+    for (int idx = tid; idx < GT * d; idx += 256) {
+        int r = idx / d, k = idx - r * d;
+        sa[k * GLD + r] = (i0 + r < n) ? X[(i0 + r) * d + k] / ls[k] : 0.0;
+        sb[k * GLD + r] = (k0 + r < n) ? X[(k0 + r) * d + k] / ls[k] : 0.0;
+    }
+    if (tid < GT) {
+        sai[tid] = (i0 + tid < n) ? alpha[i0 + tid] : 0.0;
+        sak[tid] = (k0 + tid < n) ? alpha[k0 + tid] : 0.0;
+    }
+    __syncthreads();
+
+    double q[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) q[i][j] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < d; ++k) {
+        double2 a01 = *reinterpret_cast<const double2*>(sa + k * GLD + ty * 4);
+        double2 a23 = *reinterpret_cast<const double2*>(sa + k * GLD + ty * 4 + 2);
+        double2 b01 = *reinterpret_cast<const double2*>(sb + k * GLD + tx * 4);
+        double2 b23 = *reinterpret_cast<const double2*>(sb + k * GLD + tx * 4 + 2);
+        double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double df = a[i] - b[j];
+                q[i][j] = fma(df, df, q[i][j]);
+            }
+    }
+    const double wsym = (ti == tj) ? 1.0 : 2.0;  // off-diagonal tiles stand for both (i,k) and (k,i)
+    double wg[4][4];
+    double gkv = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int64_t row = i0 + ty * 4 + i;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int64_t col = k0 + tx * 4 + j;
+            double w = 0.0, k0v = 0.0, g = 0.0;
+            if (row < n && col < n) {
+                w = wsym * (sai[ty * 4 + i] * sak[tx * 4 + j] - Ki[row * npad + col]);
+                if (KIND == BOBE_KERNEL_RBF) {
+                    k0v = kv * exp(-0.5 * q[i][j]);
+                    g = k0v;
+                } else {
+                    bool clamped = q[i][j] < 1e-30;
+                    double r = sqrt(clamped ? 1e-30 : q[i][j]);
+                    double e = exp(-SQRT5 * r);
+                    k0v = kv * (1.0 + r * (SQRT5 + r * (5.0 / 3.0))) * e;
+                    g = clamped ? 0.0 : kv * (5.0 / 3.0) * (1.0 + SQRT5 * r) * e;
+                }
+            }
+            gkv = fma(w, k0v, gkv);
+            wg[i][j] = w * g;
+        }
+    }
+    const int np1 = d + 1;
+    for (int k = 0; k < d; ++k) {
+        double2 a01 = *reinterpret_cast<const double2*>(sa + k * GLD + ty * 4);
+        double2 a23 = *reinterpret_cast<const double2*>(sa + k * GLD + ty * 4 + 2);
+        double2 b01 = *reinterpret_cast<const double2*>(sb + k * GLD + tx * 4);
+        double2 b23 = *reinterpret_cast<const double2*>(sb + k * GLD + tx * 4 + 2);
+        double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double df = a[i] - b[j];
+                s = fma(wg[i][j], df * df, s);
+            }
+        s = warp_sum(s);
+        if (lane == 0) wred[warp * np1 + k] = s;
+    }
+    gkv = warp_sum(gkv);
+    if (lane == 0) wred[warp * np1 + d] = gkv;
+    __syncthreads();
+    if (tid < np1) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += wred[w * np1 + tid];
+        partial[(z * ntiles + blockIdx.x) * np1 + tid] = s;
+    }
+}
+
+__global__ void mll_finish_kernel(const double* __restrict__ partial, int ntiles, int d, int P, int has_kv, int64_t n,
+                                  const double* __restrict__ logdet, const double* __restrict__ quad,
+                                  const int32_t* __restrict__ info, double* __restrict__ val,
+                                  double* __restrict__ grad) {
+    const int64_t z = blockIdx.x;
+    const int j = threadIdx.x;
+    const int np1 = d + 1;
+    if (j < P) {
+        double g = 0.0;
+        if (j < d || (has_kv && j == d)) {
+            double s = 0.0;
+            for (int t = 0; t < ntiles; ++t) s += partial[(z * ntiles + t) * np1 + j];
+            g = 0.5 * s;
+        }
+        if (info[z]) g = nan("");
+        grad[z * P + j] = g;
+    }
+    if (j == 0) val[z] = -0.5 * quad[z] - logdet[z] - 0.5 * (double)n * 1.8378770664093454835606594728112;
+}
+
+struct MllLayout {
+    int64_t npad, tiles, ntile_pairs;
+    int64_t off_ls, off_kv, off_KB, off_L, off_Lt, off_Linv, off_U, off_Q, off_diag, off_stat, off_z, off_alpha, off_logdet,
+        off_quad, off_partial, total;
+};
+
+static MllLayout mll_layout(int64_t n, int64_t d, int64_t R) {
+    MllLayout l{};
+    l.npad = npad_of(n);
+    l.tiles = (n + GT - 1) / GT;
+    l.ntile_pairs = l.tiles * (l.tiles + 1) / 2;
+    int64_t m2 = l.npad * l.npad, o = 0;
+    auto take = [&](int64_t doubles) {
+        int64_t at = o;
+        o += round_up(doubles, 32);
+        return at;
+    };
+    l.off_ls = take(R * d);
+    l.off_kv = take(R);
+    l.off_KB = take(R * m2);
+    l.off_L = take(R * m2);
+    l.off_Lt = take(R * m2);
+    l.off_Linv = take(R * m2);
+    l.off_U = take(R * m2);
+    l.off_Q = take(R * factor_q_elems(l.npad));
+    l.off_diag = take(R * l.npad);
+    l.off_stat = take(3 * R);
+    l.off_z = take(solve_ws_doubles(l.npad, R));
+    l.off_alpha = take(R * l.npad);
+    l.off_logdet = take(R);
+    l.off_quad = take(R);
+    l.off_partial = take(R * l.ntile_pairs * (d + 1));
+    l.total = o;
+    return l;
+}
+
+}  // namespace bobe
+
+using namespace bobe;
+
+extern "C" int64_t bobe_mll_grad_workspace_bytes(int64_t n, int64_t d, int64_t R) {
+    if (n <= 0 || d <= 0 || R <= 0) return 0;
+    return mll_layout(n, d, R).total * 8 + 256;
+}
+
+extern "C" int32_t bobe_mll_grad_batched(void* stream_, int32_t kind, const double* X, const double* y, int64_t n,
+                                         int64_t d, const double* log_params, int64_t R, int64_t P, int32_t has_kv,
+                                         double fixed_kv, double noise, double* val, double* grad, int32_t* info,
+                                         void* ws, int64_t ws_bytes) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!X || !y || !log_params || !val || !grad || !info || !ws) {
+        set_error("mll_grad: null pointer");
+        return BOBE_E_ARG;
+    }
+    if (n <= 0 || d <= 0 || R <= 0 || P < d + (has_kv ? 1 : 0) || P > 256 || d > 200) {
+        set_error("mll_grad: bad sizes n=%lld d=%lld R=%lld P=%lld", (long long)n, (long long)d, (long long)R,
+                  (long long)P);
+        return BOBE_E_ARG;
+    }
+    MllLayout l = mll_layout(n, d, R);
+    double* w = (double*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    if ((char*)(w + l.total) > (char*)ws + ws_bytes) {
+        set_error("mll_grad: workspace too small (%lld < %lld)", (long long)ws_bytes,
+                  (long long)bobe_mll_grad_workspace_bytes(n, d, R));
+        return BOBE_E_WORKSPACE;
+    }
+    double *ls = w + l.off_ls, *kv = w + l.off_kv;
+    FactorBuffers fb{w + l.off_KB, w + l.off_L, w + l.off_Lt, w + l.off_Linv, w + l.off_U, w + l.off_Q, w + l.off_diag,
+                     w + l.off_stat, (int*)(w + l.off_stat + 2 * R), 0};
+    double *zws = w + l.off_z, *alpha = w + l.off_alpha, *logdet = w + l.off_logdet, *quad = w + l.off_quad,
+           *partial = w + l.off_partial;
+    const int npad = (int)l.npad;
+
+    int64_t tot = R * d > R ? R * d : R;
+    exp_params_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(log_params, R, P, d, has_kv, fixed_kv, ls, kv);
+    if (int32_t rc = check_launch("exp_params_kernel")) return rc;
+
+    KmatArgs ka{};
+    ka.xa = X; ka.xb = X; ka.ls = ls; ka.kv_ptr = kv; ka.out = fb.KB;
+    ka.n1 = n; ka.n2 = n; ka.d = d; ka.ldo = npad; ka.rows_pad = npad; ka.cols_pad = npad;
+    ka.store_rows = npad; ka.store_cols = npad; ka.vec_ok = 1;
+    ka.ls_stride = d; ka.out_stride = (int64_t)npad * npad; ka.noise = noise; ka.add_noise = 1; ka.pad_identity = 1;
+    if (int32_t rc = launch_kmat(stream, kind, ka, (int)R)) return rc;
+    if (int32_t rc = factor_recursive(stream, fb, npad, (int)R)) return rc;
+    SolveArgs sa{kind, X, ls, kv, d, noise};
+    if (int32_t rc = launch_solve_vectors(stream, fb, sa, y, n, npad, (int)R, zws, alpha, logdet, quad, info)) return rc;
+    if (int32_t rc = launch_kinv(stream, fb, npad, (int)R)) return rc;
+
+    int smem = (int)((2 * d * GLD + 2 * GT + 8 * (d + 1)) * sizeof(double));
+    dim3 grid((unsigned)l.ntile_pairs, (unsigned)R);
+    cudaError_t e;
+    if (kind == BOBE_KERNEL_RBF) {
+        e = cudaFuncSetAttribute(mll_grad_tile_kernel<BOBE_KERNEL_RBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess)
+            mll_grad_tile_kernel<BOBE_KERNEL_RBF><<<grid, 256, smem, stream>>>(X, n, (int)d, ls, kv, fb.KB, npad, alpha,
+                                                                             has_kv, (int)P, partial, (int)l.ntile_pairs);
+    } else {
+        e = cudaFuncSetAttribute(mll_grad_tile_kernel<BOBE_KERNEL_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess)
+            mll_grad_tile_kernel<BOBE_KERNEL_MATERN52><<<grid, 256, smem, stream>>>(X, n, (int)d, ls, kv, fb.KB, npad, alpha,
+                                                                                  has_kv, (int)P, partial, (int)l.ntile_pairs);
+    }
+    if (e != cudaSuccess) {
+        set_error("mll_grad attr: %s", cudaGetErrorString(e));
+        return BOBE_E_CUDA;
+    }
+    if (int32_t rc = check_launch("mll_grad_tile_kernel")) return rc;
+    mll_finish_kernel<<<(unsigned)R, 256, 0, stream>>>(partial, (int)l.ntile_pairs, (int)d, (int)P, has_kv, n, logdet,
+                                                      quad, info, val, grad);
+    return check_launch("mll_finish_kernel");
+}

@@ -1,0 +1,180 @@
+"""Tensor-level wrappers over the C-ABI: torch supplies device memory and the stream, nothing else.
+
+Every function takes/returns CUDA float64 tensors and launches on ``torch.cuda.current_stream()``.
+No function here has a CPU path; a CPU tensor raises.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+KIND = {"rbf": _lib.KERNEL_RBF, "matern": _lib.KERNEL_MATERN52}
+
+_ws_cache = {}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    """Grow-only scratch arena per device (the C-ABI never allocates)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _ws_cache[key] = None
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=f"cuda:{key}")
+        _ws_cache[key] = buf
+    return buf
+
+
+def release_workspace():
+    _ws_cache.clear()
+
+
+def _chk(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float64:
+        raise TypeError(f"{name} must be a CUDA float64 tensor (no CPU fallback)")
+    return t.contiguous()
+
+
+def npad(n: int) -> int:
+    return int(lib.bobe_npad(int(n)))
+
+
+def kernel_matrix(kind: str, xa, xb, ls, kv: float, noise: float, add_noise: bool) -> torch.Tensor:
+    """K(xa, xb) [+ noise I] -- BOBE/gp.py:124-168."""
+    xa, xb, ls = _chk(xa, "xa"), _chk(xb, "xb"), _chk(ls, "ls")
+    n1, d = xa.shape
+    n2 = xb.shape[0]
+    out = torch.empty((n1, n2), dtype=torch.float64, device=xa.device)
+    with torch.cuda.device(xa.device):
+        check(lib.bobe_kernel_matrix(_stream(), KIND[kind], xa.data_ptr(), n1, xb.data_ptr(), n2, d, ls.data_ptr(),
+                                     float(kv), float(noise), int(bool(add_noise)), out.data_ptr(), n2),
+              "bobe_kernel_matrix")
+    return out
+
+
+def factorize(kind: str, X, y, ls, kv, noise: float, want_L: bool = True):
+    """Batched K -> (L, Linv, alpha, logdet, quad, info).  ls (B,d), kv (B,).  BOBE/gp.py:258-260,544-550."""
+    X, y, ls, kv = _chk(X, "X"), _chk(y, "y").reshape(-1), _chk(ls, "ls"), _chk(kv, "kv")
+    if ls.dim() == 1:
+        ls = ls[None, :]
+    kv = kv.reshape(-1)
+    B = ls.shape[0]
+    n, d = X.shape
+    p = npad(n)
+    dev = X.device
+    L = torch.empty((B, p, p), dtype=torch.float64, device=dev) if want_L else None
+    Linv = torch.empty((B, p, p), dtype=torch.float64, device=dev)
+    alpha = torch.empty((B, p), dtype=torch.float64, device=dev)
+    logdet = torch.empty(B, dtype=torch.float64, device=dev)
+    quad = torch.empty(B, dtype=torch.float64, device=dev)
+    info = torch.empty(B, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = lib.bobe_factorize_workspace_bytes(n, B)
+        ws = _workspace(nbytes, dev)
+        check(lib.bobe_factorize(_stream(), KIND[kind], X.data_ptr(), y.data_ptr(), n, d, ls.data_ptr(), kv.data_ptr(),
+                                 float(noise), B, L.data_ptr() if want_L else None, Linv.data_ptr(), alpha.data_ptr(),
+                                 logdet.data_ptr(), quad.data_ptr(), info.data_ptr(), ws.data_ptr(), ws.numel()),
+              "bobe_factorize")
+    return L, Linv, alpha, logdet, quad, info
+
+
+def mll_grad_batched(kind: str, X, y, log_params, has_kv: bool, fixed_kv: float, noise: float,
+                     max_batch: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """log p(y | theta_r) and d/d theta for R restarts -- BOBE/gp.py:385-398 via BOBE/optim.py:309."""
+    X, y, lp = _chk(X, "X"), _chk(y, "y").reshape(-1), _chk(log_params, "log_params")
+    if lp.dim() == 1:
+        lp = lp[None, :]
+    R, P = lp.shape
+    n, d = X.shape
+    dev = X.device
+    val = torch.empty(R, dtype=torch.float64, device=dev)
+    grad = torch.empty((R, P), dtype=torch.float64, device=dev)
+    info = torch.empty(R, dtype=torch.int32, device=dev)
+    if max_batch is None:  # keep the workspace under ~1/3 of device memory
+        per = lib.bobe_mll_grad_workspace_bytes(n, d, 1)
+        free = torch.cuda.get_device_properties(dev).total_memory // 3
+        max_batch = max(1, int(free // max(per, 1)))
+    with torch.cuda.device(dev):
+        for r0 in range(0, R, max_batch):
+            r1 = min(R, r0 + max_batch)
+            nbytes = lib.bobe_mll_grad_workspace_bytes(n, d, r1 - r0)
+            ws = _workspace(nbytes, dev)
+            check(lib.bobe_mll_grad_batched(_stream(), KIND[kind], X.data_ptr(), y.data_ptr(), n, d,
+                                            lp[r0:r1].data_ptr(), r1 - r0, P, int(bool(has_kv)), float(fixed_kv),
+                                            float(noise), val[r0:r1].data_ptr(), grad[r0:r1].data_ptr(),
+                                            info[r0:r1].data_ptr(), ws.data_ptr(), ws.numel()),
+                  "bobe_mll_grad_batched")
+    return val, grad, info
+
+
+def predict(kind: str, X, ls, kv: float, noise: float, Linv, alpha, Xq, y_mean: float, y_std: float,
+            want_mean: bool = True, want_var: bool = True, standardised: bool = False):
+    """Posterior mean / variance at Xq (M, d) -- BOBE/gp.py:450-493."""
+    X, ls, Xq = _chk(X, "X"), _chk(ls, "ls"), _chk(Xq, "Xq")
+    n, d = X.shape
+    M = Xq.shape[0]
+    dev = X.device
+    mode = (_lib.PREDICT_MEAN if want_mean else 0) | (_lib.PREDICT_VAR if want_var else 0) | \
+           (_lib.PREDICT_STANDARDISED if standardised else 0)
+    mean = torch.empty(M, dtype=torch.float64, device=dev) if want_mean else None
+    var = torch.empty(M, dtype=torch.float64, device=dev) if want_var else None
+    with torch.cuda.device(dev):
+        nbytes = lib.bobe_predict_workspace_bytes(n, d, M, mode)
+        ws = _workspace(nbytes, dev)
+        check(lib.bobe_predict(_stream(), KIND[kind], X.data_ptr(), n, d, ls.data_ptr(), float(kv), float(noise),
+                               _chk(Linv, "Linv").data_ptr() if want_var else None,
+                               _chk(alpha, "alpha").data_ptr() if want_mean else None, Xq.data_ptr(), M, float(y_mean),
+                               float(y_std), mode, mean.data_ptr() if want_mean else None,
+                               var.data_ptr() if want_var else None, ws.data_ptr(), ws.numel()), "bobe_predict")
+    return mean, var
+
+
+def fantasy_var(kind: str, X, ls, kv: float, noise: float, Linv, y_std: float, Xmc, Xcand=None, reduce: str = "none"):
+    """Fantasy variance at the MC points for each candidate -- BOBE/gp.py:552-576, acquisition.py:438-465."""
+    X, ls, Xmc, Linv = _chk(X, "X"), _chk(ls, "ls"), _chk(Xmc, "Xmc"), _chk(Linv, "Linv")
+    n, d = X.shape
+    n_mc = Xmc.shape[0]
+    if Xcand is not None:
+        Xcand = _chk(Xcand, "Xcand")
+        C = Xcand.shape[0]
+    else:
+        C = n_mc
+    red = {"none": _lib.REDUCE_NONE, "mean": _lib.REDUCE_MEAN, "mean_sqrt": _lib.REDUCE_MEAN_SQRT}[reduce]
+    dev = X.device
+    out = torch.empty((C, n_mc) if red == _lib.REDUCE_NONE else (C,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = lib.bobe_fantasy_var_workspace_bytes(n, d, n_mc, C if Xcand is not None else 0)
+        ws = _workspace(nbytes, dev)
+        check(lib.bobe_fantasy_var(_stream(), KIND[kind], X.data_ptr(), n, d, ls.data_ptr(), float(kv), float(noise),
+                                   Linv.data_ptr(), float(y_std), Xmc.data_ptr(), n_mc,
+                                   Xcand.data_ptr() if Xcand is not None else None, C, red, out.data_ptr(),
+                                   ws.data_ptr(), ws.numel()), "bobe_fantasy_var")
+    return out
+
+
+def chol_append(L, k, k_self: float) -> torch.Tensor:
+    """fast_update_cholesky -- BOBE/gp.py:181-197."""
+    L, k = _chk(L, "L"), _chk(k, "k").reshape(-1)
+    n = L.shape[0]
+    out = torch.empty((n + 1, n + 1), dtype=torch.float64, device=L.device)
+    with torch.cuda.device(L.device):
+        check(lib.bobe_chol_append(_stream(), L.data_ptr(), n, L.shape[1] if n else 1, k.data_ptr(), float(k_self),
+                                   out.data_ptr(), n + 1), "bobe_chol_append")
+    return out
+
+
+def acq_ei(which: str, mean, var, best_y: float, zeta: float) -> torch.Tensor:
+    """Negated EI / LogEI from standardised (mean, var) -- BOBE/acquisition.py:226-253,318-330."""
+    mean, var = _chk(mean, "mean").reshape(-1), _chk(var, "var").reshape(-1)
+    out = torch.empty_like(mean)
+    with torch.cuda.device(mean.device):
+        check(lib.bobe_acq_ei(_stream(), _lib.ACQ_EI if which == "ei" else _lib.ACQ_LOGEI, mean.data_ptr(),
+                              var.data_ptr(), mean.numel(), float(best_y), float(zeta), out.data_ptr()), "bobe_acq_ei")
+    return out
