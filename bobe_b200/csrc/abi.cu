@@ -471,3 +471,14 @@ extern "C" int32_t bobe_acq_ei(void* stream, int32_t which, const double* mean, 
     acq_ei_kernel<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(which, mean, var, M, best_y, zeta, out);
     return check_launch("acq_ei_kernel");
 }
+
+extern "C" int32_t bobe_bench_trmm_sumsq(void* stream, const double* Linv, int64_t n, const double* kstar,
+                                         int64_t rows_pad, double kk, double* var_out) {
+    if (!Linv || !kstar || !var_out || n <= 0 || rows_pad <= 0) {
+        set_error("bench_trmm_sumsq: bad arguments");
+        return BOBE_E_ARG;
+    }
+    const int64_t npad = npad_of(n);
+    return launch_trmm_sumsq((cudaStream_t)stream, Linv, (int)npad, kstar, npad, rows_pad, 0, rows_pad, kk, 1.0, 0,
+                             var_out);
+}

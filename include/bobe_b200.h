@@ -108,6 +108,13 @@ int32_t bobe_chol_append(void* stream, const double* L, int64_t n, int64_t ldl, 
 int32_t bobe_acq_ei(void* stream, int32_t which, const double* mean, const double* var, int64_t M, double best_y,
                     double zeta, double* out);
 
+/* ---- measurement hook (bench.py only; not part of the drop-in surface) -------------------------------------
+ * Launches exactly the dominant kernel of bobe_predict (the fused triangular multiply + column sum of squares)
+ * once over `rows_pad` queries whose K* panel (rows_pad, npad) is already in `kstar`, so that bench.py can time
+ * that kernel alone with CUDA events for the roofline figure.  rows_pad must be a multiple of 128. */
+int32_t bobe_bench_trmm_sumsq(void* stream, const double* Linv, int64_t n, const double* kstar, int64_t rows_pad,
+                              double kk, double* var_out);
+
 #ifdef __cplusplus
 }
 #endif

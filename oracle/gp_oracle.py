@@ -28,6 +28,7 @@ SQRT2 = math.sqrt(2.0)  # BOBE/gp.py:18
 SQRT3 = math.sqrt(3.0)  # BOBE/gp.py:19
 SQRT5 = math.sqrt(5.0)  # BOBE/gp.py:20
 LOG_2PI = math.log(2.0 * math.pi)
+DIST_SQ_TEMP_ELEMS = 2**18  # size cap of the (rows, n2, d) temporary in dist_sq; arithmetic per entry unchanged
 
 
 # ----------------------------------------------------------------------------------------------
@@ -39,7 +40,7 @@ def dist_sq(x, y):
     y = np.asarray(y, dtype=np.float64)
     out = np.empty((x.shape[0], y.shape[0]))
     # row-chunked only to bound the (n1,n2,d) temporary; the arithmetic per entry is unchanged
-    step = max(1, int(2**24 // max(1, y.shape[0] * x.shape[1])))
+    step = max(1, int(DIST_SQ_TEMP_ELEMS // max(1, y.shape[0] * x.shape[1])))
     for s in range(0, x.shape[0], step):
         diff = x[s:s + step, None, :] - y[None, :, :]
         out[s:s + step] = np.sum(np.square(diff), axis=-1)

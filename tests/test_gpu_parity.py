@@ -1,0 +1,258 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle and the committed golden vectors.
+
+Tolerances (BASELINE.json north_star, made well-defined by SURVEY.md 8c): |d| <= tol * max(|ref|, scale) with
+tol = 1e-9 for mean and log-ML (scale: y_std resp. n), 1e-7 for variance and gradients (scale: y_std^2 resp.
+max|grad|).  Integer outputs (info flags, NaN patterns) must match exactly.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR, mixed_err
+from oracle import gp_oracle as O
+from oracle.gen_golden import CASES, make_case
+
+pytestmark = pytest.mark.gpu
+
+TOL_MEAN, TOL_MLL, TOL_VAR, TOL_GRAD = 1e-9, 1e-9, 1e-7, 1e-7
+
+
+def T(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")
+
+
+def make_gp(ref, **kw):
+    from bobe_b200 import GP
+    return GP(ref.train_x, ref.train_y * ref.y_std + ref.y_mean, noise=ref.noise, kernel=ref.kernel_name,
+              lengthscales=ref.lengthscales, kernel_variance=ref.kernel_variance, **kw)
+
+
+def check_grad(g, gref, what=""):
+    scale = max(float(np.max(np.abs(gref))), 1.0)
+    err = float(np.max(np.abs(g - gref))) / scale
+    assert err < TOL_GRAD, (what, err)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_golden_parity(name):
+    """Every BASELINE shape: CUDA results against the golden vectors the oracle emitted."""
+    from bobe_b200 import EI, LogEI
+    gold = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    ref, X, y, Xq, x0, mc, cand = make_case(name)
+    n = X.shape[0]
+    gp = make_gp(ref)
+    assert gp.y_mean == ref.y_mean and gp.y_std == ref.y_std
+    mean, var = gp.predict_mean_var_batched(Xq)
+    assert mixed_err(mean, gold["mean"], ref.y_std) < TOL_MEAN
+    assert mixed_err(var, gold["var"], ref.y_std ** 2) < TOL_VAR
+    assert mixed_err(gp.predict_mean_batched(Xq), gold["mean"], ref.y_std) < TOL_MEAN
+    assert mixed_err(gp.predict_var_batched(Xq), gold["var"], ref.y_std ** 2) < TOL_VAR
+    ms, vs = gp.predict_batched(Xq)
+    assert vs.shape == (Xq.shape[0], 1)
+    assert mixed_err(ms, gold["mean_std"], 1.0) < TOL_MEAN and mixed_err(vs.ravel(), gold["var_std"], 1.0) < TOL_VAR
+    v, g = gp.neg_mll_and_grad_batched(x0)
+    for r in range(x0.shape[0]):
+        assert abs(v[r] - gold["neg_mll"][r]) <= TOL_MLL * max(abs(gold["neg_mll"][r]), n), (r, v[r], gold["neg_mll"][r])
+        check_grad(g[r], gold["neg_mll_grad"][r], f"restart {r}")
+    assert mixed_err(gp.fantasy_var(cand, mc), gold["fantasy"], ref.y_std ** 2) < TOL_VAR
+    assert mixed_err(gp.fantasy_acquisition(mc, None, std=False), gold["wipv_self"], ref.y_std ** 2) < TOL_VAR
+    assert mixed_err(gp.fantasy_acquisition(mc, None, std=True), gold["wipstd_self"], ref.y_std) < TOL_VAR
+    best = float(ref.train_y.max())
+    ei = EI().fun_batched(Xq, gp, best, 0.01)
+    lei = LogEI().fun_batched(Xq, gp, best, 0.01)
+    # EI multiplies the 1e-7-tolerance variance: same tolerance, scale = the largest EI in the batch
+    assert mixed_err(ei, gold["ei"], max(float(np.max(np.abs(gold["ei"]))), 1e-12)) < 1e-6
+    assert mixed_err(lei, gold["logei"], 1.0) < 1e-6
+    assert abs(float(gp._logdet.item()) - float(gold["logdet"])) <= TOL_MLL * n
+    assert np.linalg.norm(gp.alphas.ravel() - gold["alpha"]) <= 1e-6 * np.linalg.norm(gold["alpha"])
+
+
+def test_truth_gap_report():
+    """Parity residuals beside the oracle-vs-extended-precision gap at the worst-conditioned BASELINE shape
+    (SURVEY.md fact 5): the CUDA path must sit within a small multiple of the oracle's own rounding noise."""
+    gold = np.load(os.path.join(GOLDEN_DIR, "A_banana_rbf_n100_d2.npz"))
+    ref, X, y, Xq, x0, mc, cand = make_case("A_banana_rbf_n100_d2")
+    gp = make_gp(ref)
+    ms, vs = gp.predict_batched(Xq[:32])
+    gap_oracle = mixed_err(gold["mean_std"][:32], gold["truth_mean_std"], 1.0)
+    gap_cuda = mixed_err(ms, gold["truth_mean_std"], 1.0)
+    v, g = gp.neg_mll_and_grad_batched(x0[:1])
+    pl, pg = ref.log_prior_and_grad(x0[0])
+    mll_cuda, mll_oracle, mll_truth = -v[0] - pl, -gold["neg_mll"][0] - pl, float(gold["truth_mll"])
+    gt = gold["truth_mll_grad"]
+    gg_cuda = np.max(np.abs((-g[0] - pg) - gt)) / np.max(np.abs(gt))
+    gg_oracle = np.max(np.abs((-gold["neg_mll_grad"][0] - pg) - gt)) / np.max(np.abs(gt))
+    print(f"\n[truth gap, n=100 d=2 RBF cond~3e9] mean: oracle {gap_oracle:.1e} cuda {gap_cuda:.1e} | "
+          f"mll abs: oracle {abs(mll_oracle - mll_truth):.1e} cuda {abs(mll_cuda - mll_truth):.1e} | "
+          f"grad rel: oracle {gg_oracle:.1e} cuda {gg_cuda:.1e}")
+    assert gap_cuda < TOL_MEAN and abs(mll_cuda - mll_truth) < TOL_MLL * 322 and gg_cuda < TOL_GRAD
+
+
+@pytest.mark.parametrize("kernel", ["rbf", "matern"])
+@pytest.mark.parametrize("n,d", [(1, 1), (2, 3), (63, 2), (64, 5), (65, 4), (129, 1), (200, 27), (321, 7)])
+def test_edge_shapes(kernel, n, d):
+    """Padding boundaries (npad multiples of 64), d = 1, d > 16, tiny n, ragged query counts."""
+    from bobe_b200 import ops
+    rng = np.random.default_rng(n * 31 + d)
+    X = rng.uniform(0, 1, (n, d))
+    y = np.sin(3 * X.sum(1, keepdims=True)) + 0.1 * rng.normal(size=(n, 1))
+    ls = rng.uniform(0.4, 1.2, d)
+    ref = O.OracleGP(X, y, kernel=kernel, noise=1e-4, lengthscales=ls, kernel_variance=1.7)
+    gp = make_gp(ref)
+    assert gp.cholesky.shape == (n, n) and np.allclose(np.triu(gp.cholesky, 1), 0)
+    assert mixed_err(gp.cholesky, ref.cholesky, float(np.abs(ref.cholesky).max())) < 1e-9
+    for M in (1, 5, 127, 128, 129):
+        Xq = rng.uniform(0, 1, (M, d))
+        mean, var = gp.predict_mean_var_batched(Xq)
+        assert mean.shape == (M,) and var.shape == (M,)
+        assert mixed_err(mean, ref.predict_mean_batched(Xq), ref.y_std) < TOL_MEAN
+        assert mixed_err(var, ref.predict_var_batched(Xq), ref.y_std ** 2) < TOL_VAR
+    K = ops.kernel_matrix(ref.kernel_name, T(X), T(X[: max(1, n // 2)]), T(ls), 1.7, 1e-4, False).cpu().numpy()
+    assert mixed_err(K, ref.kernel(X, X[: max(1, n // 2)], ls, 1.7, 1e-4, False), 1e-300) < 1e-13
+    x0 = O.synthetic_restarts(ref, 3, seed=n)
+    x0[1:] = np.clip(x0[1:], np.log(0.05), np.log(50.0))
+    v, g = gp.neg_mll_and_grad_batched(x0)
+    for r in range(3):
+        vr, gr = ref.neg_mll_and_grad(x0[r])
+        if np.isfinite(vr):
+            assert abs(v[r] - vr) <= TOL_MLL * max(abs(vr), n)
+            check_grad(g[r], gr)
+        else:
+            assert np.isnan(v[r])
+
+
+def test_single_point_methods_and_shapes():
+    """Shapes/values of the *_single methods (reference tests/test_gp.py:92-141)."""
+    ref, X, y, Xq, x0, mc, cand = make_case("M_matern_n300_d3")
+    gp = make_gp(ref)
+    x = Xq[0]
+    m, v = gp.predict_mean_single(x), gp.predict_var_single(x)
+    assert np.shape(m) == () and np.shape(v) == () and v > 0
+    assert abs(m - ref.predict_mean_single(x)) <= TOL_MEAN * max(abs(m), ref.y_std)
+    assert abs(v - ref.predict_var_single(x)) <= TOL_VAR * max(abs(v), ref.y_std ** 2)
+    ms, vs = gp.predict_single(x)
+    mr, vr = ref.predict_single(x)
+    assert np.shape(ms) == () and vs.shape == (1,)
+    assert abs(ms - mr) <= TOL_MEAN and abs(vs[0] - vr[0]) <= TOL_VAR
+    fv = gp.fantasy_var(cand[0], mc)
+    ktm = ref.kernel(ref.train_x, mc, ref.lengthscales, ref.kernel_variance, ref.noise, False)
+    assert fv.shape == (mc.shape[0],)
+    assert mixed_err(fv, ref.fantasy_var(cand[0], mc, ktm), ref.y_std ** 2) < TOL_VAR  # literal BOBE/gp.py:552-576
+
+
+def test_non_pd_restart_is_nan_for_that_restart_only():
+    """A negative 'noise' makes K indefinite: the reference silently yields NaN for that restart."""
+    from bobe_b200 import ops
+    X, y = O.synthetic_training_set(150, 3)
+    ys = O.standardise(y)[0]
+    lp = np.log(np.array([[0.5, 0.5, 0.5, 1.0], [0.5, 0.5, 0.5, 1.0]]))
+    val_bad, grad_bad, info_bad = ops.mll_grad_batched("rbf", T(X), T(ys), T(lp), True, 1.0, -0.5)
+    assert torch.isnan(val_bad).all() and torch.isnan(grad_bad).all() and (info_bad == 1).all()
+    # mixed batch: restart 1 has an absurd lengthscale that makes K numerically singular without noise
+    lp2 = np.log(np.array([[0.5, 0.5, 0.5, 1.0], [50.0, 50.0, 50.0, 1e8]]))
+    val, grad, info = ops.mll_grad_batched("rbf", T(X), T(ys), T(lp2), True, 1.0, 0.0)
+    ref = O.OracleGP(X, y, kernel="rbf", noise=0.0)
+    v0, g0 = ref.neg_mll_and_grad(lp2[0])
+    pl, pg = ref.log_prior_and_grad(lp2[0])
+    assert info[0].item() == 0 and abs(val[0].item() - (-v0 - pl)) <= TOL_MLL * max(abs(v0), 150)
+    assert info[1].item() == 1 and torch.isnan(val[1]) and torch.isnan(grad[1]).all()
+    # GP state with a non-PD kernel: all-NaN cholesky, NaN mean, variance floored where the reference floors it
+    from bobe_b200 import GP
+    gp = GP(X, y, kernel="rbf", noise=-0.5, lengthscales=np.full(3, 0.5))
+    assert np.isnan(gp.cholesky).all()
+    ms, vs = gp.predict_batched(X[:4])
+    assert np.isnan(ms).all() and np.all(vs == 1e-12)  # BOBE/gp.py:487-488
+    assert np.isnan(gp.predict_var_batched(X[:4])).all()  # clip propagates NaN, BOBE/gp.py:465
+
+
+def test_variance_floor_and_interpolation_at_training_points():
+    ref, X, y, Xq, x0, mc, cand = make_case("B_rbf_n500_d4")
+    gp = make_gp(ref)
+    var = gp.predict_var_batched(X[:200])
+    assert np.all(var >= 1e-12 * ref.y_std ** 2 * (1 - 1e-12)) and np.all(var < 1e-3)
+    ms, _ = gp.predict_batched(X[:200])
+    assert np.max(np.abs(ms - (ref.train_y.ravel()[:200] - ref.noise * gp.alphas.ravel()[:200]))) < 1e-8
+
+
+def test_headline_shape_properties():
+    """Size-independent properties at BASELINE's full headline size (n=2000, d=16, M=1e5 per call):
+    chunk-consistency (bitwise), tensor-in/tensor-out, floor, and agreement with the oracle on a sub-sample."""
+    ref, X, y, _, _, _, _ = make_case("H_matern_n2000_d16")
+    gp = make_gp(ref)
+    M = 100_000
+    Xq = T(np.random.default_rng(11).uniform(0, 1, (M, 16)))
+    mean, var = gp.predict_mean_var_batched(Xq)
+    assert mean.is_cuda and var.is_cuda and mean.shape == (M,)
+    assert torch.isfinite(mean).all() and (var > 0).all() and (var <= (1 + 1e-8) * ref.y_std ** 2 * 1.0000001).all()
+    # any split of the query set gives bitwise identical results (no cross-query coupling, deterministic reductions)
+    m1, v1 = gp.predict_mean_var_batched(Xq[:33_333])
+    m2, v2 = gp.predict_mean_var_batched(Xq[33_333:])
+    assert torch.equal(torch.cat([m1, m2]), mean) and torch.equal(torch.cat([v1, v2]), var)
+    mean_b, var_b = gp.predict_mean_var_batched(Xq)
+    assert torch.equal(mean_b, mean) and torch.equal(var_b, var)  # run-to-run determinism
+    idx = np.random.default_rng(12).choice(M, 200, replace=False)
+    xs = Xq[idx].cpu().numpy()
+    assert mixed_err(mean[idx].cpu().numpy(), ref.predict_mean_batched(xs), ref.y_std) < TOL_MEAN
+    assert mixed_err(var[idx].cpu().numpy(), ref.predict_var_batched(xs), ref.y_std ** 2) < TOL_VAR
+    # linearity of the mean in y: GP(y1 + y2) standardised means add up after un-standardising
+    from bobe_b200 import GP
+    y2 = np.cos(X.sum(1, keepdims=True))
+    gpa = GP(X, y2, kernel="matern", lengthscales=np.ones(16))
+    gpb = GP(X, y + y2, kernel="matern", lengthscales=np.ones(16))
+    q = Xq[:500]
+    lhs = gpb.predict_mean_batched(q)
+    rhs = gp.predict_mean_batched(q) + gpa.predict_mean_batched(q)
+    assert float((lhs - rhs).abs().max()) < 1e-7 * max(1.0, float(lhs.abs().max()))
+
+
+def test_fantasy_variance_property_and_large_candidate_set():
+    """fantasy_var(x) equals predict_var of a GP that really contains x (any y value) -- at n = 500."""
+    from bobe_b200 import GP
+    ref, X, y, Xq, x0, mc, cand = make_case("B_rbf_n500_d6")
+    gp = make_gp(ref)
+    xn = cand[0]
+    fv = gp.fantasy_var(xn, mc)
+    gp2 = GP(np.vstack([X, xn]), np.vstack([y, [[float(y.mean())]]]), kernel="rbf", lengthscales=ref.lengthscales)
+    raw = gp2.predict_var_batched(mc) / gp2.y_std ** 2 * ref.y_std ** 2
+    assert mixed_err(fv, raw, ref.y_std ** 2) < 1e-6
+    # 2000 candidates x 700 MC points through the chunked path, against the oracle's shared-V algebra
+    rng = np.random.default_rng(5)
+    C, mcb = rng.uniform(0, 1, (2000, 6)), rng.uniform(0, 1, (700, 6))
+    out = gp.fantasy_acquisition(mcb, C, std=False)
+    assert mixed_err(out[:64], O.wipv_values(ref, C[:64], mcb), ref.y_std ** 2) < TOL_VAR
+    out_s = gp.fantasy_acquisition(mcb, C[:64], std=True)
+    assert mixed_err(out_s, O.wipv_values(ref, C[:64], mcb, std=True), ref.y_std) < TOL_VAR
+
+
+def test_chol_append_and_kernel_functions():
+    from bobe_b200 import rbf_kernel, matern_kernel, fast_update_cholesky, kernel_diag
+    ref, X, y, Xq, x0, mc, cand = make_case("M_matern_n300_d3")
+    for n in (0, 1, 31, 32, 33, 300):
+        L = ref.cholesky[:n, :n]
+        k = ref._k12(cand[0]).ravel()[:n]
+        got = fast_update_cholesky(L, k, ref.kernel_variance + ref.noise)
+        want = O.fast_update_cholesky(L, k, ref.kernel_variance + ref.noise)
+        assert got.shape == (n + 1, n + 1) and mixed_err(got, want, 1.0) < 1e-10
+    nanrow = fast_update_cholesky(ref.cholesky, ref._k12(X[0]).ravel() * 1.001, ref.kernel_variance)
+    assert np.isnan(nanrow[-1, -1])  # negative pivot -> NaN, like jnp.sqrt (BOBE/gp.py:187)
+    for fn, fo in ((rbf_kernel, O.rbf_kernel), (matern_kernel, O.matern_kernel)):
+        K = fn(X[:70], X[:70], ref.lengthscales, 2.0, 1e-3, include_noise=True)
+        assert mixed_err(K, fo(X[:70], X[:70], ref.lengthscales, 2.0, 1e-3, True), 1e-300) < 1e-13
+        Kt = fn(T(X[:70]), T(Xq[:33]), ref.lengthscales, 2.0, 1e-3, include_noise=False)
+        assert Kt.is_cuda and mixed_err(Kt.cpu().numpy(), fo(X[:70], Xq[:33], ref.lengthscales, 2.0, 1e-3, False), 1e-300) < 1e-13
+    assert np.array_equal(kernel_diag(X[:5], 2.0, 0.5), np.full(5, 2.5))
+
+
+def test_acq_ei_tails():
+    """LogEI branches: u > -1, -1e6 < u <= -1, u <= -1e6 (BOBE/acquisition.py:44-75) and the variance clamps."""
+    from bobe_b200 import ops
+    mu = np.array([0.5, 0.0, -0.2, -3.0, -40.0, -1.0, -1.0, 0.3])
+    var = np.array([0.04, 1.0, 0.01, 0.01, 1e-4, 1e-16, 1e-30, 0.0])
+    for which, fo in (("ei", O.ei_values), ("logei", O.logei_values)):
+        got = ops.acq_ei(which, T(mu), T(var), 0.1, 0.01).cpu().numpy()
+        want = fo(mu, var, 0.1, 0.01)
+        assert np.all(np.isfinite(got) == np.isfinite(want))
+        fin = np.isfinite(want)
+        assert mixed_err(got[fin], want[fin], 1e-300) < 1e-10, (which, got, want)

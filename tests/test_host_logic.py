@@ -1,0 +1,228 @@
+"""CPU-only tests of the host side: GP bookkeeping (no arithmetic), priors, optimisers, the C-ABI surface."""
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+import bobe_b200
+from bobe_b200 import GP, priors, optim
+from oracle import gp_oracle as O
+
+
+def toy(n=20, d=3, seed=42):
+    rng = np.random.RandomState(seed)
+    X = rng.uniform(0, 1, size=(n, d))
+    return X, -np.sum((X - 0.5) ** 2, axis=1).reshape(-1, 1)
+
+
+def test_abi_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "bobe_b200.h")).read()
+    declared = set(re.findall(r"\b(bobe_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 14
+    from bobe_b200 import _lib
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(_lib.lib, name)
+    assert _lib.lib.bobe_abi_version() == 1
+    assert _lib.lib.bobe_npad(1) == 64 and _lib.lib.bobe_npad(64) == 64 and _lib.lib.bobe_npad(2000) == 2048
+    # workspace queries are host-only arithmetic and must be monotone in the batch
+    w1 = _lib.lib.bobe_mll_grad_workspace_bytes(2000, 16, 1)
+    w8 = _lib.lib.bobe_mll_grad_workspace_bytes(2000, 16, 8)
+    assert 0 < w1 < w8 < 9 * w1
+    assert _lib.lib.bobe_predict_workspace_bytes(2000, 16, 10**6, 3) == 148 * 128 * 2048 * 8 + 512
+
+
+def test_abi_argument_errors_without_a_gpu():
+    from bobe_b200._lib import lib
+    rc = lib.bobe_kernel_matrix(None, 0, None, 4, None, 4, 2, None, 1.0, 0.0, 0, None, 4)
+    assert rc == -1 and b"bad arguments" in lib.bobe_last_error_string()
+    rc = lib.bobe_predict(None, 0, None, 10, 2, None, 1.0, 0.0, None, None, None, 5, 0.0, 1.0, 3, None, None, None, 0)
+    assert rc == -1
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    X, y = toy()
+    gp = GP(X, y)  # construction is host bookkeeping only
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gp.predict_mean_batched(X[:2])
+    with pytest.raises(TypeError, match="CUDA float64"):
+        bobe_b200.ops.kernel_matrix("rbf", torch.zeros(2, 2, dtype=torch.float64), torch.zeros(2, 2, dtype=torch.float64),
+                                    torch.ones(2, dtype=torch.float64), 1.0, 0.0, False)
+
+
+def test_gp_setup_matches_reference_conventions():
+    X, y = toy(20, 3)
+    gp = GP(X, y, noise=1e-6, kernel="rbf", lengthscale_bounds=[0.01, 10], kernel_variance_bounds=[1e-4, 1e4])
+    ref = O.OracleGP(X, y, noise=1e-6, kernel="rbf", lengthscale_bounds=[0.01, 10], kernel_variance_bounds=[1e-4, 1e4])
+    assert gp.ndim == 3 and gp.npoints == 20 and gp.kernel_name == "rbf"
+    assert gp.y_mean == ref.y_mean and gp.y_std == ref.y_std
+    assert np.array_equal(gp.train_y, ref.train_y) and gp.train_y.shape == (20, 1)
+    assert np.array_equal(gp.hyperparam_bounds, ref.hyperparam_bounds) and gp.hyperparam_bounds.shape == (2, 4)
+    assert gp.param_names == ["x_0", "x_1", "x_2"] and gp.num_hyperparams == 4
+    assert GP(X, y, kernel="anything-else").kernel_name == "matern"  # BOBE/gp.py:251
+    assert np.array_equal(gp.get_hyperparams(), np.array([1, 1, 1, 1.0]))
+    assert gp.hyperparams_dict()["kernel_variance"] == "1.0000"
+    with pytest.raises(ValueError):
+        GP(X, y[:5])
+    with pytest.raises(ValueError):
+        GP(X.ravel(), y.ravel()[: X.size])
+    g1 = GP(X, y.ravel())  # 1-D y is reshaped (BOBE/gp.py:288-289)
+    assert g1.train_y.shape == (20, 1)
+    gz = GP(X, np.ones((20, 1)))
+    assert gz.y_std == 1.0  # zero variance -> 1 (BOBE/gp.py:300-302)
+
+
+@pytest.mark.parametrize("prior", [None, "DSLP", "SAAS"])
+@pytest.mark.parametrize("fixed", [False, True])
+def test_parameter_layout_and_prior_gradients(prior, fixed):
+    X, y = toy(15, 4)
+    kw = dict(lengthscale_prior=prior)
+    if fixed:
+        kw.update(kernel_variance_prior="fixed", kernel_variance=2.0)
+    gp = GP(X, y, **kw)
+    ref = O.OracleGP(X, y, **kw)
+    P = 4 + (0 if fixed else 1) + (1 if prior == "SAAS" else 0)
+    assert gp.num_hyperparams == P == ref.num_hyperparams
+    lp = np.random.default_rng(0).uniform(-1, 1, P)
+    ls, kv, tausq = gp._parse_hyperparams(lp)
+    ls_r, kv_r, t_r = ref._parse_hyperparams(lp)
+    assert np.array_equal(ls, ls_r) and kv == kv_r and tausq == t_r
+    val = gp.prior_func(ls, kv, tausq)
+    g = gp._prior_grad(ls, kv, tausq)
+    val_r, g_r = ref.log_prior_and_grad(lp)
+    assert math.isclose(val, val_r, rel_tol=1e-13, abs_tol=1e-13) and np.allclose(g, g_r, rtol=1e-13, atol=1e-14)
+    h = 1e-6
+    for j in range(P):
+        e = np.zeros(P)
+        e[j] = h
+        fd = (gp.prior_func(*gp._parse_hyperparams(lp + e)) - gp.prior_func(*gp._parse_hyperparams(lp - e))) / (2 * h)
+        assert abs(fd - g[j]) < 1e-6 * max(1.0, abs(g[j]))
+
+
+def test_prior_registry():
+    assert isinstance(priors.make_distribution({"name": "LogNormal", "loc": 0.0, "scale": 1.0}), priors.LogNormal)
+    with pytest.raises(ValueError, match="not found"):
+        priors.make_distribution({"name": "NoSuchDist"})
+    for dist, z in ((priors.Normal(0.3, 2.0), 1.3), (priors.Gamma(2.0, 3.0), 0.7), (priors.HalfCauchy(0.5), 0.2)):
+        h = 1e-6
+        fd = (dist.log_prob(z * math.exp(h)) - dist.log_prob(z * math.exp(-h))) / (2 * h)
+        assert abs(fd - dist.dlogp_dlogz(z)) < 1e-7
+
+
+def test_update_dedupes_and_restandardises():
+    import torch
+    X, y = toy(15, 2)
+    gp = GP(X, y, noise=1e-6)
+    ref = O.OracleGP(X, y, noise=1e-6)
+    new_X = np.array([[0.8, 0.2], [0.3, 0.9], X[3] + 5e-7])  # third is a duplicate within atol 1e-6
+    new_y = -np.sum((new_X - 0.5) ** 2, axis=1, keepdims=True)
+    if not torch.cuda.is_available():
+        gp.update(new_X, new_y)
+        ref.update(new_X, new_y)
+        assert gp.npoints == 17 == ref.npoints
+        assert np.allclose(gp.train_y, ref.train_y, rtol=0, atol=1e-15) and gp.y_std == ref.y_std
+        gp.update(new_X[0:1], new_y[0:1])
+        assert gp.npoints == 17
+    st = gp.state_dict() if torch.cuda.is_available() else None
+    assert st is None or set(st) >= {"train_x", "train_y", "cholesky", "alphas", "gp_class"}
+
+
+def test_get_random_point_in_unit_cube():
+    X, y = toy(20, 3)
+    gp = GP(X, y)
+    rng = np.random.default_rng(42)
+    pts = np.array([gp.get_random_point(rng=rng) for _ in range(10)])
+    assert pts.shape == (10, 3) and np.all(pts >= 0) and np.all(pts <= 1) and not np.allclose(pts, pts[0])
+
+
+# ---- optimisers -----------------------------------------------------------------------------------------
+def _rosen_vg(x):
+    x = np.asarray(x)
+    f = 100 * (x[1] - x[0] ** 2) ** 2 + (1 - x[0]) ** 2
+    g = np.array([-400 * x[0] * (x[1] - x[0] ** 2) - 2 * (1 - x[0]), 200 * (x[1] - x[0] ** 2)])
+    return float(f), g
+
+
+def _rosen_batched(xs):
+    out = [_rosen_vg(x) for x in np.atleast_2d(xs)]
+    return np.array([o[0] for o in out]), np.stack([o[1] for o in out])
+
+
+def test_optimize_scipy_sequential_and_lockstep_agree():
+    x0 = np.random.default_rng(1).uniform(-1, 2, (6, 2))
+    a, fa = optim.optimize_scipy(num_params=2, bounds=[-2, 2], x0=x0, optimizer_options={}, maxiter=300, n_restarts=6,
+                                 value_and_grad=_rosen_vg)
+    b, fb = optim.optimize_scipy(num_params=2, bounds=[-2, 2], x0=x0, optimizer_options={}, maxiter=300, n_restarts=6,
+                                 batched_value_and_grad=_rosen_batched)
+    assert np.allclose(a, [1, 1], atol=1e-3) and fa < 1e-6
+    assert np.array_equal(a, b) and fa == fb  # same L-BFGS-B iterates, only the evaluation is batched
+    assert optim.optimize_scipy.last_batched_calls < 300
+
+
+def test_optimize_scipy_skips_nan_restarts_and_mutates_options_like_the_reference():
+    def vg(x):
+        if x[0] < 0:
+            return float("nan"), np.array([np.nan, np.nan])
+        return _rosen_vg(x)
+    x0 = np.array([[-1.0, 0.0], [0.5, 0.5]])
+    opts = {"method": "L-BFGS-B"}
+    best, f = optim.optimize_scipy(num_params=2, bounds=np.array([[-2, -2], [2, 2.0]]), x0=x0, optimizer_options=opts,
+                                   maxiter=200, n_restarts=2, value_and_grad=vg)
+    assert f < 1e-6 and "method" not in opts and opts["maxiter"] == 200  # BOBE/optim.py:292-294
+    with pytest.raises(ValueError):
+        optim.optimize_scipy(num_params=2, x0=x0, n_restarts=3, optimizer_options={}, value_and_grad=vg)
+    with pytest.raises(ValueError):
+        optim._setup_bounds(np.zeros((3, 2)), 2)
+
+
+def test_optimize_scipy_finite_difference_fallback():
+    best, f = optim.optimize_scipy(fun=lambda x: float(np.sum((x - 0.3) ** 2)), num_params=3, bounds=[0, 1],
+                                   x0=np.full((1, 3), 0.9), optimizer_options={}, maxiter=100, n_restarts=1)
+    assert np.allclose(best, 0.3, atol=1e-5)
+
+
+def test_adam_optimisers_unit_cube_semantics():
+    vg = lambda x: (float(np.sum((x - 2.0) ** 2)), 2 * (np.asarray(x) - 2.0))  # minimum at 2 in [0, 4]
+    x0u = np.array([[0.1, 0.9]])
+    best, f = optim.optimize_optax(num_params=2, bounds=[0, 4], x0=x0u, maxiter=3000, n_restarts=1,
+                                   optimizer_options={"name": "adam", "lr": 5e-3, "early_stop_patience": 50},
+                                   value_and_grad=vg)
+    assert np.allclose(best, 2.0, atol=5e-2) and f < 1e-2
+    bvg = lambda xs: (np.sum((xs - 2.0) ** 2, axis=1), 2 * (xs - 2.0))
+    best2, f2 = optim.optimize_optax_vmap(num_params=2, bounds=[0, 4], x0=np.array([[0.1, 0.9], [0.8, 0.2]]),
+                                          maxiter=3000, n_restarts=2, batched_value_and_grad=bvg,
+                                          optimizer_options={"name": "adam", "lr": 5e-3, "early_stop_patience": 50})
+    assert np.allclose(best2, 2.0, atol=5e-2)
+    with pytest.raises(ValueError):
+        optim.optimize_optax(num_params=2, x0=x0u, optimizer_options={"name": "lbfgs"}, value_and_grad=vg)
+
+
+def test_scale_unit_roundtrip():
+    b = np.array([[-1.0, 0.0], [3.0, 10.0]])
+    x = np.array([[0.0, 5.0]])
+    assert np.allclose(optim.scale_from_unit(optim.scale_to_unit(x, b), b), x)
+
+
+def test_fd_batched_gradient():
+    from bobe_b200.acquisition import _fd_batched
+    f = lambda xs: np.sum(np.sin(3 * xs), axis=1)
+    xs = np.array([[0.2, 0.7], [0.0, 1.0]])  # second point sits on the box faces: one-sided differences
+    v, g = _fd_batched(f)(xs)
+    assert np.allclose(v, f(xs)) and np.allclose(g, 3 * np.cos(3 * xs), atol=1e-4)
+
+
+def test_mc_points_selection():
+    from bobe_b200.acquisition import get_mc_points, get_mc_samples
+    X, y = toy(10, 2)
+    s = get_mc_samples(GP(X, y), num_samples=64, method="uniform", np_rng=np.random.default_rng(0))
+    assert s["x"].shape == (64, 2)
+    pts = get_mc_points(s, mc_points_size=16, rng=np.random.default_rng(1))
+    assert pts.shape == (16, 2)
+    with pytest.raises(ValueError):
+        get_mc_samples(GP(X, y), method="bogus")

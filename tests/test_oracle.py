@@ -1,0 +1,249 @@
+"""Pins the CPU oracle (oracle/gp_oracle.py) by mathematics -- the reference holds no golden vectors for this
+path and cannot be run here (no JAX): closed forms, identities, gradient three ways, extended precision, and
+the committed golden fixtures (regeneration check)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gp_oracle as O
+from conftest import GOLDEN_DIR, mixed_err
+
+
+def toy(n=30, d=3, seed=42):
+    rng = np.random.RandomState(seed)
+    X = rng.uniform(0, 1, size=(n, d))
+    y = -np.sum((X - 0.5) ** 2, axis=1).reshape(-1, 1)
+    return X, y
+
+
+def test_kernel_basic_properties():
+    X, _ = toy()
+    for kern in (O.rbf_kernel, O.matern_kernel):
+        K = kern(X, X, np.array([0.3, 0.5, 0.7]), 2.0, 1e-6, True)
+        assert np.allclose(K, K.T, atol=1e-15)
+        assert np.allclose(np.diag(K), 2.0 + 1e-6, rtol=1e-12)
+        K0 = kern(X, X[:5], np.array([0.3, 0.5, 0.7]), 2.0, 1e-6, False)
+        assert K0.shape == (30, 5) and np.all(K0 > 0) and np.all(K0 <= 2.0 + 1e-12)
+
+
+def test_kernel_closed_form_entries():
+    xa, xb = np.array([[0.1, 0.2]]), np.array([[0.4, 0.6]])
+    ls, kv = np.array([0.5, 0.25]), 1.7
+    q = ((0.1 - 0.4) / 0.5) ** 2 + ((0.2 - 0.6) / 0.25) ** 2
+    assert math.isclose(O.rbf_kernel(xa, xb, ls, kv, 0.0, False)[0, 0], kv * math.exp(-0.5 * q), rel_tol=1e-14)
+    r = math.sqrt(q)
+    m = kv * (1 + math.sqrt(5) * r + 5 * q / 3) * math.exp(-math.sqrt(5) * r)
+    assert math.isclose(O.matern_kernel(xa, xb, ls, kv, 0.0, False)[0, 0], m, rel_tol=1e-14)
+
+
+def test_mll_closed_form_n1_n2():
+    # n = 1: K = kv + noise, log p = -y^2/(2K) - 1/2 log K - 1/2 log 2 pi
+    k = np.array([[2.5]])
+    yv = np.array([[0.7]])
+    ref = -0.5 * 0.49 / 2.5 - 0.5 * math.log(2.5) - 0.5 * math.log(2 * math.pi)
+    assert math.isclose(O.gp_mll(k, yv, 1), ref, rel_tol=1e-14)
+    # n = 2 by the explicit 2x2 inverse / determinant
+    a, b, c = 2.0, 0.6, 1.5
+    K = np.array([[a, b], [b, c]])
+    yv = np.array([[0.3], [-1.1]])
+    det = a * c - b * b
+    quad = (c * 0.09 - 2 * b * 0.3 * (-1.1) + a * 1.21) / det
+    ref = -0.5 * quad - 0.5 * math.log(det) - math.log(2 * math.pi)
+    assert math.isclose(O.gp_mll(K, yv, 2), ref, rel_tol=1e-13)
+
+
+def test_interpolation_and_noise_level_variance():
+    X, y = toy(25, 2)
+    gp = O.OracleGP(X, y, noise=1e-6, lengthscales=np.array([0.3, 0.3]))
+    mean = gp.predict_mean_batched(X)
+    assert np.max(np.abs(mean - y.ravel())) < 1e-4
+    # exact identity: K0 alpha = y - noise * alpha  (standardised units)
+    ms, _ = gp.predict_batched(X)
+    assert np.max(np.abs(ms - (gp.train_y.ravel() - gp.noise * gp.alphas.ravel()))) < 1e-9
+    var = gp.predict_var_batched(X)
+    assert np.all(var > 0) and np.all(var < 1e-3)  # reference asserts < 1e-3 (tests/test_gp.py:139)
+
+
+def test_standardisation_and_zero_std():
+    ys, m, s = O.standardise(np.array([[1.0], [3.0]]))
+    assert m == 2.0 and s == 1.0 and np.allclose(ys.ravel(), [-1, 1])
+    ys, m, s = O.standardise(np.array([[5.0], [5.0]]))
+    assert s == 1.0 and np.allclose(ys, 0)
+
+
+def _torch_neg_mll(gp, lp):
+    """Reverse-mode through torch.linalg.cholesky: the same construction jax.value_and_grad uses."""
+    X = torch.tensor(gp.train_x)
+    yv = torch.tensor(gp.train_y)
+    lp = torch.tensor(lp, requires_grad=True)
+    hp = torch.exp(lp)
+    d = gp.ndim
+    ls = hp[:d]
+    kv = torch.tensor(gp.kernel_variance, dtype=torch.float64) if gp.fixed_kernel_variance else hp[d]
+    xs = X / ls
+    dsq = ((xs[:, None, :] - xs[None, :, :]) ** 2).sum(-1)
+    if gp.kernel_name == "rbf":
+        K = kv * torch.exp(-0.5 * dsq)
+    else:
+        r = torch.sqrt(torch.where(dsq < 1e-30, torch.full_like(dsq, 1e-30), dsq))
+        K = kv * (1.0 + r * (O.SQRT5 + r * 5.0 / 3.0)) * torch.exp(-O.SQRT5 * r)
+    K = K + gp.noise * torch.eye(X.shape[0], dtype=torch.float64)
+    L = torch.linalg.cholesky(K)
+    alpha = torch.cholesky_solve(yv, L)
+    mll = -0.5 * (yv.T @ alpha).squeeze() - torch.log(torch.diagonal(L)).sum() - 0.5 * X.shape[0] * math.log(2 * math.pi)
+    # priors
+    if gp.lengthscale_prior_spec == "SAAS":
+        tausq = hp[-1]
+        lp_kv = -0.5 * torch.log(kv) ** 2 - math.log(math.sqrt(2 * math.pi)) - torch.log(kv)
+        hc = lambda z, s: math.log(2.0) - math.log(math.pi) - math.log(s) - torch.log1p((z / s) ** 2)
+        mll = mll + lp_kv + hc(tausq, 0.1) + hc(1.0 / (tausq * ls ** 2), 1.0).sum()
+    elif gp.lengthscale_prior_spec == "DSLP":
+        loc, sc = O.SQRT2 + 0.5 * math.log(d), O.SQRT3
+        mll = mll + (-0.5 * ((torch.log(ls) - loc) / sc) ** 2 - math.log(sc * math.sqrt(2 * math.pi)) - torch.log(ls)).sum()
+        mll = mll - math.log(gp.kernel_variance_bounds[1] - gp.kernel_variance_bounds[0])
+    else:
+        mll = mll - d * math.log(gp.lengthscale_bounds[1] - gp.lengthscale_bounds[0])
+        if not gp.fixed_kernel_variance:
+            mll = mll - math.log(gp.kernel_variance_bounds[1] - gp.kernel_variance_bounds[0])
+    loss = -mll
+    loss.backward()
+    return float(loss.detach()), lp.grad.numpy()
+
+
+@pytest.mark.parametrize("kernel", ["rbf", "matern"])
+@pytest.mark.parametrize("prior", [None, "DSLP", "SAAS", "fixed_kv"])
+def test_gradient_three_ways(kernel, prior):
+    X, y = toy(40, 3, seed=1)
+    kw = {}
+    if prior == "fixed_kv":
+        kw = dict(kernel_variance_prior="fixed", kernel_variance=1.3)
+    elif prior is not None:
+        kw = dict(lengthscale_prior=prior)
+    gp = O.OracleGP(X, y, kernel=kernel, noise=1e-6, **kw)
+    rng = np.random.default_rng(3)
+    lp = rng.uniform(-1.0, 0.5, gp.num_hyperparams)
+    v, g = gp.neg_mll_and_grad(lp)
+    assert math.isclose(v, gp.neg_mll(lp), rel_tol=1e-12)
+    vt, gt = _torch_neg_mll(gp, lp)
+    assert abs(v - vt) <= 1e-10 * max(abs(vt), 40)
+    assert np.max(np.abs(g - gt)) <= 1e-8 * max(np.max(np.abs(gt)), 1.0)
+    h = 1e-6
+    for j in range(gp.num_hyperparams):
+        e = np.zeros_like(lp)
+        e[j] = h
+        fd = (gp.neg_mll(lp + e) - gp.neg_mll(lp - e)) / (2 * h)
+        assert abs(fd - g[j]) <= 2e-5 * max(abs(g[j]), 1.0)
+
+
+def test_matern_clamp_has_zero_gradient_on_duplicates():
+    X, y = toy(10, 2)
+    X[1] = X[0]  # exact duplicate: dsq == 0 off the diagonal too, clamp active, gradient contribution 0
+    y[1] = y[0]
+    gp = O.OracleGP(X, y, kernel="matern", noise=1e-4)
+    lp = np.log(gp.get_hyperparams())
+    v, g = gp.neg_mll_and_grad(lp)
+    vt, gt = _torch_neg_mll(gp, lp)
+    assert np.all(np.isfinite(g)) and np.max(np.abs(g - gt)) <= 1e-8 * max(np.max(np.abs(gt)), 1.0)
+
+
+def test_non_pd_gives_nan_not_exception():
+    X, y = toy(20, 2)
+    X[1] = X[0]
+    gp = O.OracleGP(X, y, kernel="rbf", noise=0.0, lengthscales=np.array([5.0, 5.0]))
+    lp = np.log(gp.get_hyperparams())
+    v, g = gp.neg_mll_and_grad(lp)
+    assert np.isnan(v) and np.all(np.isnan(g))
+
+
+def test_fantasy_var_equals_predict_var_of_updated_gp():
+    X, y = toy(35, 3, seed=7)
+    for kernel in ("rbf", "matern"):
+        gp = O.OracleGP(X, y, kernel=kernel, noise=1e-6, lengthscales=np.array([0.4, 0.6, 0.5]))
+        mc = np.random.default_rng(0).uniform(0, 1, (20, 3))
+        xn = np.array([0.21, 0.77, 0.4])
+        ktm = gp.kernel(gp.train_x, mc, gp.lengthscales, gp.kernel_variance, gp.noise, False)
+        fv = gp.fantasy_var(xn, mc, ktm)
+        gp2 = O.OracleGP(X, y, kernel=kernel, noise=1e-6, lengthscales=np.array([0.4, 0.6, 0.5]))
+        y_std0 = gp2.y_std
+        gp2.train_x = np.vstack([gp2.train_x, xn])  # value-independent: keep the standardisation fixed
+        gp2.train_y = np.vstack([gp2.train_y, [[0.123]]])
+        gp2.recompute_cholesky()
+        raw = np.maximum(gp2._raw_var(mc), O.SAFE_NOISE_FLOOR) * y_std0 ** 2
+        assert mixed_err(fv, raw, y_std0 ** 2) < 1e-9
+        shared = gp.fantasy_var_shared(np.vstack([xn, mc[:3]]), mc)
+        assert mixed_err(shared[0], fv, y_std0 ** 2) < 1e-9
+        assert mixed_err(shared[1], gp.fantasy_var(mc[0], mc, ktm), y_std0 ** 2) < 1e-9
+
+
+def test_fast_update_cholesky_matches_full_factor():
+    X, y = toy(20, 2)
+    gp = O.OracleGP(X, y, noise=1e-6)
+    xn = np.array([[0.33, 0.9]])
+    k = gp._k12(xn).ravel()
+    Lnew = O.fast_update_cholesky(gp.cholesky, k, gp.kernel_variance + gp.noise)
+    Xf = np.vstack([X, xn])
+    Kf = gp.kernel(Xf, Xf, gp.lengthscales, gp.kernel_variance, gp.noise, True)
+    assert np.max(np.abs(Lnew - np.linalg.cholesky(Kf))) < 1e-7
+
+
+def test_oracle_against_extended_precision_truth():
+    from oracle.truth_mp import TruthGP
+    X, y = O.synthetic_training_set(40, 3)
+    for kernel, ell in (("rbf", 0.6), ("matern", 0.7)):
+        gp = O.OracleGP(X, y, kernel=kernel, lengthscales=np.full(3, ell))
+        T = TruthGP(gp.kernel_name, X, gp.train_y, gp.lengthscales, gp.kernel_variance, gp.noise)
+        Xq = O.synthetic_queries(10, 3)
+        mt, vt = T.predict(Xq)
+        ms, _ = gp.predict_batched(Xq)
+        assert mixed_err(ms, mt, 1.0) < 1e-9
+        assert mixed_err(gp._raw_var(Xq), vt, 1.0) < 1e-9
+        lp = np.log(gp.get_hyperparams())
+        v, g = gp.neg_mll_and_grad(lp)
+        pl, pg = gp.log_prior_and_grad(lp)
+        assert abs((-v - pl) - T.mll()) < 1e-9 * 40
+        gt = T.mll_grad()
+        assert np.max(np.abs((-g - pg) - gt)) < 1e-7 * np.max(np.abs(gt))
+
+
+def test_log_ei_against_mpmath():
+    import mpmath as mp
+    mp.mp.dps = 50
+    us = np.array([3.0, 0.5, -0.5, -1.0, -1.5, -5.0, -30.0, -1e3, -2e6])
+    got = O.log_ei_helper(us)
+    for u, gv in zip(us, got):
+        um = mp.mpf(float(u))
+        if u > -1e4:
+            ref = mp.log(mp.npdf(um) + um * mp.ncdf(um))
+        else:  # asymptotic series of the Mills ratio, accurate far in the tail
+            ref = mp.log(mp.npdf(um)) - 2 * mp.log(-um) + mp.log(1 - 3 / um ** 2 + 15 / um ** 4)
+        tol = 1e-12 if u > -1e6 else 1e-6  # below -1e6 the reference switches to the leading term only
+        assert abs(float(ref) - gv) <= tol * abs(float(ref)), (u, gv, float(ref))
+    assert np.all(O.ei_values(np.array([0.1, -3.0]), np.array([[0.04], [1e-30]]), 0.0, 0.0) <= 0)
+
+
+def test_priors_logprob_values():
+    assert math.isclose(float(O.lognormal_logprob(2.0, 0.3, 1.7)),
+                        -0.5 * ((math.log(2) - 0.3) / 1.7) ** 2 - math.log(1.7 * math.sqrt(2 * math.pi)) - math.log(2))
+    assert math.isclose(float(O.halfcauchy_logprob(0.5, 0.1)), math.log(2 / (math.pi * 0.1 * (1 + 25))))
+    assert math.isclose(float(O.uniform_logprob(0.3, 0.01, 5)), -math.log(4.99))
+
+
+@pytest.mark.parametrize("name", ["A_banana_rbf_n100_d2", "M_matern_n300_d3", "B_rbf_n500_d4"])
+def test_golden_fixtures_are_reproduced_by_the_oracle(name):
+    from oracle.gen_golden import make_case
+    gold = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    gp, X, y, Xq, x0, mc, cand = make_case(name)
+    # BLAS thread counts differ between machines: the ill-conditioned cases move at the 1e-9 level
+    assert mixed_err(gp.predict_mean_batched(Xq), gold["mean"], gp.y_std) < 5e-9
+    assert mixed_err(gp.predict_var_batched(Xq), gold["var"], gp.y_std ** 2) < 1e-8
+    v, g = gp.neg_mll_and_grad(x0[0])
+    assert abs(v - gold["neg_mll"][0]) < 1e-8 * max(abs(v), X.shape[0])
+    assert mixed_err(gp.fantasy_var_shared(cand, mc), gold["fantasy"], gp.y_std ** 2) < 1e-8
+    if "truth_mll" in gold.files:
+        # the oracle's own rounding noise at cond(K) ~ 3e9, for the record
+        pl = gp.log_prior_and_grad(x0[0])[0]
+        assert abs((-gold["neg_mll"][0] - pl) - float(gold["truth_mll"])) < 1e-8 * X.shape[0]
+        assert mixed_err(gold["mean_std"][:32], gold["truth_mean_std"], 1.0) < 1e-9
