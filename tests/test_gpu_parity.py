@@ -45,16 +45,34 @@ def test_golden_parity(name):
     gp = make_gp(ref)
     assert gp.y_mean == ref.y_mean and gp.y_std == ref.y_std
     mean, var = gp.predict_mean_var_batched(Xq)
-    assert mixed_err(mean, gold["mean"], ref.y_std) < TOL_MEAN
+    tol_mean = 3 * TOL_MEAN if "truth_mean_std" in gold.files else TOL_MEAN  # see the exact-value check below
+    assert mixed_err(mean, gold["mean"], ref.y_std) < tol_mean
     assert mixed_err(var, gold["var"], ref.y_std ** 2) < TOL_VAR
-    assert mixed_err(gp.predict_mean_batched(Xq), gold["mean"], ref.y_std) < TOL_MEAN
+    assert mixed_err(gp.predict_mean_batched(Xq), gold["mean"], ref.y_std) < tol_mean
     assert mixed_err(gp.predict_var_batched(Xq), gold["var"], ref.y_std ** 2) < TOL_VAR
     ms, vs = gp.predict_batched(Xq)
     assert vs.shape == (Xq.shape[0], 1)
-    assert mixed_err(ms, gold["mean_std"], 1.0) < TOL_MEAN and mixed_err(vs.ravel(), gold["var_std"], 1.0) < TOL_VAR
+    assert mixed_err(vs.ravel(), gold["var_std"], 1.0) < TOL_VAR
     v, g = gp.neg_mll_and_grad_batched(x0)
+    has_truth = "truth_mean_std" in gold.files
+    if has_truth:
+        # Ill-conditioned shapes (cond(K) up to 2e10): the float64 oracle itself sits ~1e-9 from the exact value
+        # (SURVEY.md fact 5), so the CUDA result is held to the tolerance against the EXACT (60-digit) value and
+        # the oracle's own gap is printed beside it.
+        pl = ref.log_prior_and_grad(x0[0])[0]
+        e_cuda = mixed_err(ms[:32], gold["truth_mean_std"], 1.0)
+        e_orac = mixed_err(gold["mean_std"][:32], gold["truth_mean_std"], 1.0)
+        m_cuda = abs((-v[0] - pl) - float(gold["truth_mll"])) / max(abs(float(gold["truth_mll"])), n)
+        m_orac = abs((-gold["neg_mll"][0] - pl) - float(gold["truth_mll"])) / max(abs(float(gold["truth_mll"])), n)
+        print(f"\n[{name}] vs exact: mean cuda {e_cuda:.1e} oracle {e_orac:.1e} | mll cuda {m_cuda:.1e} oracle {m_orac:.1e}"
+              f" | cuda vs oracle: mean {mixed_err(ms, gold['mean_std'], 1.0):.1e}")
+        assert e_cuda < TOL_MEAN and m_cuda < TOL_MLL
+        assert mixed_err(ms, gold["mean_std"], 1.0) < 3 * TOL_MEAN  # and never far from the oracle either
+    else:
+        assert mixed_err(ms, gold["mean_std"], 1.0) < TOL_MEAN
     for r in range(x0.shape[0]):
-        assert abs(v[r] - gold["neg_mll"][r]) <= TOL_MLL * max(abs(gold["neg_mll"][r]), n), (r, v[r], gold["neg_mll"][r])
+        tol_r = 3 * TOL_MLL if (has_truth and r == 0) else TOL_MLL  # r == 0 is held to the exact value above
+        assert abs(v[r] - gold["neg_mll"][r]) <= tol_r * max(abs(gold["neg_mll"][r]), n), (r, v[r], gold["neg_mll"][r])
         check_grad(g[r], gold["neg_mll_grad"][r], f"restart {r}")
     assert mixed_err(gp.fantasy_var(cand, mc), gold["fantasy"], ref.y_std ** 2) < TOL_VAR
     assert mixed_err(gp.fantasy_acquisition(mc, None, std=False), gold["wipv_self"], ref.y_std ** 2) < TOL_VAR
@@ -64,7 +82,11 @@ def test_golden_parity(name):
     lei = LogEI().fun_batched(Xq, gp, best, 0.01)
     # EI multiplies the 1e-7-tolerance variance: same tolerance, scale = the largest EI in the batch
     assert mixed_err(ei, gold["ei"], max(float(np.max(np.abs(gold["ei"]))), 1e-12)) < 1e-6
-    assert mixed_err(lei, gold["logei"], 1.0) < 1e-6
+    # log EI ~ -u^2/2 with u = (mu - best)/sigma amplifies the (absolute, 1e-7) variance tolerance by u^2/var;
+    # end to end it is compared where the variance is not at the noise floor.  The epilogue arithmetic itself
+    # is checked on identical inputs, tails included, in test_acq_ei_tails.
+    ok = gold["var_std"] > 1e-4
+    assert ok.sum() > 10 and mixed_err(lei[ok], gold["logei"][ok], 1.0) < 1e-6
     assert abs(float(gp._logdet.item()) - float(gold["logdet"])) <= TOL_MLL * n
     assert np.linalg.norm(gp.alphas.ravel() - gold["alpha"]) <= 1e-6 * np.linalg.norm(gold["alpha"])
 
@@ -150,8 +172,9 @@ def test_non_pd_restart_is_nan_for_that_restart_only():
     lp = np.log(np.array([[0.5, 0.5, 0.5, 1.0], [0.5, 0.5, 0.5, 1.0]]))
     val_bad, grad_bad, info_bad = ops.mll_grad_batched("rbf", T(X), T(ys), T(lp), True, 1.0, -0.5)
     assert torch.isnan(val_bad).all() and torch.isnan(grad_bad).all() and (info_bad == 1).all()
-    # mixed batch: restart 1 has an absurd lengthscale that makes K numerically singular without noise
-    lp2 = np.log(np.array([[0.5, 0.5, 0.5, 1.0], [50.0, 50.0, 50.0, 1e8]]))
+    # mixed batch without noise: restart 0 is nearly diagonal (well conditioned); restart 1 has a lengthscale so
+    # large that every kernel entry rounds to exactly kv, i.e. K = ones is exactly singular (second pivot == 0)
+    lp2 = np.log(np.array([[0.05, 0.05, 0.05, 1.0], [1e9, 1e9, 1e9, 1.0]]))
     val, grad, info = ops.mll_grad_batched("rbf", T(X), T(ys), T(lp2), True, 1.0, 0.0)
     ref = O.OracleGP(X, y, kernel="rbf", noise=0.0)
     v0, g0 = ref.neg_mll_and_grad(lp2[0])
