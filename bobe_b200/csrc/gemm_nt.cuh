@@ -13,17 +13,19 @@
 
 namespace bobe {
 
-template <int BM_, int BN_, int WM_, int WN_, int STAGES_>
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int BK_ = 16>
 struct TileCfg {
     static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_;
-    static constexpr int BK = 16;
+    static constexpr int BK = BK_;
+    static constexpr int PANELS = BK / 8;  // k8 panels per stage
     static constexpr int THREADS = 32 * WM * WN;
     static constexpr int WTM = BM / WM, WTN = BN / WN;  // warp tile
     static constexpr int MF = WTM / 8, NF = WTN / 8;    // 8x8 fragments per warp tile
     static constexpr int STAGE_DOUBLES = (BM + BN) * BK;
     static constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;
     static_assert(WTM % 8 == 0 && WTN % 8 == 0, "warp tile must be a multiple of 8x8");
-    static_assert((BM * 8) % THREADS == 0 && (BN * 8) % THREADS == 0, "loader mapping");
+    static_assert(BK % 16 == 0, "BK must be a multiple of 16 (k ranges are 16-aligned)");
+    static_assert((BM * BK / 2) % THREADS == 0 && (BN * BK / 2) % THREADS == 0, "loader mapping");
 };
 
 // flags describing known-zero structure of the operands (only used to shorten the k loop; the zeros are
@@ -38,29 +40,83 @@ enum : int {
 
 template <class Cfg>
 struct Mainloop {
-    // one operand tile of one stage: rows x 16 doubles, global row stride ld
-    template <int ROWS>
-    __device__ static __forceinline__ void load_tile(double* s, const double* g, int64_t ld, int rows_valid, int k0) {
-        constexpr int CHUNKS = ROWS * 8;
+    static constexpr int ROWS_PER_SLOT = Cfg::THREADS / (8 * Cfg::PANELS) * 2;  // rows between a thread's chunks
+    static constexpr int SLOTS_A = Cfg::BM / ROWS_PER_SLOT, SLOTS_B = Cfg::BN / ROWS_PER_SLOT;
+
+    // Per-thread addressing of the global->shared copies, computed ONCE per tile (the k loop only adds BK).
+    // Thread mapping: 8 consecutive threads fill two adjacent 64-byte panel rows (128 contiguous smem bytes),
+    // the next 8 the same rows of the next k8 panel; slot s of a thread is ROWS_PER_SLOT rows further down.
+    struct Loader {
+        const double* gA;   // this thread's first 16-byte chunk of A at k = kb
+        const double* gB;
+        int64_t stepA, stepB;  // ROWS_PER_SLOT * ld
+        uint32_t sA, sB;       // shared-memory byte addresses of the chunk in stage 0
+        uint32_t okA, okB;     // bit s set: slot s is a valid row (others are zero-filled)
+
+        __device__ __forceinline__ void init(const double* A, int64_t lda, int rowsA, const double* Bt, int64_t ldb,
+                                             int rowsB, int kb, double* smem) {
+            const int tid = threadIdx.x;
+            const int c4 = tid & 3, panel = (tid >> 3) % Cfg::PANELS;
+            const int row = ((tid / (8 * Cfg::PANELS)) << 1) | ((tid >> 2) & 1);
+            gA = A + (int64_t)row * lda + kb + panel * 8 + c4 * 2;
+            gB = Bt + (int64_t)row * ldb + kb + panel * 8 + c4 * 2;
+            stepA = (int64_t)ROWS_PER_SLOT * lda;
+            stepB = (int64_t)ROWS_PER_SLOT * ldb;
+            uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+            sA = base + ((panel * Cfg::BM + row) * 8 + c4 * 2) * 8;
+            sB = base + (Cfg::BM * Cfg::BK + (panel * Cfg::BN + row) * 8 + c4 * 2) * 8;
+            okA = okB = 0;
 #pragma unroll
-        for (int it = 0; it < CHUNKS / Cfg::THREADS; ++it) {
-            int id = threadIdx.x + it * Cfg::THREADS;
-            int c4 = id & 3, row = ((id >> 4) << 1) | ((id >> 2) & 1), panel = (id >> 3) & 1;
-            bool ok = row < rows_valid;
-            const double* src = g + (int64_t)(ok ? row : 0) * ld + k0 + panel * 8 + c4 * 2;
-            cp_async16(s + ((panel * ROWS + row) * 8 + c4 * 2), src, ok);
+            for (int sl = 0; sl < SLOTS_A; ++sl) okA |= (row + sl * ROWS_PER_SLOT < rowsA) ? (1u << sl) : 0u;
+#pragma unroll
+            for (int sl = 0; sl < SLOTS_B; ++sl) okB |= (row + sl * ROWS_PER_SLOT < rowsB) ? (1u << sl) : 0u;
         }
+        // copy k-tile `kt` (relative to kb) into pipeline stage `stage`
+        __device__ __forceinline__ void issue(int kt, int stage) const {
+            const uint32_t so = stage * (Cfg::STAGE_DOUBLES * 8);
+            const double* a = gA + kt * Cfg::BK;
+            const double* b = gB + kt * Cfg::BK;
+#pragma unroll
+            for (int sl = 0; sl < SLOTS_A; ++sl) {
+                bool ok = (okA >> sl) & 1u;
+                const double* src = ok ? a + sl * stepA : gA;
+                int sz = ok ? 16 : 0;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sA + so + sl * (ROWS_PER_SLOT * 64)),
+                             "l"(src), "r"(sz));
+            }
+#pragma unroll
+            for (int sl = 0; sl < SLOTS_B; ++sl) {
+                bool ok = (okB >> sl) & 1u;
+                const double* src = ok ? b + sl * stepB : gB;
+                int sz = ok ? 16 : 0;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sB + so + sl * (ROWS_PER_SLOT * 64)),
+                             "l"(src), "r"(sz));
+            }
+        }
+    };
+
+    __device__ static __forceinline__ void mma_panel(double (&acc)[Cfg::MF][Cfg::NF][2], const double* sA,
+                                                     const double* sB, int p, int wm, int wn, int g, int t) {
+        double2 a[Cfg::MF], b[Cfg::NF];
+#pragma unroll
+        for (int mf = 0; mf < Cfg::MF; ++mf)
+            a[mf] = *reinterpret_cast<const double2*>(sA + ((p * Cfg::BM + wm * Cfg::WTM + mf * 8 + g) * 8 + 2 * t));
+#pragma unroll
+        for (int nf = 0; nf < Cfg::NF; ++nf)
+            b[nf] = *reinterpret_cast<const double2*>(sB + ((p * Cfg::BN + wn * Cfg::WTN + nf * 8 + g) * 8 + 2 * t));
+        // two passes (k = {0,2,4,6} then {1,3,5,7}): MF*NF independent MMAs between the two that update the
+        // same accumulator, so no MMA ever waits on the latency of the previous one
+#pragma unroll
+        for (int mf = 0; mf < Cfg::MF; ++mf)
+#pragma unroll
+            for (int nf = 0; nf < Cfg::NF; ++nf) dmma884(acc[mf][nf][0], acc[mf][nf][1], a[mf].x, b[nf].x);
+#pragma unroll
+        for (int mf = 0; mf < Cfg::MF; ++mf)
+#pragma unroll
+            for (int nf = 0; nf < Cfg::NF; ++nf) dmma884(acc[mf][nf][0], acc[mf][nf][1], a[mf].y, b[nf].y);
     }
 
-    __device__ static __forceinline__ void load_stage(double* smem, int stage, const double* A, int64_t lda,
-                                                      int rowsA, const double* Bt, int64_t ldb, int rowsB, int k0) {
-        double* sA = smem + stage * Cfg::STAGE_DOUBLES;
-        double* sB = sA + Cfg::BM * Cfg::BK;
-        load_tile<Cfg::BM>(sA, A, lda, rowsA, k0);
-        load_tile<Cfg::BN>(sB, Bt, ldb, rowsB, k0);
-    }
-
-    // acc += A[0:BM, kb:ke] * Bt[0:BN, kb:ke]^T   (kb, ke multiples of 16; A/Bt point at the tile's first row)
+    // acc += A[0:BM, kb:ke] * Bt[0:BN, kb:ke]^T   (kb, ke multiples of BK; A/Bt point at the tile's first row)
     __device__ static __forceinline__ void run(double (&acc)[Cfg::MF][Cfg::NF][2], const double* A, int64_t lda,
                                                int rowsA, const double* Bt, int64_t ldb, int rowsB, int kb, int ke,
                                                double* smem) {
@@ -68,39 +124,31 @@ struct Mainloop {
         const int g = lane >> 2, t = lane & 3;
         const int wm = warp / Cfg::WN, wn = warp % Cfg::WN;
         const int ktiles = (ke - kb) / Cfg::BK;
+        Loader ld;
+        ld.init(A, lda, rowsA, Bt, ldb, rowsB, kb, smem);
 
 #pragma unroll
         for (int s = 0; s < Cfg::STAGES - 1; ++s) {
-            if (s < ktiles) load_stage(smem, s, A, lda, rowsA, Bt, ldb, rowsB, kb + s * Cfg::BK);
+            if (s < ktiles) ld.issue(s, s);
             cp_async_commit();
         }
+        int stage = 0;  // stage holding k-tile kt
         for (int kt = 0; kt < ktiles; ++kt) {
             cp_async_wait<Cfg::STAGES - 2>();
-            __syncthreads();
-            {
+            __syncthreads();  // k-tile kt has landed for everyone; everyone is done reading k-tile kt-1
+            const double* sA = smem + stage * Cfg::STAGE_DOUBLES;
+            const double* sB = sA + Cfg::BM * Cfg::BK;
+            mma_panel(acc, sA, sB, 0, wm, wn, g, t);
+            {   // refill the stage freed by k-tile kt-1, issued BEHIND the first panel's MMAs so that the address
+                // arithmetic and the LDGSTS issue overlap with tensor work instead of idling the pipe
                 int nk = kt + Cfg::STAGES - 1;
-                if (nk < ktiles) load_stage(smem, nk % Cfg::STAGES, A, lda, rowsA, Bt, ldb, rowsB, kb + nk * Cfg::BK);
+                int nstage = stage == 0 ? Cfg::STAGES - 1 : stage - 1;
+                if (nk < ktiles) ld.issue(nk, nstage);
                 cp_async_commit();
             }
-            const double* sA = smem + (kt % Cfg::STAGES) * Cfg::STAGE_DOUBLES;
-            const double* sB = sA + Cfg::BM * Cfg::BK;
 #pragma unroll
-            for (int p = 0; p < 2; ++p) {
-                double2 a[Cfg::MF], b[Cfg::NF];
-#pragma unroll
-                for (int mf = 0; mf < Cfg::MF; ++mf)
-                    a[mf] = *reinterpret_cast<const double2*>(sA + ((p * Cfg::BM + wm * Cfg::WTM + mf * 8 + g) * 8 + 2 * t));
-#pragma unroll
-                for (int nf = 0; nf < Cfg::NF; ++nf)
-                    b[nf] = *reinterpret_cast<const double2*>(sB + ((p * Cfg::BN + wn * Cfg::WTN + nf * 8 + g) * 8 + 2 * t));
-#pragma unroll
-                for (int mf = 0; mf < Cfg::MF; ++mf)
-#pragma unroll
-                    for (int nf = 0; nf < Cfg::NF; ++nf) {
-                        dmma884(acc[mf][nf][0], acc[mf][nf][1], a[mf].x, b[nf].x);
-                        dmma884(acc[mf][nf][0], acc[mf][nf][1], a[mf].y, b[nf].y);
-                    }
-            }
+            for (int p = 1; p < Cfg::PANELS; ++p) mma_panel(acc, sA, sB, p, wm, wn, g, t);
+            stage = stage + 1 == Cfg::STAGES ? 0 : stage + 1;
         }
         cp_async_wait<0>();
         __syncthreads();  // smem may be reused by the caller (next tile / epilogue)
@@ -108,15 +156,16 @@ struct Mainloop {
 };
 
 // k-range of a tile from the structure flags
-__device__ __forceinline__ void tile_k_range(int flags, int i0, int j0, int BM, int BN, int K, int& kb, int& ke) {
+__device__ __forceinline__ void tile_k_range(int flags, int i0, int j0, int BM, int BN, int BK, int K, int& kb,
+                                             int& ke) {
     kb = 0;
     ke = K;
     if (flags & GEMM_A_LOWER) ke = min(ke, i0 + BM);
     if (flags & GEMM_B_LOWER) ke = min(ke, j0 + BN);
     if (flags & GEMM_A_UPPER) kb = max(kb, i0);
     if (flags & GEMM_B_UPPER) kb = max(kb, j0);
-    kb = (kb / 16) * 16;
-    ke = min(K, ((ke + 15) / 16) * 16);
+    kb = (kb / BK) * BK;
+    ke = min(K, ((ke + BK - 1) / BK) * BK);
     if (ke < kb) ke = kb;
 }
 
@@ -145,7 +194,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(GemmArgs p) {
     const double* A = p.A + z * p.strideA + (int64_t)i0 * p.lda;
     const double* Bt = p.Bt + z * p.strideB + (int64_t)j0 * p.ldb;
     int kb, ke;
-    tile_k_range(p.flags, i0, j0, Cfg::BM, Cfg::BN, p.K, kb, ke);
+    tile_k_range(p.flags, i0, j0, Cfg::BM, Cfg::BN, Cfg::BK, p.K, kb, ke);
 
     double acc[Cfg::MF][Cfg::NF][2];
 #pragma unroll
@@ -181,6 +230,73 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(GemmArgs p) {
                 Ct[(int64_t)col * p.ldct + row] = v0;
                 Ct[(int64_t)(col + 1) * p.ldct + row] = v1;
             }
+        }
+    }
+}
+
+// ---- predictive variance: var_j = kk - sum_i ( sum_{k<=i} Linv[i][k] Kstar[j][k] )^2 -----------------------
+// One CTA owns BN queries and sweeps all row blocks of Linv (a lower-triangular NT product), squaring and
+// summing each finished BM x BN block of V into per-query registers.  V never leaves the SM.
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
+    trmm_sumsq_kernel(const double* __restrict__ Linv, int npad, const double* __restrict__ Kstar, int64_t ldk,
+                      int64_t q_begin, int64_t M, double kk, double scale, int standardised,
+                      double* __restrict__ var_out) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double red[Cfg::WM][Cfg::BN];
+    const int j0 = blockIdx.x * Cfg::BN;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp / Cfg::WN, wn = warp % Cfg::WN;
+    const double* Bt = Kstar + (int64_t)j0 * ldk;
+
+    double colsum[Cfg::NF][2];
+#pragma unroll
+    for (int nf = 0; nf < Cfg::NF; ++nf) colsum[nf][0] = colsum[nf][1] = 0.0;
+
+    for (int i0 = 0; i0 < npad; i0 += Cfg::BM) {
+        double acc[Cfg::MF][Cfg::NF][2];
+#pragma unroll
+        for (int mf = 0; mf < Cfg::MF; ++mf)
+#pragma unroll
+            for (int nf = 0; nf < Cfg::NF; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
+        int ke = min(npad, i0 + Cfg::BM);
+        Mainloop<Cfg>::run(acc, Linv + (int64_t)i0 * npad, npad, min(Cfg::BM, npad - i0), Bt, ldk, Cfg::BN, 0, ke, smem);
+#pragma unroll
+        for (int mf = 0; mf < Cfg::MF; ++mf)
+#pragma unroll
+            for (int nf = 0; nf < Cfg::NF; ++nf) {
+                colsum[nf][0] = fma(acc[mf][nf][0], acc[mf][nf][0], colsum[nf][0]);
+                colsum[nf][1] = fma(acc[mf][nf][1], acc[mf][nf][1], colsum[nf][1]);
+            }
+    }
+    // reduce over the 8 row groups of the warp (lanes differing in g), then over the WM warps along M
+#pragma unroll
+    for (int nf = 0; nf < Cfg::NF; ++nf)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            double v = colsum[nf][c];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (g == 0) red[wm][wn * Cfg::WTN + nf * 8 + 2 * t + c] = v;
+        }
+    __syncthreads();
+    for (int c = threadIdx.x; c < Cfg::BN; c += Cfg::THREADS) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < Cfg::WM; ++w) s += red[w][c];
+        int64_t q = q_begin + j0 + c;
+        if (q < M) {
+            double var = kk - s;
+            if (standardised) {  // predict_single, BOBE/gp.py:487-488: NaN -> floor, then < floor -> floor
+                if (isnan(var)) var = SAFE_FLOOR;
+                if (var < SAFE_FLOOR) var = SAFE_FLOOR;
+            } else {  // predict_var_single, BOBE/gp.py:465-466: clip (NaN propagates), times y_std^2
+                if (var < SAFE_FLOOR) var = SAFE_FLOOR;
+                var *= scale;
+            }
+            var_out[q] = var;
         }
     }
 }
