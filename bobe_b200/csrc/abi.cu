@@ -456,7 +456,7 @@ extern "C" int32_t bobe_chol_append(void* stream_, const double* L, int64_t n, i
         if (int32_t rc = check_launch("chol_append_copy_kernel")) return rc;
     }
     int smem = (int)(n * 8 + 16);
-    cudaFuncSetAttribute(chol_append_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (int32_t rc = ensure_smem<chol_append_solve_kernel>(smem)) return rc;
     chol_append_solve_kernel<<<1, 1024, smem, stream>>>(L, n, ldl, k, k_self, L_out + n * ldo);
     return check_launch("chol_append_solve_kernel");
 }

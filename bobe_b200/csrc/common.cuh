@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstdio>
 
 #include "../../include/bobe_b200.h"
@@ -18,6 +19,25 @@ inline int64_t round_up(int64_t a, int64_t b) { return ((a + b - 1) / b) * b; }
 
 void set_error(const char* fmt, ...);
 int32_t check_launch(const char* what);
+
+// Raise a kernel's dynamic shared-memory limit.  cudaFuncSetAttribute costs ~10 us of host time, which dominates a
+// chain of hundreds of small dependent launches, so it is issued at most once per (kernel, device, size).
+template <auto Kernel>
+inline int32_t ensure_smem(int bytes) {
+    static std::atomic<int> have[64];  // zero-initialised; largest limit already set per device
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (have[dev].load(std::memory_order_relaxed) >= bytes) return BOBE_OK;
+    cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(smem=%d): %s", bytes, cudaGetErrorString(e));
+        return BOBE_E_CUDA;
+    }
+    int cur = have[dev].load(std::memory_order_relaxed);
+    while (cur < bytes && !have[dev].compare_exchange_weak(cur, bytes)) {
+    }
+    return BOBE_OK;
+}
 
 // ---- FP64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col).  SASS: DMMA.8x8x4 -------------------
 // lane = 4*g + t :  a = A[g][t],  b = B[t][g],  c0/c1 = C[g][2t], C[g][2t+1]

@@ -11,90 +11,9 @@
 // and info = 1 for that batch entry only, never an error.
 #include "gemm_nt.cuh"
 #include "kernels.cuh"
+#include "leaf.cuh"
 
 namespace bobe {
-
-constexpr int LLD = NB + 1;
-constexpr double REFINE_RATIO = 1e3;
-
-__global__ void __launch_bounds__(256) leaf_chol_inv_kernel(const double* __restrict__ KB, double* __restrict__ L,
-                                                            double* __restrict__ Lt, double* __restrict__ Linv,
-                                                            double* __restrict__ U, double* __restrict__ diag,
-                                                            double* __restrict__ dstat, int* __restrict__ gate,
-                                                            int npad, int o) {
-    extern __shared__ __align__(16) double sm[];
-    double* A = sm;                  // [NB][LLD] lower factor being built
-    double* X = sm + NB * LLD;       // [NB][LLD] its inverse
-    double* dd = X + NB * LLD;       // [NB]
-    double* invd = dd + NB;          // [NB]
-    const int tid = threadIdx.x;
-    const int64_t zoff = (int64_t)blockIdx.z * npad * npad;
-    const double* Kz = KB + zoff + (int64_t)o * npad + o;
-
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        int r = idx >> 6, c = idx & 63;
-        A[r * LLD + c] = (c <= r) ? Kz[(int64_t)r * npad + c] : 0.0;
-        X[r * LLD + c] = 0.0;
-    }
-    // unblocked right-looking Cholesky
-    for (int j = 0; j < NB; ++j) {
-        __syncthreads();
-        double dj = sqrt(A[j * LLD + j]);
-        if (tid > j && tid < NB) A[tid * LLD + j] = A[tid * LLD + j] / dj;
-        if (tid == j) dd[j] = dj;
-        __syncthreads();
-        for (int i = j + 1 + (tid >> 4); i < NB; i += 16) {
-            double aij = A[i * LLD + j];
-            for (int k = j + 1 + (tid & 15); k <= i; k += 16) A[i * LLD + k] = fma(-aij, A[k * LLD + j], A[i * LLD + k]);
-        }
-    }
-    __syncthreads();
-    if (tid < NB) invd[tid] = 1.0 / dd[tid];
-    __syncthreads();
-    // inverse by forward substitution: 4 lanes per column
-    {
-        const int c = tid >> 2, l4 = tid & 3;
-        const int cmin = (tid >> 5) << 3;  // smallest column handled by this warp
-        if (l4 == 0) X[c * LLD + c] = invd[c];
-        __syncwarp();
-        for (int i = cmin + 1; i < NB; ++i) {
-            double s = 0.0;
-            if (i > c)
-                for (int k = c + l4; k < i; k += 4) s = fma(A[i * LLD + k], X[k * LLD + c], s);
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (l4 == 0 && i > c) X[i * LLD + c] = -s * invd[i];
-            __syncwarp();
-        }
-    }
-    __syncthreads();
-    double* Lz = L + zoff + (int64_t)o * npad + o;
-    double* Ltz = Lt + zoff + (int64_t)o * npad + o;
-    double* Liz = Linv + zoff + (int64_t)o * npad + o;
-    double* Uz = U + zoff + (int64_t)o * npad + o;
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        int r = idx >> 6, c = idx & 63;
-        int64_t off = (int64_t)r * npad + c;
-        double d = dd[r];
-        Lz[off] = (c < r) ? A[r * LLD + c] : (c == r ? d : 0.0);
-        Ltz[off] = (c > r) ? A[c * LLD + r] : (c == r ? d : 0.0);
-        Liz[off] = (c <= r) ? X[r * LLD + c] : 0.0;
-        Uz[off] = (c >= r) ? X[c * LLD + r] : 0.0;
-    }
-    if (tid < NB) diag[(int64_t)blockIdx.z * npad + o + tid] = dd[tid];
-    // running extreme pivots of this matrix (leaves of one matrix run in stream order: no atomics needed).
-    // max/min pivot is a lower bound on cond(L); beyond REFINE_RATIO the panel solves get a correction step.
-    if (tid == 0) {
-        double lo = dstat[blockIdx.z * 2], hi = dstat[blockIdx.z * 2 + 1];
-        for (int i = 0; i < NB; ++i) {
-            lo = fmin(lo, dd[i]);
-            hi = fmax(hi, dd[i]);
-        }
-        dstat[blockIdx.z * 2] = lo;
-        dstat[blockIdx.z * 2 + 1] = hi;
-        if (hi > REFINE_RATIO * lo) gate[blockIdx.z] = 1;
-    }
-}
 
 __global__ void init_stat_kernel(double* dstat, int* gate, int batch, int force) {
     int z = blockIdx.x * blockDim.x + threadIdx.x;
@@ -127,12 +46,16 @@ struct Rec {
     void run(int b0, int b1) {
         if (rc != BOBE_OK) return;
         int nb = b1 - b0;
-        if (nb == 1) {
-            int smem = (2 * NB * LLD + 2 * NB) * (int)sizeof(double);
-            cudaFuncSetAttribute(leaf_chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            leaf_chol_inv_kernel<<<dim3(1, 1, batch), 256, smem, stream>>>(fb.KB, fb.L, fb.Lt, fb.Linv, fb.U, fb.diag,
-                                                                         fb.dstat, fb.gate, npad, b0 * NB);
-            rc = check_launch("leaf_chol_inv_kernel");
+        if (nb <= 2) {  // leaf: one CTA per matrix does the whole 64- or 128-block in shared memory
+            LeafIO io{fb.KB, fb.L, fb.Lt, fb.Linv, fb.U, fb.diag, fb.dstat, fb.gate, npad, b0 * NB};
+            if (nb == 1) {
+                if ((rc = ensure_smem<leaf64_kernel>(LEAF64_SMEM)) != BOBE_OK) return;
+                leaf64_kernel<<<dim3(1, 1, batch), LEAF_THREADS, LEAF64_SMEM, stream>>>(io);
+            } else {
+                if ((rc = ensure_smem<leaf128_kernel>(LEAF128_SMEM)) != BOBE_OK) return;
+                leaf128_kernel<<<dim3(1, 1, batch), LEAF_THREADS, LEAF128_SMEM, stream>>>(io);
+            }
+            rc = check_launch("leaf kernel");
             return;
         }
         int mid = b0 + (nb + 1) / 2;

@@ -26,32 +26,25 @@ int32_t check_launch(const char* what) {
     return BOBE_OK;
 }
 
-template <class K>
-static int32_t ensure_smem(K kernel, int bytes) {
-    // idempotent and cheap; set on every call so that it holds for whichever device is current
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) {
-        set_error("cudaFuncSetAttribute(smem=%d): %s", bytes, cudaGetErrorString(e));
-        return BOBE_E_CUDA;
-    }
-    return BOBE_OK;
-}
-
 int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& a, int batch) {
     if (a.M <= 0 || a.N <= 0 || batch <= 0) return BOBE_OK;
     if ((a.K % 16) || (a.N % 2) || (a.lda % 2) || (a.ldb % 2) || (a.ldc % 2)) {
         set_error("gemm_nt: K must be a multiple of 16 and N/ld even (M=%d N=%d K=%d)", a.M, a.N, a.K);
         return BOBE_E_ARG;
     }
-    bool small = (a.M <= 64 || a.N <= 64);
+    // 128x128 tiles are the efficient ones, but the lower levels of the recursion are latency-bound chains of small
+    // products: when the big tiling cannot put two CTAs' worth of work on every SM, use 64x64 tiles (4x the CTAs,
+    // each finishing in well under half the time).
+    const int64_t big_ctas = (int64_t)((a.M + 127) / 128) * ((a.N + 127) / 128) * batch;
+    bool small = (a.M <= 64 || a.N <= 64) || big_ctas < 2 * 148;
     if (small) {
         using Cfg = CfgSmall;
-        if (int32_t rc = ensure_smem(gemm_nt_kernel<Cfg>, Cfg::SMEM_BYTES)) return rc;
+        if (int32_t rc = ensure_smem<gemm_nt_kernel<Cfg>>(Cfg::SMEM_BYTES)) return rc;
         dim3 grid((a.N + Cfg::BN - 1) / Cfg::BN, (a.M + Cfg::BM - 1) / Cfg::BM, batch);
         gemm_nt_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a);
     } else {
         using Cfg = CfgBig;
-        if (int32_t rc = ensure_smem(gemm_nt_kernel<Cfg>, Cfg::SMEM_BYTES)) return rc;
+        if (int32_t rc = ensure_smem<gemm_nt_kernel<Cfg>>(Cfg::SMEM_BYTES)) return rc;
         dim3 grid((a.N + Cfg::BN - 1) / Cfg::BN, (a.M + Cfg::BM - 1) / Cfg::BM, batch);
         gemm_nt_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a);
     }
@@ -66,7 +59,7 @@ int32_t launch_trmm_sumsq(cudaStream_t stream, const double* Linv, int npad, con
         set_error("trmm_sumsq: query chunk must be padded to %d", Cfg::BN);
         return BOBE_E_ARG;
     }
-    if (int32_t rc = ensure_smem(trmm_sumsq_kernel<Cfg>, Cfg::SMEM_BYTES)) return rc;
+    if (int32_t rc = ensure_smem<trmm_sumsq_kernel<Cfg>>(Cfg::SMEM_BYTES)) return rc;
     dim3 grid(rows_pad / Cfg::BN);
     trmm_sumsq_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(Linv, npad, Kstar, ldk, q_begin, M, kk,
                                                                          scale, standardised, var_out);

@@ -132,17 +132,12 @@ int32_t launch_kmat(cudaStream_t stream, int kind, const KmatArgs& a, int batch)
         return BOBE_E_ARG;
     }
     dim3 grid((unsigned)splits, (unsigned)row_tiles, (unsigned)batch);
-    cudaError_t e;
     if (kind == BOBE_KERNEL_RBF) {
-        e = cudaFuncSetAttribute(kmat_kernel<BOBE_KERNEL_RBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) kmat_kernel<BOBE_KERNEL_RBF><<<grid, 256, smem, stream>>>(a);
+        if (int32_t rc = ensure_smem<kmat_kernel<BOBE_KERNEL_RBF>>(smem)) return rc;
+        kmat_kernel<BOBE_KERNEL_RBF><<<grid, 256, smem, stream>>>(a);
     } else {
-        e = cudaFuncSetAttribute(kmat_kernel<BOBE_KERNEL_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) kmat_kernel<BOBE_KERNEL_MATERN52><<<grid, 256, smem, stream>>>(a);
-    }
-    if (e != cudaSuccess) {
-        set_error("kmat attr: %s", cudaGetErrorString(e));
-        return BOBE_E_CUDA;
+        if (int32_t rc = ensure_smem<kmat_kernel<BOBE_KERNEL_MATERN52>>(smem)) return rc;
+        kmat_kernel<BOBE_KERNEL_MATERN52><<<grid, 256, smem, stream>>>(a);
     }
     return check_launch("kmat_kernel");
 }

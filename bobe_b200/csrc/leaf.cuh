@@ -1,0 +1,264 @@
+// Leaves of the recursive factorisation: one CTA factorises AND inverts a 64x64 or a 128x128 diagonal block
+// entirely in shared memory.  The lower levels of the recursion are chains of tiny dependent steps; doing a
+// whole 128-block (two 64-leaves + the six 64^3 products between them) in one launch removes ~10 launches per
+// block from the critical path (see profiles/r01/README.md, "leaf fusion").
+#pragma once
+#include "common.cuh"
+
+namespace bobe {
+
+constexpr int SLD = 72;  // smem row stride (doubles) of every 64x64 operand: 16-byte aligned rows, and rows g, g+1 land
+                         // in different halves of the 32 banks, so LDS.128 fragment loads are conflict-free
+constexpr int LEAF_THREADS = 256;
+constexpr double REFINE_RATIO = 1e3;
+
+// ---- 64x64 Cholesky + inverse, register-blocked ----------------------------------------------------------
+// Thread (ty, tx) of a 16x16 grid owns A[ty+16a][tx+16b] and W[ty+16a][tx+16b] (a, b < 4) in REGISTERS for the
+// whole sweep.  Step j: the owners publish column j of A and row j of W to a double-buffered smem line (one
+// __syncthreads per step), every thread derives 1/d_j from the pivot and applies the rank-1 updates
+//   A[i][k] -= A[i][j] A[k][j] / a_jj   (k > j)          W[i][c] -= A[i][j] W[j][c] / a_jj   (i > j)
+// (W starts as I: Gauss-Jordan on L X = I).  Columns of A / rows of W stay unscaled until the end:
+// L[i][j] = A[i][j] / d_j, X[j][c] = W[j][c] / d_j.  A negative pivot gives NaN (rsqrt), never a trap.
+// In: A lower triangle (upper ignored).  Out: A = L (zero upper), W = L^-1 (zero upper), invd, dd (64 each).
+__device__ __forceinline__ void chol_inv_64(double* A, double* W, double* colb, double* rowb, double* invd,
+                                            double* dd) {
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    double ra[4][4], rw[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            int i = ty + 16 * a, k = tx + 16 * b;
+            ra[a][b] = A[i * SLD + k];
+            rw[a][b] = (i == k) ? 1.0 : 0.0;
+        }
+    for (int j = 0; j < 64; ++j) {
+        const int ja = j >> 4, jx = j & 15;
+        double* cb = colb + (j & 1) * 64;
+        double* rb = rowb + (j & 1) * 64;
+        if (tx == jx) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                double v = ra[a][0];
+                v = (ja == 1) ? ra[a][1] : v;
+                v = (ja == 2) ? ra[a][2] : v;
+                v = (ja == 3) ? ra[a][3] : v;
+                cb[ty + 16 * a] = v;
+            }
+        }
+        if (ty == jx) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                double v = rw[0][b];
+                v = (ja == 1) ? rw[1][b] : v;
+                v = (ja == 2) ? rw[2][b] : v;
+                v = (ja == 3) ? rw[3][b] : v;
+                rb[tx + 16 * b] = v;
+            }
+        }
+        __syncthreads();
+        const double ajj = cb[j];
+        // d = sqrt(a_jj) and 1/d to (near) correct rounding: one rsqrt + one Newton step each
+        double r0 = rsqrt(ajj);
+        double d0 = ajj * r0;
+        double d = fma(fma(-d0, d0, ajj), 0.5 * r0, d0);
+        double inv = fma(fma(-d, r0, 1.0), r0, r0);
+        if (tid == 0) {
+            invd[j] = inv;
+            dd[j] = d;
+        }
+        const double w = inv * inv;
+        double ai[4], ak[4], wj[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            int i = ty + 16 * a;
+            ai[a] = (i > j) ? cb[i] * w : 0.0;
+            int k = tx + 16 * a;
+            ak[a] = (k > j) ? cb[k] : 0.0;
+            wj[a] = rb[k];  // zero beyond column j (W stays lower triangular)
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                ra[a][b] = fma(-ai[a], ak[b], ra[a][b]);
+                rw[a][b] = fma(-ai[a], wj[b], rw[a][b]);
+            }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            int i = ty + 16 * a, k = tx + 16 * b;
+            A[i * SLD + k] = (k < i) ? ra[a][b] * invd[k] : (k == i ? dd[i] : 0.0);
+            W[i * SLD + k] = (k <= i) ? rw[a][b] * invd[i] : 0.0;
+        }
+    __syncthreads();
+}
+
+// ---- 64x64x64 product on smem operands with DMMA: C = alpha * A * op(B) + D -------------------------------
+// op(B)[k][j] = B[j][k] (BT, "NT") or B[k][j] (NN).  D may be null or alias C (each element is read and
+// written by the same thread).  8 warps: warp w owns rows 16*(w&3).., columns 32*(w>>2)...
+template <bool BT>
+__device__ __forceinline__ void mma64(const double* A, const double* B, double alpha, double* C, const double* D) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int r0 = (warp & 3) * 16, c0 = (warp >> 2) * 32;
+    double acc[2][4][2];
+#pragma unroll
+    for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+        for (int nf = 0; nf < 4; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
+#pragma unroll 2
+    for (int k0 = 0; k0 < 64; k0 += 8) {
+        double2 a[2], b[4];
+#pragma unroll
+        for (int mf = 0; mf < 2; ++mf)
+            a[mf] = *reinterpret_cast<const double2*>(A + (r0 + mf * 8 + g) * SLD + k0 + 2 * t);
+#pragma unroll
+        for (int nf = 0; nf < 4; ++nf) {
+            if (BT) {
+                b[nf] = *reinterpret_cast<const double2*>(B + (c0 + nf * 8 + g) * SLD + k0 + 2 * t);
+            } else {
+                b[nf].x = B[(k0 + 2 * t) * SLD + c0 + nf * 8 + g];
+                b[nf].y = B[(k0 + 2 * t + 1) * SLD + c0 + nf * 8 + g];
+            }
+        }
+#pragma unroll
+        for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+            for (int nf = 0; nf < 4; ++nf) dmma884(acc[mf][nf][0], acc[mf][nf][1], a[mf].x, b[nf].x);
+#pragma unroll
+        for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+            for (int nf = 0; nf < 4; ++nf) dmma884(acc[mf][nf][0], acc[mf][nf][1], a[mf].y, b[nf].y);
+    }
+#pragma unroll
+    for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+        for (int nf = 0; nf < 4; ++nf) {
+            int off = (r0 + mf * 8 + g) * SLD + c0 + nf * 8 + 2 * t;
+            double v0 = alpha * acc[mf][nf][0], v1 = alpha * acc[mf][nf][1];
+            if (D) {
+                double2 old = *reinterpret_cast<const double2*>(D + off);
+                v0 += old.x;
+                v1 += old.y;
+            }
+            *reinterpret_cast<double2*>(C + off) = make_double2(v0, v1);
+        }
+}
+
+struct LeafIO {
+    const double* KB;
+    double *L, *Lt, *Linv, *U, *diag, *dstat;
+    int* gate;
+    int npad, o;  // o = first row/column of the block
+};
+
+// global -> smem: 64x64 block at (row r0, col c0) of KB; lower_only zeroes the strict upper part
+__device__ __forceinline__ void leaf_load(double* S, const double* Kz, int npad, int r0, int c0, bool lower_only) {
+    for (int idx = threadIdx.x; idx < 64 * 64; idx += LEAF_THREADS) {
+        int r = idx >> 6, c = idx & 63;
+        S[r * SLD + c] = (!lower_only || c <= r) ? Kz[(int64_t)(r0 + r) * npad + c0 + c] : 0.0;
+    }
+}
+// smem block -> global at (r0, c0), plus its transpose into Gt at (c0, r0)
+__device__ __forceinline__ void leaf_store(const double* S, double* G, double* Gt, int npad, int r0, int c0) {
+    for (int idx = threadIdx.x; idx < 64 * 64; idx += LEAF_THREADS) {
+        int r = idx >> 6, c = idx & 63;
+        G[(int64_t)(r0 + r) * npad + c0 + c] = S[r * SLD + c];
+        Gt[(int64_t)(c0 + r) * npad + r0 + c] = S[c * SLD + r];
+    }
+}
+
+// running extreme pivots of this matrix (leaves of one matrix run in stream order: no atomics needed).
+// max/min pivot is a lower bound on cond(L); beyond REFINE_RATIO the panel solves get a correction step.
+__device__ __forceinline__ bool leaf_update_stats(const LeafIO& io, const double* dd, int count, int64_t z) {
+    __shared__ int s_gate;
+    if (threadIdx.x == 0) {
+        double lo = io.dstat[z * 2], hi = io.dstat[z * 2 + 1];
+        for (int i = 0; i < count; ++i) {
+            lo = fmin(lo, dd[i]);
+            hi = fmax(hi, dd[i]);
+        }
+        io.dstat[z * 2] = lo;
+        io.dstat[z * 2 + 1] = hi;
+        int gte = io.gate[z];
+        if (hi > REFINE_RATIO * lo) gte = 1;
+        io.gate[z] = gte;
+        s_gate = gte;
+    }
+    __syncthreads();
+    return s_gate != 0;
+}
+
+__global__ void __launch_bounds__(LEAF_THREADS) leaf64_kernel(LeafIO io) {
+    extern __shared__ __align__(16) double sm[];
+    double* A = sm;
+    double* W = A + 64 * SLD;
+    double* colb = W + 64 * SLD;  // [2][64]
+    double* rowb = colb + 128;    // [2][64]
+    double* invd = rowb + 128;    // [64]
+    double* dd = invd + 64;       // [64]
+    const int64_t z = blockIdx.z, zoff = z * (int64_t)io.npad * io.npad;
+    leaf_load(A, io.KB + zoff, io.npad, io.o, io.o, true);
+    __syncthreads();
+    chol_inv_64(A, W, colb, rowb, invd, dd);
+    leaf_store(A, io.L + zoff, io.Lt + zoff, io.npad, io.o, io.o);
+    leaf_store(W, io.Linv + zoff, io.U + zoff, io.npad, io.o, io.o);
+    if (threadIdx.x < 64) io.diag[z * io.npad + io.o + threadIdx.x] = dd[threadIdx.x];
+    leaf_update_stats(io, dd, 64, z);
+}
+constexpr int LEAF64_SMEM = (2 * 64 * SLD + 2 * 128 + 2 * 64) * 8;
+
+// 128x128 block = [A11 .; A21 A22]:
+//   (L11, X11) = chol_inv(A11);  L21 = A21 X11^T [+ gated correction];  A22 -= L21 L21^T;
+//   (L22, X22) = chol_inv(A22);  X21 = -(X22 L21) X11
+__global__ void __launch_bounds__(LEAF_THREADS) leaf128_kernel(LeafIO io) {
+    extern __shared__ __align__(16) double sm[];
+    double* B0 = sm;              // A11 -> L11
+    double* B1 = B0 + 64 * SLD;   // X11
+    double* B2 = B1 + 64 * SLD;   // A21 -> residual -> T
+    double* B3 = B2 + 64 * SLD;   // A22 -> L22
+    double* B4 = B3 + 64 * SLD;   // X22
+    double* B5 = B4 + 64 * SLD;   // L21 -> X21
+    double* colb = B5 + 64 * SLD;
+    double* rowb = colb + 128;
+    double* invd = rowb + 128;    // [128]
+    double* dd = invd + 128;      // [128]
+    const int64_t z = blockIdx.z, zoff = z * (int64_t)io.npad * io.npad;
+    const int o = io.o, npad = io.npad;
+    const double* Kz = io.KB + zoff;
+    leaf_load(B0, Kz, npad, o, o, true);
+    leaf_load(B2, Kz, npad, o + 64, o, false);
+    leaf_load(B3, Kz, npad, o + 64, o + 64, true);
+    __syncthreads();
+    chol_inv_64(B0, B1, colb, rowb, invd, dd);
+    const bool refine = leaf_update_stats(io, dd, 64, z);
+    mma64<true>(B2, B1, 1.0, B5, nullptr);  // L21 = A21 X11^T
+    __syncthreads();
+    if (refine) {  // same correction as the recursion applies to its panel solves (factor.cu)
+        mma64<true>(B5, B0, -1.0, B2, B2);  // R = A21 - L21 L11^T
+        __syncthreads();
+        mma64<true>(B2, B1, 1.0, B5, B5);   // L21 += R X11^T
+        __syncthreads();
+    }
+    mma64<true>(B5, B5, -1.0, B3, B3);  // A22 -= L21 L21^T
+    __syncthreads();
+    chol_inv_64(B3, B4, colb, rowb, invd + 64, dd + 64);
+    leaf_update_stats(io, dd + 64, 64, z);
+    mma64<false>(B4, B5, 1.0, B2, nullptr);  // T = X22 L21
+    leaf_store(B5, io.L + zoff, io.Lt + zoff, npad, o + 64, o);  // L21 (B5 is read-only in this phase)
+    __syncthreads();
+    mma64<false>(B2, B1, -1.0, B5, nullptr);  // X21 = -T X11
+    __syncthreads();
+    leaf_store(B0, io.L + zoff, io.Lt + zoff, npad, o, o);
+    leaf_store(B3, io.L + zoff, io.Lt + zoff, npad, o + 64, o + 64);
+    leaf_store(B1, io.Linv + zoff, io.U + zoff, npad, o, o);
+    leaf_store(B4, io.Linv + zoff, io.U + zoff, npad, o + 64, o + 64);
+    leaf_store(B5, io.Linv + zoff, io.U + zoff, npad, o + 64, o);
+    if (threadIdx.x < 128) io.diag[z * npad + o + threadIdx.x] = dd[threadIdx.x];
+}
+constexpr int LEAF128_SMEM = (6 * 64 * SLD + 2 * 128 + 2 * 128) * 8;
+
+}  // namespace bobe

@@ -7,7 +7,9 @@
 //   dK_ik/d log l_j = G_ik s_ikj,  s_ikj = ((x_ij - x_kj)/l_j)^2,
 //       G = K0 (RBF);  G = kv 5/3 (1 + sqrt5 r) exp(-sqrt5 r), 0 where the 1e-30 clamp is active (Matern-5/2)
 //   dK/d log kv = K0 (the noise-free kernel);  noise is never optimised;  tausq has no kernel gradient.
+#include <algorithm>
 #include <cmath>
+#include <mutex>
 
 #include "gemm_nt.cuh"
 #include "kernels.cuh"
@@ -160,6 +162,39 @@ __global__ void mll_finish_kernel(const double* __restrict__ partial, int ntiles
     if (j == 0) val[z] = -0.5 * quad[z] - logdet[z] - 0.5 * (double)n * 1.8378770664093454835606594728112;
 }
 
+constexpr int MLL_MAX_STREAMS = 4;
+
+// Internal side streams, created once per device.  They carry no state between calls: every call forks them
+// from the caller's stream and joins them back before returning.
+struct StreamPool {
+    cudaStream_t streams[MLL_MAX_STREAMS];
+    cudaEvent_t fork, join[MLL_MAX_STREAMS];
+};
+static StreamPool* stream_pool() {
+    static std::mutex mu;
+    static StreamPool* pools[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+        set_error("mll_grad: cudaGetDevice failed");
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    if (!pools[dev]) {
+        StreamPool* p = new StreamPool();
+        bool ok = cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < MLL_MAX_STREAMS && ok; ++i)
+            ok = cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&p->join[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) {
+            set_error("mll_grad: could not create internal streams: %s", cudaGetErrorString(cudaGetLastError()));
+            delete p;
+            return nullptr;
+        }
+        pools[dev] = p;
+    }
+    return pools[dev];
+}
+
 struct MllLayout {
     int64_t npad, tiles, ntile_pairs;
     int64_t off_ls, off_kv, off_KB, off_L, off_Lt, off_Linv, off_U, off_Q, off_diag, off_stat, off_z, off_alpha, off_logdet,
@@ -187,7 +222,7 @@ static MllLayout mll_layout(int64_t n, int64_t d, int64_t R) {
     l.off_Q = take(R * factor_q_elems(l.npad));
     l.off_diag = take(R * l.npad);
     l.off_stat = take(3 * R);
-    l.off_z = take(solve_ws_doubles(l.npad, R));
+    l.off_z = take((3 * R + MLL_MAX_STREAMS) * l.npad);
     l.off_alpha = take(R * l.npad);
     l.off_logdet = take(R);
     l.off_quad = take(R);
@@ -227,47 +262,73 @@ extern "C" int32_t bobe_mll_grad_batched(void* stream_, int32_t kind, const doub
         return BOBE_E_WORKSPACE;
     }
     double *ls = w + l.off_ls, *kv = w + l.off_kv;
-    FactorBuffers fb{w + l.off_KB, w + l.off_L, w + l.off_Lt, w + l.off_Linv, w + l.off_U, w + l.off_Q, w + l.off_diag,
-                     w + l.off_stat, (int*)(w + l.off_stat + 2 * R), 0};
-    double *zws = w + l.off_z, *alpha = w + l.off_alpha, *logdet = w + l.off_logdet, *quad = w + l.off_quad,
-           *partial = w + l.off_partial;
     const int npad = (int)l.npad;
+    const int64_t m2 = (int64_t)npad * npad, qel = factor_q_elems(npad);
 
     int64_t tot = R * d > R ? R * d : R;
     exp_params_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(log_params, R, P, d, has_kv, fixed_kv, ls, kv);
     if (int32_t rc = check_launch("exp_params_kernel")) return rc;
 
-    KmatArgs ka{};
-    ka.xa = X; ka.xb = X; ka.ls = ls; ka.kv_ptr = kv; ka.out = fb.KB;
-    ka.n1 = n; ka.n2 = n; ka.d = d; ka.ldo = npad; ka.rows_pad = npad; ka.cols_pad = npad;
-    ka.store_rows = npad; ka.store_cols = npad; ka.vec_ok = 1;
-    ka.ls_stride = d; ka.out_stride = (int64_t)npad * npad; ka.noise = noise; ka.add_noise = 1; ka.pad_identity = 1;
-    if (int32_t rc = launch_kmat(stream, kind, ka, (int)R)) return rc;
-    if (int32_t rc = factor_recursive(stream, fb, npad, (int)R)) return rc;
-    SolveArgs sa{kind, X, ls, kv, d, noise};
-    if (int32_t rc = launch_solve_vectors(stream, fb, sa, y, n, npad, (int)R, zws, alpha, logdet, quad, info)) return rc;
-    if (int32_t rc = launch_kinv(stream, fb, npad, (int)R)) return rc;
+    // The recursion is a chain of ~230 dependent launches whose lower levels cannot fill 148 SMs.  The restarts are
+    // therefore cut into sub-batches that run the whole chain on separate internal streams (forked from and
+    // joined to the caller's stream with events): one sub-batch's latency-bound leaves and small products overlap
+    // with another's large tensor-core products.
+    const int S = (int)std::min<int64_t>(MLL_MAX_STREAMS, std::max<int64_t>(1, R / 4));
+    StreamPool* pool = nullptr;
+    if (S > 1) {
+        pool = stream_pool();
+        if (!pool) return BOBE_E_CUDA;
+        if (cudaEventRecord(pool->fork, stream) != cudaSuccess) {
+            set_error("mll_grad: event record failed");
+            return BOBE_E_CUDA;
+        }
+    }
+    int32_t rc_all = BOBE_OK;
+    for (int si = 0; si < S && rc_all == BOBE_OK; ++si) {
+        const int64_t r0 = si * R / S, r1 = (si + 1) * R / S, Rs = r1 - r0;
+        cudaStream_t st = (S > 1) ? pool->streams[si] : stream;
+        if (S > 1) cudaStreamWaitEvent(st, pool->fork, 0);
+        rc_all = [&]() -> int32_t {
+            FactorBuffers fb{w + l.off_KB + r0 * m2, w + l.off_L + r0 * m2, w + l.off_Lt + r0 * m2,
+                             w + l.off_Linv + r0 * m2, w + l.off_U + r0 * m2, w + l.off_Q + r0 * qel,
+                             w + l.off_diag + r0 * npad, w + l.off_stat + 2 * r0, (int*)(w + l.off_stat + 2 * R) + r0, 0};
+            double* zws = w + l.off_z + (3 * r0 + si) * npad;  // each sub-batch: own padded y + 3 vectors per restart
+            double *alpha = w + l.off_alpha + r0 * npad, *logdet = w + l.off_logdet + r0, *quad = w + l.off_quad + r0;
+            double* partial = w + l.off_partial + r0 * l.ntile_pairs * (d + 1);
+            const double *ls_s = ls + r0 * d, *kv_s = kv + r0;
 
-    int smem = (int)((2 * d * GLD + 2 * GT + 8 * (d + 1)) * sizeof(double));
-    dim3 grid((unsigned)l.ntile_pairs, (unsigned)R);
-    cudaError_t e;
-    if (kind == BOBE_KERNEL_RBF) {
-        e = cudaFuncSetAttribute(mll_grad_tile_kernel<BOBE_KERNEL_RBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess)
-            mll_grad_tile_kernel<BOBE_KERNEL_RBF><<<grid, 256, smem, stream>>>(X, n, (int)d, ls, kv, fb.KB, npad, alpha,
-                                                                             has_kv, (int)P, partial, (int)l.ntile_pairs);
-    } else {
-        e = cudaFuncSetAttribute(mll_grad_tile_kernel<BOBE_KERNEL_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess)
-            mll_grad_tile_kernel<BOBE_KERNEL_MATERN52><<<grid, 256, smem, stream>>>(X, n, (int)d, ls, kv, fb.KB, npad, alpha,
-                                                                                  has_kv, (int)P, partial, (int)l.ntile_pairs);
+            KmatArgs ka{};
+            ka.xa = X; ka.xb = X; ka.ls = ls_s; ka.kv_ptr = kv_s; ka.out = fb.KB;
+            ka.n1 = n; ka.n2 = n; ka.d = d; ka.ldo = npad; ka.rows_pad = npad; ka.cols_pad = npad;
+            ka.store_rows = npad; ka.store_cols = npad; ka.vec_ok = 1;
+            ka.ls_stride = d; ka.out_stride = m2; ka.noise = noise; ka.add_noise = 1; ka.pad_identity = 1;
+            if (int32_t rc = launch_kmat(st, kind, ka, (int)Rs)) return rc;
+            if (int32_t rc = factor_recursive(st, fb, npad, (int)Rs)) return rc;
+            SolveArgs sa{kind, X, ls_s, kv_s, d, noise};
+            if (int32_t rc = launch_solve_vectors(st, fb, sa, y, n, npad, (int)Rs, zws, alpha, logdet, quad, info + r0))
+                return rc;
+            if (int32_t rc = launch_kinv(st, fb, npad, (int)Rs)) return rc;
+
+            int smem = (int)((2 * d * GLD + 2 * GT + 8 * (d + 1)) * sizeof(double));
+            dim3 grid((unsigned)l.ntile_pairs, (unsigned)Rs);
+            if (kind == BOBE_KERNEL_RBF) {
+                if (int32_t rc = ensure_smem<mll_grad_tile_kernel<BOBE_KERNEL_RBF>>(smem)) return rc;
+                mll_grad_tile_kernel<BOBE_KERNEL_RBF><<<grid, 256, smem, st>>>(
+                    X, n, (int)d, ls_s, kv_s, fb.KB, npad, alpha, has_kv, (int)P, partial, (int)l.ntile_pairs);
+            } else {
+                if (int32_t rc = ensure_smem<mll_grad_tile_kernel<BOBE_KERNEL_MATERN52>>(smem)) return rc;
+                mll_grad_tile_kernel<BOBE_KERNEL_MATERN52><<<grid, 256, smem, st>>>(
+                    X, n, (int)d, ls_s, kv_s, fb.KB, npad, alpha, has_kv, (int)P, partial, (int)l.ntile_pairs);
+            }
+            if (int32_t rc = check_launch("mll_grad_tile_kernel")) return rc;
+            mll_finish_kernel<<<(unsigned)Rs, 256, 0, st>>>(partial, (int)l.ntile_pairs, (int)d, (int)P, has_kv, n, logdet,
+                                                           quad, info + r0, val + r0, grad + r0 * P);
+            return check_launch("mll_finish_kernel");
+        }();
+        if (S > 1) {  // join (also on failure, so that the caller's stream never runs ahead of stray work)
+            cudaEventRecord(pool->join[si], st);
+            cudaStreamWaitEvent(stream, pool->join[si], 0);
+        }
     }
-    if (e != cudaSuccess) {
-        set_error("mll_grad attr: %s", cudaGetErrorString(e));
-        return BOBE_E_CUDA;
-    }
-    if (int32_t rc = check_launch("mll_grad_tile_kernel")) return rc;
-    mll_finish_kernel<<<(unsigned)R, 256, 0, stream>>>(partial, (int)l.ntile_pairs, (int)d, (int)P, has_kv, n, logdet,
-                                                      quad, info, val, grad);
-    return check_launch("mll_finish_kernel");
+    return rc_all;
 }

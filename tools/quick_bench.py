@@ -31,4 +31,23 @@ for R in (8, 64):
     lp = torch.log(torch.cat([torch.ones(R, d, dtype=torch.float64, device=dev) * (0.5 + torch.rand(R, d, dtype=torch.float64, device=dev)), torch.ones(R, 1, dtype=torch.float64, device=dev)], 1))
     t = ev_time(lambda: ops.mll_grad_batched("matern", X, y, lp, True, 1.0, 1e-8), iters=2)
     fl = R * (n ** 3 + n * n * (5 * d + 10 + 8))
-    print(f"mll+grad R={R}: {t:.3f} ms -> {R/t*1e3:.1f} evals/s, {fl/t/1e9:.2f} TFLOP/s algorithmic")
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(5): ops.mll_grad_batched("matern", X, y, lp, True, 1.0, 1e-8)
+    t_enq = (time.perf_counter() - t0) / 5 * 1e3; torch.cuda.synchronize()
+    print(f"mll+grad R={R}: {t:.3f} ms -> {R/t*1e3:.1f} evals/s, {fl/t/1e9:.2f} TFLOP/s algorithmic (host enqueue {t_enq:.3f} ms)")
+
+# CUDA-graph replay of the whole batched log-ML+grad call (the C-ABI is capture-safe: no sync, no allocation)
+for R in (1, 8, 64):
+    lp = torch.log(torch.cat([torch.ones(R, d, dtype=torch.float64, device=dev) * (0.5 + torch.rand(R, d, dtype=torch.float64, device=dev)), torch.ones(R, 1, dtype=torch.float64, device=dev)], 1))
+    ops.mll_grad_batched("matern", X, y, lp, True, 1.0, 1e-8); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        ops.mll_grad_batched("matern", X, y, lp, True, 1.0, 1e-8)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            out = ops.mll_grad_batched("matern", X, y, lp, True, 1.0, 1e-8)
+    torch.cuda.synchronize()
+    t = ev_time(lambda: g.replay(), iters=5)
+    t2 = ev_time(lambda: ops.mll_grad_batched("matern", X, y, lp, True, 1.0, 1e-8), iters=5)
+    print(f"R={R}: graph replay {t:.3f} ms vs eager {t2:.3f} ms; val[0] {out[0][0].item():.6f}")
