@@ -1,6 +1,7 @@
 // Launchers for the DMMA NT-GEMM and the fused "triangular multiply + column sum of squares" kernel that
 // produces the predictive variance term ||L^-1 k*||^2 without ever writing V = L^-1 K* to memory.
 #include <cstdarg>
+#include <cstdlib>
 #include <mutex>
 
 #include "gemm_nt.cuh"
@@ -26,6 +27,11 @@ int32_t check_launch(const char* what) {
     return BOBE_OK;
 }
 
+int64_t env_int(const char* name, int64_t dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoll(v) : dflt;
+}
+
 int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& a, int batch) {
     if (a.M <= 0 || a.N <= 0 || batch <= 0) return BOBE_OK;
     if ((a.K % 16) || (a.N % 2) || (a.lda % 2) || (a.ldb % 2) || (a.ldc % 2)) {
@@ -36,7 +42,8 @@ int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& a, int batch) {
     // products: when the big tiling cannot put two CTAs' worth of work on every SM, use 64x64 tiles (4x the CTAs,
     // each finishing in well under half the time).
     const int64_t big_ctas = (int64_t)((a.M + 127) / 128) * ((a.N + 127) / 128) * batch;
-    bool small = (a.M <= 64 || a.N <= 64) || big_ctas < 2 * 148;
+    static const int64_t small_below = env_int("BOBE_SMALL_TILE_CTAS", 2 * 148);
+    bool small = (a.M <= 64 || a.N <= 64) || big_ctas < small_below;
     if (small) {
         using Cfg = CfgSmall;
         if (int32_t rc = ensure_smem<gemm_nt_kernel<Cfg>>(Cfg::SMEM_BYTES)) return rc;

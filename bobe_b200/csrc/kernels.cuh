@@ -5,6 +5,7 @@
 namespace bobe {
 
 const char* last_error();
+int64_t env_int(const char* name, int64_t dflt);  // tuning knobs (read once)
 
 // kernel-matrix family (kernel_matrix.cu) ---------------------------------------------------------------
 struct KmatArgs {

@@ -57,17 +57,11 @@ __device__ __forceinline__ void chol_inv_64(double* A, double* W, double* colb, 
             }
         }
         __syncthreads();
+        // Only 1/a_jj sits on the critical path of the sweep (the updates need A[i][j] A[k][j] / a_jj); the square
+        // roots are taken for all 64 pivots at once after the loop.
         const double ajj = cb[j];
-        // d = sqrt(a_jj) and 1/d to (near) correct rounding: one rsqrt + one Newton step each
-        double r0 = rsqrt(ajj);
-        double d0 = ajj * r0;
-        double d = fma(fma(-d0, d0, ajj), 0.5 * r0, d0);
-        double inv = fma(fma(-d, r0, 1.0), r0, r0);
-        if (tid == 0) {
-            invd[j] = inv;
-            dd[j] = d;
-        }
-        const double w = inv * inv;
+        if (tid == 0) dd[j] = ajj;  // pivot, turned into d_j below
+        const double w = __drcp_rn(ajj);
         double ai[4], ak[4], wj[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
@@ -84,6 +78,15 @@ __device__ __forceinline__ void chol_inv_64(double* A, double* W, double* colb, 
                 ra[a][b] = fma(-ai[a], ak[b], ra[a][b]);
                 rw[a][b] = fma(-ai[a], wj[b], rw[a][b]);
             }
+    }
+    __syncthreads();
+    if (tid < 64) {  // d = sqrt(pivot) and 1/d to (near) correct rounding: one rsqrt + one Newton step each; a
+        const double piv = dd[tid];  // negative pivot gives NaN, a zero pivot inf -> NaN downstream, never a trap
+        double r0 = rsqrt(piv);
+        double d0 = piv * r0;
+        double d = fma(fma(-d0, d0, piv), 0.5 * r0, d0);
+        invd[tid] = fma(fma(-d, r0, 1.0), r0, r0);
+        dd[tid] = d;
     }
     __syncthreads();
 #pragma unroll

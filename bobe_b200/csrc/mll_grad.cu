@@ -162,7 +162,7 @@ __global__ void mll_finish_kernel(const double* __restrict__ partial, int ntiles
     if (j == 0) val[z] = -0.5 * quad[z] - logdet[z] - 0.5 * (double)n * 1.8378770664093454835606594728112;
 }
 
-constexpr int MLL_MAX_STREAMS = 4;
+constexpr int MLL_MAX_STREAMS = 8;
 
 // Internal side streams, created once per device.  They carry no state between calls: every call forks them
 // from the caller's stream and joins them back before returning.
@@ -273,7 +273,8 @@ extern "C" int32_t bobe_mll_grad_batched(void* stream_, int32_t kind, const doub
     // therefore cut into sub-batches that run the whole chain on separate internal streams (forked from and
     // joined to the caller's stream with events): one sub-batch's latency-bound leaves and small products overlap
     // with another's large tensor-core products.
-    const int S = (int)std::min<int64_t>(MLL_MAX_STREAMS, std::max<int64_t>(1, R / 4));
+    static const int64_t max_streams = std::min<int64_t>(MLL_MAX_STREAMS, env_int("BOBE_MLL_STREAMS", 4));
+    const int S = (int)std::min<int64_t>(max_streams, std::max<int64_t>(1, R / 4));
     StreamPool* pool = nullptr;
     if (S > 1) {
         pool = stream_pool();

@@ -43,9 +43,11 @@ def test_gp_fitting(optimizer):  # tests/test_gp.py:58-89 + the optimiser must a
     result = gp.fit(maxiter=200, x0=None)
     assert result["mll"] is not None and np.isfinite(result["mll"]) and result["mll"] >= start - 1e-9
     assert result["params"].shape == (3,)
-    ls_before = gp.lengthscales.copy()
     gp.update_hyperparams(result["params"])  # fit does not apply the parameters itself (BOBE/pool.py:292)
-    assert not np.allclose(gp.lengthscales, ls_before)
+    assert np.allclose(gp.lengthscales, np.exp(result["params"][:2]))
+    # (with these reference settings the optimum sits on the l = 5 bound with kv ~ 800, cond(K) > 1e12; whether
+    # L-BFGS-B reports CONVERGENCE or ABNORMAL there is rounding-noise dependent, and the reference's acceptance rule
+    # (BOBE/optim.py:340) keeps the start point in the latter case - both outcomes are legitimate)
     # scipy returns the minimiser itself; the reference's Adam loop returns the parameters AFTER the last step
     # together with the best value seen (BOBE/optim.py:146-159), so the two can differ slightly there
     assert np.isclose(-gp.neg_mll(result["params"]), result["mll"], rtol=1e-9 if optimizer == "scipy" else 1e-2)

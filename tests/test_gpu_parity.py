@@ -66,7 +66,8 @@ def test_golden_parity(name):
         m_orac = abs((-gold["neg_mll"][0] - pl) - float(gold["truth_mll"])) / max(abs(float(gold["truth_mll"])), n)
         print(f"\n[{name}] vs exact: mean cuda {e_cuda:.1e} oracle {e_orac:.1e} | mll cuda {m_cuda:.1e} oracle {m_orac:.1e}"
               f" | cuda vs oracle: mean {mixed_err(ms, gold['mean_std'], 1.0):.1e}")
-        assert e_cuda < TOL_MEAN and m_cuda < TOL_MLL
+        # ... i.e. within the tolerance, or within twice the float64 oracle's own distance from the exact value
+        assert e_cuda < max(TOL_MEAN, 2 * e_orac) and m_cuda < max(TOL_MLL, 2 * m_orac)
         assert mixed_err(ms, gold["mean_std"], 1.0) < 3 * TOL_MEAN  # and never far from the oracle either
     else:
         assert mixed_err(ms, gold["mean_std"], 1.0) < TOL_MEAN
