@@ -65,14 +65,60 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// ---- branch-free FP64 elementary functions for the kernel builds -----------------------------------------------
+// The CUDA math library's exp()/sqrt() carry special-case paths (denormals, overflow, NaN) behind branches and
+// CALLs; the kernel builds only ever see x <= 0 resp. q >= 1e-30, so the straight-line cores suffice.  Both are
+// accurate to ~1 ulp (Cody-Waite reduction + degree-13 Taylor on |r| <= ln2/2; rsqrt seed + 2 Goldschmidt steps +
+// a final residual correction).
+
+// exp(x) for x <= 0.  Results below 2^-1021 (x < -707.7) are flushed to 0.
+__device__ __forceinline__ double exp_nonpos(double x) {
+    const double SHIFT = 6755399441055744.0;  // 1.5 * 2^52: rounds x*log2(e) to an integer in the low word
+    double t = fma(x, 1.4426950408889634074, SHIFT);
+    int n = __double2loint(t);
+    double fn = t - SHIFT;
+    double r = fma(fn, -6.93147180559945286227e-01, x);   // ln2 (hi)
+    r = fma(fn, -2.31904681384629955842e-17, r);          // ln2 (lo)
+    double p = 1.6059043836821613e-10;                     // 1/13!
+    p = fma(p, r, 2.0876756987868099e-09);                 // 1/12!
+    p = fma(p, r, 2.5052108385441719e-08);                 // 1/11!
+    p = fma(p, r, 2.7557319223985891e-07);                 // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);                 // 1/9!
+    p = fma(p, r, 2.4801587301587302e-05);                 // 1/8!
+    p = fma(p, r, 1.9841269841269841e-04);                 // 1/7!
+    p = fma(p, r, 1.3888888888888889e-03);                 // 1/6!
+    p = fma(p, r, 8.3333333333333332e-03);                 // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);                 // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);                 // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    double res = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));  // p * 2^n, n in [-1021, 0]
+    return x < -707.7 ? 0.0 : res;
+}
+
+// sqrt(q) for normal positive q.
+__device__ __forceinline__ double sqrt_pos(double q) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(q));  // MUFU.RSQ64H seed, ~2^-20 relative
+    double g = q * y, h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    return fma(fma(-g, g, q), h, g);  // residual correction: g + (q - g^2) / (2 g)
+}
+
 // kernel value from the squared scaled distance q (BOBE/gp.py:149-151 and :161-165)
 template <int KIND>
 __device__ __forceinline__ double kernel_from_q(double q, double kv) {
     if (KIND == BOBE_KERNEL_RBF) {
-        return kv * exp(-0.5 * q);
+        return kv * exp_nonpos(-0.5 * q);
     } else {
-        double r = sqrt(q < 1e-30 ? 1e-30 : q);
-        double e = exp(-SQRT5 * r);
+        double r = sqrt_pos(q < 1e-30 ? 1e-30 : q);
+        double e = exp_nonpos(-SQRT5 * r);
         double poly = 1.0 + r * (SQRT5 + r * (5.0 / 3.0));
         return kv * poly * e;
     }

@@ -99,12 +99,12 @@ __global__ void __launch_bounds__(256) mll_grad_tile_kernel(const double* __rest
             if (row < n && col < n) {
                 w = wsym * (sai[ty * 4 + i] * sak[tx * 4 + j] - Ki[row * npad + col]);
                 if (KIND == BOBE_KERNEL_RBF) {
-                    k0v = kv * exp(-0.5 * q[i][j]);
+                    k0v = kv * exp_nonpos(-0.5 * q[i][j]);
                     g = k0v;
                 } else {
                     bool clamped = q[i][j] < 1e-30;
-                    double r = sqrt(clamped ? 1e-30 : q[i][j]);
-                    double e = exp(-SQRT5 * r);
+                    double r = sqrt_pos(clamped ? 1e-30 : q[i][j]);
+                    double e = exp_nonpos(-SQRT5 * r);
                     k0v = kv * (1.0 + r * (SQRT5 + r * (5.0 / 3.0))) * e;
                     g = clamped ? 0.0 : kv * (5.0 / 3.0) * (1.0 + SQRT5 * r) * e;
                 }

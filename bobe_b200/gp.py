@@ -356,19 +356,31 @@ class GP:
             self._ensure_factor()
 
     # ---- prediction ------------------------------------------------------------------------------------
+    _PIPE_ROWS = 8 * 148 * 128  # host-side pipelining granularity: 8 device chunks of bobe_predict
+
     def _predict(self, x, want_mean, want_var, standardised):
         as_t = _is_t(x)
         self._ensure_factor()
+        if self.train_x.shape[0] == 0:
+            raise ValueError("GP has no training points")
+        if not (as_t and x.is_cuda):
+            xh = x if as_t else torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64)))
+            if xh.dim() == 1:
+                xh = xh[None, :]
+            if xh.shape[1] != self.ndim:
+                raise ValueError(f"query points must have {self.ndim} columns")
+            if xh.shape[0] > self._PIPE_ROWS:
+                mean, var = self._predict_host_pipelined(xh.to(torch.float64), want_mean, want_var, standardised)
+                if not as_t:
+                    mean = mean.numpy() if mean is not None else None
+                    var = var.numpy() if var is not None else None
+                return mean, var
         xq = _to_dev(x, self.device)
         if xq.dim() == 1:
             xq = xq[None, :]
         if xq.shape[1] != self.ndim:
             raise ValueError(f"query points must have {self.ndim} columns")
-        if self.train_x.shape[0] == 0:
-            raise ValueError("GP has no training points")
-        mean, var = ops.predict(self.kernel_name, self._X_dev, self._ls_dev, float(self.kernel_variance),
-                                float(self.noise), self._Linv_dev, self._alpha_dev, xq, float(self.y_mean),
-                                float(self.y_std), want_mean, want_var, standardised)
+        mean, var = self._predict_dev(xq, want_mean, want_var, standardised)
         if not as_t:
             mean = mean.cpu().numpy() if mean is not None else None
             var = var.cpu().numpy() if var is not None else None
@@ -376,6 +388,42 @@ class GP:
             mean = mean.cpu() if mean is not None else None
             var = var.cpu() if var is not None else None
         return mean, var
+
+    def _predict_dev(self, xq, want_mean, want_var, standardised):
+        return ops.predict(self.kernel_name, self._X_dev, self._ls_dev, float(self.kernel_variance),
+                           float(self.noise), self._Linv_dev, self._alpha_dev, xq, float(self.y_mean),
+                           float(self.y_std), want_mean, want_var, standardised)
+
+    def _predict_host_pipelined(self, xh, want_mean, want_var, standardised):
+        """Large host-resident query sets: the H2D copy of block i+1 (copy stream, double-buffered staging) overlaps
+        with the kernels of block i; results return through pinned buffers.  Arithmetic identical to one big call
+        (queries are independent)."""
+        dev = self.device
+        M, d = xh.shape
+        rows = self._PIPE_ROWS
+        comp = torch.cuda.current_stream(dev)
+        copy = torch.cuda.Stream(dev)
+        stage = [torch.empty((rows, d), dtype=torch.float64, device=dev) for _ in range(2)]
+        copied = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+        mean_h = torch.empty(M, dtype=torch.float64).pin_memory() if want_mean else None
+        var_h = torch.empty(M, dtype=torch.float64).pin_memory() if want_var else None
+        for i, s in enumerate(range(0, M, rows)):
+            e, b = min(M, s + rows), i & 1
+            with torch.cuda.stream(copy):
+                if i >= 2:
+                    copy.wait_event(freed[b])
+                stage[b][: e - s].copy_(xh[s:e], non_blocking=True)
+                copied[b].record(copy)
+            comp.wait_event(copied[b])
+            mean, var = self._predict_dev(stage[b][: e - s], want_mean, want_var, standardised)
+            freed[b].record(comp)
+            if want_mean:
+                mean_h[s:e].copy_(mean, non_blocking=True)
+            if want_var:
+                var_h[s:e].copy_(var, non_blocking=True)
+        comp.synchronize()
+        return mean_h, var_h
 
     def predict_mean_single(self, x):
         """BOBE/gp.py:450-457 -- un-standardised mean, scalar."""
