@@ -23,7 +23,7 @@ SIGNATURES = {
     "bobe_abi_version": (_i32, []),
     "bobe_npad": (_i64, [_i64]),
     "bobe_kernel_matrix": (_i32, [_vp, _i32, _vp, _i64, _vp, _i64, _i64, _vp, _f64, _f64, _i32, _vp, _i64]),
-    "bobe_factorize_workspace_bytes": (_i64, [_i64, _i64]),
+    "bobe_factorize_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "bobe_factorize": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _vp, _vp, _f64, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
                               _vp, _i64]),
     "bobe_mll_grad_workspace_bytes": (_i64, [_i64, _i64, _i64]),

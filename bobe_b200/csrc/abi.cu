@@ -206,11 +206,12 @@ extern "C" int32_t bobe_kernel_matrix(void* stream, int32_t kind, const double* 
 // ---- factorize ------------------------------------------------------------------------------------------
 namespace {
 struct FactorLayout {
-    double *KB, *L, *Lt, *Linv, *U, *Q, *diag, *stat, *z, *alpha;
+    double *KB, *L, *Lt, *Linv, *U, *Q, *diag, *stat, *z, *alpha, *xs;
     int64_t bytes;
     bool fits;
 };
-FactorLayout factor_layout(void* ws, int64_t ws_bytes, int64_t n, int64_t batch, bool need_L, bool need_Linv) {
+FactorLayout factor_layout(void* ws, int64_t ws_bytes, int64_t n, int64_t d, int64_t batch, bool need_L,
+                           bool need_Linv) {
     int64_t npad = npad_of(n), m2 = npad * npad;
     Carver c(ws);
     FactorLayout l{};
@@ -224,15 +225,16 @@ FactorLayout factor_layout(void* ws, int64_t ws_bytes, int64_t n, int64_t batch,
     l.stat = c.take(3 * batch);
     l.z = c.take(solve_ws_doubles(npad, batch));
     l.alpha = c.take(batch * npad);
+    l.xs = c.take(batch * d * npad);
     l.bytes = c.bytes();
     l.fits = ws ? c.fits(ws, ws_bytes) : false;
     return l;
 }
 }  // namespace
 
-extern "C" int64_t bobe_factorize_workspace_bytes(int64_t n, int64_t batch) {
-    if (n <= 0 || batch <= 0) return 0;
-    return factor_layout(nullptr, 0, n, batch, true, true).bytes;
+extern "C" int64_t bobe_factorize_workspace_bytes(int64_t n, int64_t d, int64_t batch) {
+    if (n <= 0 || d <= 0 || batch <= 0) return 0;
+    return factor_layout(nullptr, 0, n, d, batch, true, true).bytes;
 }
 
 extern "C" int32_t bobe_factorize(void* stream_, int32_t kind, const double* X, const double* y, int64_t n, int64_t d,
@@ -244,7 +246,7 @@ extern "C" int32_t bobe_factorize(void* stream_, int32_t kind, const double* X, 
         set_error("factorize: bad arguments");
         return BOBE_E_ARG;
     }
-    FactorLayout l = factor_layout(ws, ws_bytes, n, batch, L == nullptr, Linv == nullptr);
+    FactorLayout l = factor_layout(ws, ws_bytes, n, d, batch, L == nullptr, Linv == nullptr);
     if (!l.fits) {
         set_error("factorize: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)l.bytes);
         return BOBE_E_WORKSPACE;
@@ -255,24 +257,27 @@ extern "C" int32_t bobe_factorize(void* stream_, int32_t kind, const double* X, 
     }
     const int npad = (int)npad_of(n);
     FactorBuffers fb{l.KB, L ? L : l.L, l.Lt, Linv ? Linv : l.Linv, l.U, l.Q, l.diag, l.stat, (int*)(l.stat + 2 * batch), 0};
+    if (int32_t rc = launch_prescale(stream, X, n, d, ls, d, l.xs, npad, d * (int64_t)npad, (int)batch)) return rc;
     KmatArgs ka{};
     ka.xa = X; ka.xb = X; ka.ls = ls; ka.kv_ptr = kv; ka.out = fb.KB;
+    ka.xbs = l.xs; ka.xbs_ld = npad; ka.xbs_stride = d * (int64_t)npad;
     ka.n1 = n; ka.n2 = n; ka.d = d; ka.ldo = npad; ka.rows_pad = npad; ka.cols_pad = npad;
     ka.store_rows = npad; ka.store_cols = npad; ka.vec_ok = 1;
     ka.ls_stride = d; ka.out_stride = (int64_t)npad * npad; ka.noise = noise; ka.add_noise = 1; ka.pad_identity = 1;
+    ka.lower_only = 1;  // the factorisation reads the lower triangle only
     if (int32_t rc = launch_kmat(stream, kind, ka, (int)batch)) return rc;
     if (int32_t rc = factor_recursive(stream, fb, npad, (int)batch)) return rc;
-    SolveArgs sa{kind, X, ls, kv, d, noise};
+    SolveArgs sa{kind, X, ls, kv, d, noise, l.xs};
     return launch_solve_vectors(stream, fb, sa, y, n, npad, (int)batch, l.z, alpha ? alpha : l.alpha, logdet, quad,
                                 info);
 }
 
 // ---- predict --------------------------------------------------------------------------------------------
 extern "C" int64_t bobe_predict_workspace_bytes(int64_t n, int64_t d, int64_t M, int32_t mode) {
-    (void)d;
-    if (!(mode & BOBE_PREDICT_VAR) || M <= 0) return 256;
-    int64_t rows = round_up(M < QCHUNK ? M : QCHUNK, 128);
-    return rows * npad_of(n) * 8 + 512;
+    if (M <= 0 || n <= 0 || d <= 0) return 256;
+    int64_t bytes = round_up(d * npad_of(n), 32) * 8 + 512;  // scaled, transposed training inputs
+    if (mode & BOBE_PREDICT_VAR) bytes += round_up(M < QCHUNK ? M : QCHUNK, 128) * npad_of(n) * 8;  // K* panel
+    return bytes;
 }
 
 extern "C" int32_t bobe_predict(void* stream_, int32_t kind, const double* X, int64_t n, int64_t d, const double* ls,
@@ -289,24 +294,24 @@ extern "C" int32_t bobe_predict(void* stream_, int32_t kind, const double* X, in
     }
     if (M == 0) return BOBE_OK;
     const int64_t npad = npad_of(n);
-    double* kstar = nullptr;
-    if (want_var) {
-        if (!ws || ws_bytes < bobe_predict_workspace_bytes(n, d, M, mode)) {
-            set_error("predict: workspace too small (%lld < %lld)", (long long)ws_bytes,
-                      (long long)bobe_predict_workspace_bytes(n, d, M, mode));
-            return BOBE_E_WORKSPACE;
-        }
-        if (!aligned16(Linv)) {
-            set_error("predict: Linv must be 16-byte aligned");
-            return BOBE_E_ARG;
-        }
-        kstar = align256(ws);
+    if (!ws || ws_bytes < bobe_predict_workspace_bytes(n, d, M, mode)) {
+        set_error("predict: workspace too small (%lld < %lld)", (long long)ws_bytes,
+                  (long long)bobe_predict_workspace_bytes(n, d, M, mode));
+        return BOBE_E_WORKSPACE;
     }
+    if (want_var && !aligned16(Linv)) {
+        set_error("predict: Linv must be 16-byte aligned");
+        return BOBE_E_ARG;
+    }
+    double* xs = align256(ws);  // (d, npad) = X^T / l, built once per call
+    double* kstar = want_var ? xs + round_up(d * npad, 32) : nullptr;
+    if (int32_t rc = launch_prescale(stream, X, n, d, ls, 0, xs, npad, 0, 1)) return rc;
     for (int64_t q0 = 0; q0 < M; q0 += QCHUNK) {
         int64_t rows = (M - q0 < QCHUNK) ? M - q0 : QCHUNK;
         int64_t rows_pad = round_up(rows, 128);
         KmatArgs a{};
         a.xa = Xq + q0 * d; a.xb = X; a.ls = ls; a.kv = kv; a.noise = noise;
+        a.xbs = xs; a.xbs_ld = npad;
         a.alpha = want_mean ? alpha : nullptr;
         a.mean_out = want_mean ? mean_out + q0 : nullptr;
         a.out = kstar;
@@ -327,11 +332,11 @@ extern "C" int32_t bobe_predict(void* stream_, int32_t kind, const double* X, in
 namespace {
 constexpr int64_t MCCHUNK = 16384;
 struct FantasyLayout {
-    double *Kmc, *VT, *base, *Kc, *VcT, *delta2, *G, *kc, *acc;
+    double *Kmc, *VT, *base, *Kc, *VcT, *delta2, *G, *kc, *acc, *xs;
     int64_t chunk, cpad, bytes;
     bool fits;
 };
-FantasyLayout fantasy_layout(void* ws, int64_t ws_bytes, int64_t n, int64_t n_mc, int64_t C, bool self) {
+FantasyLayout fantasy_layout(void* ws, int64_t ws_bytes, int64_t n, int64_t d, int64_t n_mc, int64_t C, bool self) {
     int64_t npad = npad_of(n);
     FantasyLayout l{};
     l.chunk = self ? round_up(n_mc, 64) : round_up(n_mc < MCCHUNK ? n_mc : MCCHUNK, 64);
@@ -346,6 +351,7 @@ FantasyLayout fantasy_layout(void* ws, int64_t ws_bytes, int64_t n, int64_t n_mc
     l.G = c.take(l.cpad * l.chunk);
     l.kc = c.take(l.cpad * l.chunk);
     l.acc = c.take(l.cpad);
+    l.xs = c.take(d * npad);
     l.bytes = c.bytes();
     l.fits = ws ? c.fits(ws, ws_bytes) : false;
     return l;
@@ -353,10 +359,9 @@ FantasyLayout fantasy_layout(void* ws, int64_t ws_bytes, int64_t n, int64_t n_mc
 }  // namespace
 
 extern "C" int64_t bobe_fantasy_var_workspace_bytes(int64_t n, int64_t d, int64_t n_mc, int64_t C) {
-    (void)d;
-    if (n <= 0 || n_mc <= 0) return 256;
+    if (n <= 0 || n_mc <= 0 || d <= 0) return 256;
     // C <= 0 means "the MC points are the candidates"
-    return fantasy_layout(nullptr, 0, n, n_mc, C, C <= 0).bytes;
+    return fantasy_layout(nullptr, 0, n, d, n_mc, C, C <= 0).bytes;
 }
 
 extern "C" int32_t bobe_fantasy_var(void* stream_, int32_t kind, const double* X, int64_t n, int64_t d,
@@ -369,16 +374,18 @@ extern "C" int32_t bobe_fantasy_var(void* stream_, int32_t kind, const double* X
         set_error("fantasy_var: bad arguments");
         return BOBE_E_ARG;
     }
-    FantasyLayout l = fantasy_layout(ws, ws_bytes, n, n_mc, C, self);
+    FantasyLayout l = fantasy_layout(ws, ws_bytes, n, d, n_mc, C, self);
     if (!l.fits) {
         set_error("fantasy_var: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)l.bytes);
         return BOBE_E_WORKSPACE;
     }
     const int64_t npad = npad_of(n);
     const double kk = kv + noise;  // kernel_diag(..., include_noise=True), BOBE/gp.py:561,570
+    if (int32_t rc = launch_prescale(stream, X, n, d, ls, 0, l.xs, npad, 0, 1)) return rc;
     auto kstar_panel = [&](const double* pts, int64_t rows, int64_t rows_pad, double* Kout) {
         KmatArgs a{};
         a.xa = pts; a.xb = X; a.ls = ls; a.kv = kv; a.noise = noise; a.out = Kout;
+        a.xbs = l.xs; a.xbs_ld = npad;
         a.n1 = rows; a.n2 = n; a.d = d; a.ldo = npad; a.rows_pad = rows_pad; a.cols_pad = npad;
         a.store_rows = rows_pad; a.store_cols = npad; a.vec_ok = 1;
         return launch_kmat(stream, kind, a, 1);

@@ -124,4 +124,75 @@ __device__ __forceinline__ double kernel_from_q(double q, double kv) {
     }
 }
 
+// Taylor coefficients 1/12! .. 1/0! of exp (Horner order, after the leading 1/13!)
+__constant__ double EXP_TAYLOR[13] = {2.0876756987868099e-09, 2.5052108385441719e-08, 2.7557319223985891e-07,
+                                      2.7557319223985893e-06, 2.4801587301587302e-05, 1.9841269841269841e-04,
+                                      1.3888888888888889e-03, 8.3333333333333332e-03, 4.1666666666666664e-02,
+                                      1.6666666666666666e-01, 0.5, 1.0, 1.0};
+
+// ---- the same functions for N values in lock step ----------------------------------------------------------------
+// One value at a time the polynomial is a chain of ~30 dependent FP64 instructions, each waiting out the pipe
+// latency, and every 64-bit coefficient costs two UMOVs.  Evaluating N independent values per Horner step keeps
+// N instructions in flight per warp and amortises each coefficient load over N uses.  Arithmetic per value is
+// bit-identical to exp_nonpos / sqrt_pos / kernel_from_q above.
+template <int N>
+__device__ __forceinline__ void exp_nonpos_n(const double (&x)[N], double (&res)[N]) {
+    const double SHIFT = 6755399441055744.0;
+    double r[N], p[N];
+    int n[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        double t = fma(x[j], 1.4426950408889634074, SHIFT);
+        n[j] = __double2loint(t);
+        double fn = t - SHIFT;
+        double rr = fma(fn, -6.93147180559945286227e-01, x[j]);
+        r[j] = fma(fn, -2.31904681384629955842e-17, rr);
+        p[j] = 1.6059043836821613e-10;
+    }
+    // A REAL loop over the Horner steps (not unrolled): ptxas otherwise re-serialises the unrolled code into one
+    // 13-deep dependent chain per value, which leaves the FP64 pipe idle for most of each instruction's latency.
+#pragma unroll 1
+    for (int c = 0; c < 13; ++c) {
+        const double cc = EXP_TAYLOR[c];
+#pragma unroll
+        for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], cc);
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        // x < -707.7 decided on the high word (x <= 0, so a larger unsigned high word is a larger magnitude);
+        // 0xC0861D99 is the high word of -707.7 and the low word's 2^-20 relative slack is immaterial (both sides of
+        // the threshold give a normal, correctly scaled result down to x = -708.3)
+        const bool under = (unsigned)__double2hiint(x[j]) > 0xC0861D99u;
+        const int hi = __double2hiint(p[j]) + (n[j] << 20);
+        res[j] = __hiloint2double(under ? 0 : hi, under ? 0 : __double2loint(p[j]));
+    }
+}
+
+template <int KIND, int N>
+__device__ __forceinline__ void kernel_from_q_n(const double (&q)[N], double kv, double (&out)[N]) {
+    if (KIND == BOBE_KERNEL_RBF) {
+        double x[N], e[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) x[j] = -0.5 * q[j];
+        exp_nonpos_n<N>(x, e);
+#pragma unroll
+        for (int j = 0; j < N; ++j) out[j] = kv * e[j];
+    } else {
+        double r[N], x[N], e[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            // q >= 0, so the IEEE order is the integer order: an exact `q < 1e-30` without touching the FP64 pipe
+            const double qc = (__double_as_longlong(q[j]) < __double_as_longlong(1e-30)) ? 1e-30 : q[j];
+            r[j] = sqrt_pos(qc);
+            x[j] = -SQRT5 * r[j];
+        }
+        exp_nonpos_n<N>(x, e);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double poly = 1.0 + r[j] * (SQRT5 + r[j] * (5.0 / 3.0));
+            out[j] = kv * poly * e[j];
+        }
+    }
+}
+
 }  // namespace bobe

@@ -253,6 +253,7 @@ int32_t launch_solve_vectors(cudaStream_t stream, const FactorBuffers& fb, const
     {
         KmatArgs ka{};
         ka.xa = sa.X; ka.xb = sa.X; ka.ls = sa.ls; ka.kv_ptr = sa.kv; ka.alpha = alpha; ka.mean_out = k0a;
+        ka.xbs = sa.xs; ka.xbs_ld = npad; ka.xbs_stride = sa.d * (int64_t)npad;
         ka.n1 = n; ka.n2 = n; ka.d = sa.d; ka.rows_pad = npad; ka.cols_pad = npad;
         ka.ls_stride = sa.d; ka.alpha_stride = npad; ka.mean_stride = npad; ka.mean_standardised = 1;
         ka.gate = fb.gate;

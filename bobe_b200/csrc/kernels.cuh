@@ -11,6 +11,8 @@ int64_t env_int(const char* name, int64_t dflt);  // tuning knobs (read once)
 struct KmatArgs {
     const double* xa;      // (n1, d) rows of the output
     const double* xb;      // (n2, d) columns of the output
+    const double* xbs;     // optional: xb already scaled and transposed, (batch, d, xbs_ld) from launch_prescale
+    int64_t xbs_ld, xbs_stride;
     const double* ls;      // (batch, d) lengthscales, stride ls_stride
     const double* kv_ptr;  // (batch) kernel variances or null -> kv
     const double* alpha;   // (cols_pad) optional: mean_out[i] = sum_j alpha[j] K[i][j]   (needs col_splits == 1)
@@ -25,9 +27,13 @@ struct KmatArgs {
     double kv, noise, y_mean, y_std;
     int add_noise;     // + noise on the diagonal (square case)
     int pad_identity;  // 1: padded part is the identity (factorisation input), 0: zeros (K* panels)
+    int lower_only;    // 1: square symmetric build, tiles strictly above the diagonal are skipped (left unwritten)
     int mean_standardised;
 };
 int32_t launch_kmat(cudaStream_t stream, int kind, const KmatArgs& a, int batch);
+// xs[z][k][j] = x[j][k] / ls[z][k] (zero for n <= j < ld): the column operand of launch_kmat in its compute layout
+int32_t launch_prescale(cudaStream_t stream, const double* x, int64_t n, int64_t d, const double* ls, int64_t ls_stride,
+                        double* xs, int64_t ld, int64_t xs_stride, int batch);
 
 // trmm + sumsq (gemm.cu) ---------------------------------------------------------------------------------
 int32_t launch_trmm_sumsq(cudaStream_t stream, const double* Linv, int npad, const double* Kstar, int64_t ldk,
@@ -57,6 +63,7 @@ struct SolveArgs {  // what the alpha refinement needs to rebuild K alpha
     const double* kv;  // (batch)
     int64_t d;
     double noise;
+    const double* xs;  // (batch, d, npad) scaled, transposed X from launch_prescale (same ls)
 };
 int64_t solve_ws_doubles(int64_t npad, int64_t batch);
 int32_t launch_solve_vectors(cudaStream_t stream, const FactorBuffers& fb, const SolveArgs& sa, const double* y,

@@ -198,7 +198,7 @@ static StreamPool* stream_pool() {
 struct MllLayout {
     int64_t npad, tiles, ntile_pairs;
     int64_t off_ls, off_kv, off_KB, off_L, off_Lt, off_Linv, off_U, off_Q, off_diag, off_stat, off_z, off_alpha, off_logdet,
-        off_quad, off_partial, total;
+        off_quad, off_partial, off_xs, total;
 };
 
 static MllLayout mll_layout(int64_t n, int64_t d, int64_t R) {
@@ -227,6 +227,7 @@ static MllLayout mll_layout(int64_t n, int64_t d, int64_t R) {
     l.off_logdet = take(R);
     l.off_quad = take(R);
     l.off_partial = take(R * l.ntile_pairs * (d + 1));
+    l.off_xs = take(R * d * l.npad);
     l.total = o;
     return l;
 }
@@ -249,7 +250,7 @@ extern "C" int32_t bobe_mll_grad_batched(void* stream_, int32_t kind, const doub
         set_error("mll_grad: null pointer");
         return BOBE_E_ARG;
     }
-    if (n <= 0 || d <= 0 || R <= 0 || P < d + (has_kv ? 1 : 0) || P > 256 || d > 200) {
+    if (n <= 0 || d <= 0 || R <= 0 || P < d + (has_kv ? 1 : 0) || P > 256 || d > BOBE_MAX_DIM) {
         set_error("mll_grad: bad sizes n=%lld d=%lld R=%lld P=%lld", (long long)n, (long long)d, (long long)R,
                   (long long)P);
         return BOBE_E_ARG;
@@ -298,14 +299,18 @@ extern "C" int32_t bobe_mll_grad_batched(void* stream_, int32_t kind, const doub
             double* partial = w + l.off_partial + r0 * l.ntile_pairs * (d + 1);
             const double *ls_s = ls + r0 * d, *kv_s = kv + r0;
 
+            double* xs = w + l.off_xs + r0 * d * npad;
+            if (int32_t rc = launch_prescale(st, X, n, d, ls_s, d, xs, npad, d * (int64_t)npad, (int)Rs)) return rc;
             KmatArgs ka{};
             ka.xa = X; ka.xb = X; ka.ls = ls_s; ka.kv_ptr = kv_s; ka.out = fb.KB;
+            ka.xbs = xs; ka.xbs_ld = npad; ka.xbs_stride = d * (int64_t)npad;
             ka.n1 = n; ka.n2 = n; ka.d = d; ka.ldo = npad; ka.rows_pad = npad; ka.cols_pad = npad;
             ka.store_rows = npad; ka.store_cols = npad; ka.vec_ok = 1;
             ka.ls_stride = d; ka.out_stride = m2; ka.noise = noise; ka.add_noise = 1; ka.pad_identity = 1;
+            ka.lower_only = 1;  // the factorisation reads the lower triangle only
             if (int32_t rc = launch_kmat(st, kind, ka, (int)Rs)) return rc;
             if (int32_t rc = factor_recursive(st, fb, npad, (int)Rs)) return rc;
-            SolveArgs sa{kind, X, ls_s, kv_s, d, noise};
+            SolveArgs sa{kind, X, ls_s, kv_s, d, noise, xs};
             if (int32_t rc = launch_solve_vectors(st, fb, sa, y, n, npad, (int)Rs, zws, alpha, logdet, quad, info + r0))
                 return rc;
             if (int32_t rc = launch_kinv(st, fb, npad, (int)Rs)) return rc;

@@ -76,7 +76,7 @@ def factorize(kind: str, X, y, ls, kv, noise: float, want_L: bool = True):
     quad = torch.empty(B, dtype=torch.float64, device=dev)
     info = torch.empty(B, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        nbytes = lib.bobe_factorize_workspace_bytes(n, B)
+        nbytes = lib.bobe_factorize_workspace_bytes(n, d, B)
         ws = _workspace(nbytes, dev)
         check(lib.bobe_factorize(_stream(), KIND[kind], X.data_ptr(), y.data_ptr(), n, d, ls.data_ptr(), kv.data_ptr(),
                                  float(noise), B, L.data_ptr() if want_L else None, Linv.data_ptr(), alpha.data_ptr(),

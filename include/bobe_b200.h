@@ -29,6 +29,8 @@ extern "C" {
 #define BOBE_KERNEL_RBF 0      /* BOBE/gp.py:124-154 */
 #define BOBE_KERNEL_MATERN52 1 /* BOBE/gp.py:156-168 */
 
+#define BOBE_MAX_DIM 144 /* largest input dimension d (shared-memory staging of one 64-row tile per operand) */
+
 #define BOBE_OK 0
 #define BOBE_E_ARG (-1)       /* bad argument (shape, null pointer, misaligned) */
 #define BOBE_E_WORKSPACE (-2) /* workspace too small */
@@ -63,7 +65,7 @@ int32_t bobe_kernel_matrix(void* stream, int32_t kind, const double* xa, int64_t
  *   L (batch, npad, npad) lower with zero upper; Linv (batch, npad, npad) = L^-1, lower;
  *   alpha (batch, npad); logdet (batch) = sum log L_ii; quad (batch) = y^T K^-1 y; info (batch) int32,
  *   0 = PD, 1 = not PD (outputs NaN). */
-int64_t bobe_factorize_workspace_bytes(int64_t n, int64_t batch);
+int64_t bobe_factorize_workspace_bytes(int64_t n, int64_t d, int64_t batch);
 int32_t bobe_factorize(void* stream, int32_t kind, const double* X, const double* y, int64_t n, int64_t d,
                        const double* ls, const double* kv, double noise, int64_t batch, double* L, double* Linv,
                        double* alpha, double* logdet, double* quad, int32_t* info, void* ws, int64_t ws_bytes);
