@@ -68,7 +68,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ---- branch-free FP64 elementary functions for the kernel builds -----------------------------------------------
 // The CUDA math library's exp()/sqrt() carry special-case paths (denormals, overflow, NaN) behind branches and
 // CALLs; the kernel builds only ever see x <= 0 resp. q >= 1e-30, so the straight-line cores suffice.  Both are
-// accurate to ~1 ulp (Cody-Waite reduction + degree-13 Taylor on |r| <= ln2/2; rsqrt seed + 2 Goldschmidt steps +
+// accurate to ~1 ulp (Cody-Waite reduction + degree-13 Taylor on |r| <= ln2/2; rsqrt seed + 1 Goldschmidt step +
 // a final residual correction).
 
 // exp(x) for x <= 0.  Results below 2^-1021 (x < -707.7) are flushed to 0.
@@ -97,15 +97,14 @@ __device__ __forceinline__ double exp_nonpos(double x) {
     return x < -707.7 ? 0.0 : res;
 }
 
-// sqrt(q) for normal positive q.
+// sqrt(q) for normal positive q: MUFU.RSQ64H seed (2^-20 relative), ONE Goldschmidt step (-> ~2^-39) and a residual
+// correction (-> ~2^-78 before the final rounding).  tools/sqrt_probe.cu: identical to the correctly rounded
+// __dsqrt_rn on all 2^30 sampled arguments over 2^-100 .. 2^20 (profiles/r01/sqrt_probe.txt).
 __device__ __forceinline__ double sqrt_pos(double q) {
     double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(q));  // MUFU.RSQ64H seed, ~2^-20 relative
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(q));
     double g = q * y, h = 0.5 * y;
     double r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    r = fma(-g, h, 0.5);
     g = fma(g, r, g);
     h = fma(h, r, h);
     return fma(fma(-g, g, q), h, g);  // residual correction: g + (q - g^2) / (2 g)
@@ -125,10 +124,10 @@ __device__ __forceinline__ double kernel_from_q(double q, double kv) {
 }
 
 // Taylor coefficients 1/12! .. 1/0! of exp (Horner order, after the leading 1/13!)
-__constant__ double EXP_TAYLOR[13] = {2.0876756987868099e-09, 2.5052108385441719e-08, 2.7557319223985891e-07,
+__constant__ double EXP_TAYLOR[14] = {2.0876756987868099e-09, 2.5052108385441719e-08, 2.7557319223985891e-07,
                                       2.7557319223985893e-06, 2.4801587301587302e-05, 1.9841269841269841e-04,
                                       1.3888888888888889e-03, 8.3333333333333332e-03, 4.1666666666666664e-02,
-                                      1.6666666666666666e-01, 0.5, 1.0, 1.0};
+                                      1.6666666666666666e-01, 0.5, 1.0, 1.0, 0.0};
 
 // ---- the same functions for N values in lock step ----------------------------------------------------------------
 // One value at a time the polynomial is a chain of ~30 dependent FP64 instructions, each waiting out the pipe
@@ -151,12 +150,21 @@ __device__ __forceinline__ void exp_nonpos_n(const double (&x)[N], double (&res)
     }
     // A REAL loop over the Horner steps (not unrolled): ptxas otherwise re-serialises the unrolled code into one
     // 13-deep dependent chain per value, which leaves the FP64 pipe idle for most of each instruction's latency.
+    // Two steps per trip; the next pair of coefficients is fetched (LDCU) before the current pair is used, so the
+    // constant-bank latency hides behind 2 N DFMAs.
+    double c0 = EXP_TAYLOR[0], c1 = EXP_TAYLOR[1];
 #pragma unroll 1
-    for (int c = 0; c < 13; ++c) {
-        const double cc = EXP_TAYLOR[c];
+    for (int c = 2; c <= 12; c += 2) {
+        const double n0 = EXP_TAYLOR[c], n1 = EXP_TAYLOR[c + 1];
 #pragma unroll
-        for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], cc);
+        for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], c0);
+#pragma unroll
+        for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], c1);
+        c0 = n0;
+        c1 = n1;
     }
+#pragma unroll
+    for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], c0);  // c0 = EXP_TAYLOR[12] = 1/0!
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         // x < -707.7 decided on the high word (x <= 0, so a larger unsigned high word is a larger magnitude);

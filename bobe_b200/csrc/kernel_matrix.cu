@@ -8,6 +8,7 @@ namespace bobe {
 constexpr int KT = 64;    // tile edge (rows and columns)
 constexpr int KLD = 66;   // smem row stride (doubles): even, so 16-byte vector reads stay aligned
 constexpr int KTHREADS = 128;
+constexpr int KROWS = 4;  // rows of a thread's 8 x 4 tile whose kernel values are evaluated together
 
 // One CTA (128 threads as 8 x 16) computes 64 x 64 tiles of K: thread (ty, tx) owns rows 8 ty .. 8 ty + 7 and the
 // columns {2 tx, 2 tx + 1, 32 + 2 tx, 33 + 2 tx} -- 32 independent distance accumulators per thread, fed per
@@ -104,16 +105,21 @@ __global__ void __launch_bounds__(KTHREADS, 2) kmat_kernel(KmatArgs p) {
         for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) q[i][j] = 0.0;
+        // register double buffer: the six LDS.128 of dimension k+1 are in flight while dimension k is consumed
+        const double* ap = sa + ty * 8;
+        const double* bp = sbt + 2 * tx;
+        double2 a01 = *reinterpret_cast<const double2*>(ap), a23 = *reinterpret_cast<const double2*>(ap + 2);
+        double2 a45 = *reinterpret_cast<const double2*>(ap + 4), a67 = *reinterpret_cast<const double2*>(ap + 6);
+        double2 b01 = *reinterpret_cast<const double2*>(bp), b23 = *reinterpret_cast<const double2*>(bp + 32);
 #pragma unroll 2
         for (int k = 0; k < d; ++k) {
-            const double* ap = sa + k * KLD + ty * 8;
-            const double* bp = sbt + k * KLD + 2 * tx;
-            double2 a01 = *reinterpret_cast<const double2*>(ap);
-            double2 a23 = *reinterpret_cast<const double2*>(ap + 2);
-            double2 a45 = *reinterpret_cast<const double2*>(ap + 4);
-            double2 a67 = *reinterpret_cast<const double2*>(ap + 6);
-            double2 b01 = *reinterpret_cast<const double2*>(bp);
-            double2 b23 = *reinterpret_cast<const double2*>(bp + 32);
+            const int kn = (k + 1 < d ? k + 1 : k) * KLD;
+            const double2 n01 = *reinterpret_cast<const double2*>(ap + kn);
+            const double2 n23 = *reinterpret_cast<const double2*>(ap + kn + 2);
+            const double2 n45 = *reinterpret_cast<const double2*>(ap + kn + 4);
+            const double2 n67 = *reinterpret_cast<const double2*>(ap + kn + 6);
+            const double2 m01 = *reinterpret_cast<const double2*>(bp + kn);
+            const double2 m23 = *reinterpret_cast<const double2*>(bp + kn + 32);
             double a[8] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y, a67.x, a67.y};
             double b[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
@@ -123,6 +129,7 @@ __global__ void __launch_bounds__(KTHREADS, 2) kmat_kernel(KmatArgs p) {
                     double df = a[i] - b[j];
                     q[i][j] = fma(df, df, q[i][j]);
                 }
+            a01 = n01; a23 = n23; a45 = n45; a67 = n67; b01 = m01; b23 = m23;
         }
         double al[4] = {0.0, 0.0, 0.0, 0.0};
         if (alpha) {
@@ -132,16 +139,15 @@ __global__ void __launch_bounds__(KTHREADS, 2) kmat_kernel(KmatArgs p) {
         // interior tiles (all 64 x 64 elements inside (n1, n2), no diagonal term) take the check-free path
         const bool interior = i0 + KT <= p.n1 && j0 + KT <= p.n2 && !(p.add_noise && i0 == j0);
 #pragma unroll
-        for (int ip = 0; ip < 8; ip += 2) {  // two rows (8 values) per lock-step evaluation
-            double qq[8], v[8];
+        for (int ip = 0; ip < 8; ip += KROWS) {  // KROWS rows (4 KROWS values) per lock-step evaluation
+            double qq[4 * KROWS], v[4 * KROWS];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                qq[j] = q[ip][j];
-                qq[4 + j] = q[ip + 1][j];
-            }
-            kernel_from_q_n<KIND, 8>(qq, kv, v);
+            for (int h = 0; h < KROWS; ++h)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+                for (int j = 0; j < 4; ++j) qq[4 * h + j] = q[ip + h][j];
+            kernel_from_q_n<KIND, 4 * KROWS>(qq, kv, v);
+#pragma unroll
+            for (int h = 0; h < KROWS; ++h) {
                 const int i = ip + h;
                 const int64_t row = i0 + ty * 8 + i;
                 double* vr = v + 4 * h;
