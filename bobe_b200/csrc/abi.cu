@@ -320,7 +320,7 @@ extern "C" int32_t bobe_predict(void* stream_, int32_t kind, const double* X, in
         a.y_mean = y_mean; a.y_std = y_std; a.mean_standardised = standardised;
         if (int32_t rc = launch_kmat(stream, kind, a, 1)) return rc;
         if (want_var) {
-            if (int32_t rc = launch_trmm_sumsq(stream, Linv, (int)npad, kstar, npad, rows_pad, q0, M, kv + noise,
+            if (int32_t rc = launch_trmm_sumsq(stream, Linv, (int)n, (int)npad, kstar, npad, rows_pad, q0, M, kv + noise,
                                                y_std * y_std, standardised, var_out))
                 return rc;
         }
@@ -486,6 +486,6 @@ extern "C" int32_t bobe_bench_trmm_sumsq(void* stream, const double* Linv, int64
         return BOBE_E_ARG;
     }
     const int64_t npad = npad_of(n);
-    return launch_trmm_sumsq((cudaStream_t)stream, Linv, (int)npad, kstar, npad, rows_pad, 0, rows_pad, kk, 1.0, 0,
+    return launch_trmm_sumsq((cudaStream_t)stream, Linv, (int)n, (int)npad, kstar, npad, rows_pad, 0, rows_pad, kk, 1.0, 0,
                              var_out);
 }

@@ -58,17 +58,17 @@ int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& a, int batch) {
     return check_launch("gemm_nt_kernel");
 }
 
-int32_t launch_trmm_sumsq(cudaStream_t stream, const double* Linv, int npad, const double* Kstar, int64_t ldk,
+int32_t launch_trmm_sumsq(cudaStream_t stream, const double* Linv, int n, int npad, const double* Kstar, int64_t ldk,
                           int64_t rows_pad, int64_t q_begin, int64_t M, double kk, double scale, int standardised,
                           double* var_out) {
-    using Cfg = CfgBig;
+    using Cfg = CfgTrmm;
     if (rows_pad % Cfg::BN) {
         set_error("trmm_sumsq: query chunk must be padded to %d", Cfg::BN);
         return BOBE_E_ARG;
     }
     if (int32_t rc = ensure_smem<trmm_sumsq_kernel<Cfg>>(Cfg::SMEM_BYTES)) return rc;
     dim3 grid(rows_pad / Cfg::BN);
-    trmm_sumsq_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(Linv, npad, Kstar, ldk, q_begin, M, kk,
+    trmm_sumsq_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(Linv, n, npad, Kstar, ldk, q_begin, M, kk,
                                                                          scale, standardised, var_out);
     return check_launch("trmm_sumsq_kernel");
 }

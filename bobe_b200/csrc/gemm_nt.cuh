@@ -13,9 +13,16 @@
 
 namespace bobe {
 
-template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int BK_ = 16>
+// ILV: warp wm owns the 8-row groups {wm, wm + WM, wm + 2 WM, ...} of the tile instead of WTM consecutive rows, so
+// that a triangular operand leaves every warp the same number of live fragments (see Mainloop::run, tri0).
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int BK_ = 16, bool ILV_ = false>
 struct TileCfg {
     static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_;
+    static constexpr bool ILV = ILV_;
+    // first row (within the tile) of fragment mf of warp-row wm
+    __host__ __device__ static constexpr int frag_row(int wm, int mf) {
+        return ILV_ ? mf * 8 * WM_ + wm * 8 : wm * (BM_ / WM_) + mf * 8;
+    }
     static constexpr int BK = BK_;
     static constexpr int PANELS = BK / 8;  // k8 panels per stage
     static constexpr int THREADS = 32 * WM * WN;
@@ -100,7 +107,7 @@ struct Mainloop {
         double2 a[Cfg::MF], b[Cfg::NF];
 #pragma unroll
         for (int mf = 0; mf < Cfg::MF; ++mf)
-            a[mf] = *reinterpret_cast<const double2*>(sA + ((p * Cfg::BM + wm * Cfg::WTM + mf * 8 + g) * 8 + 2 * t));
+            a[mf] = *reinterpret_cast<const double2*>(sA + ((p * Cfg::BM + Cfg::frag_row(wm, mf) + g) * 8 + 2 * t));
 #pragma unroll
         for (int nf = 0; nf < Cfg::NF; ++nf)
             b[nf] = *reinterpret_cast<const double2*>(sB + ((p * Cfg::BN + wn * Cfg::WTN + nf * 8 + g) * 8 + 2 * t));
@@ -116,16 +123,59 @@ struct Mainloop {
             for (int nf = 0; nf < Cfg::NF; ++nf) dmma884(acc[mf][nf][0], acc[mf][nf][1], a[mf].y, b[nf].y);
     }
 
+    // same, restricted to the row fragments lo <= mf < hi (warp-uniform bounds): the others are known to
+    // multiply zeros (above the diagonal of a lower-triangular A, or rows beyond the matrix)
+    __device__ static __forceinline__ void mma_panel_range(double (&acc)[Cfg::MF][Cfg::NF][2], const double* sA,
+                                                           const double* sB, int p, int wm, int wn, int g, int t,
+                                                           int lo, int hi) {
+        double2 a[Cfg::MF], b[Cfg::NF];
+#pragma unroll
+        for (int mf = 0; mf < Cfg::MF; ++mf)
+            a[mf] = *reinterpret_cast<const double2*>(sA + ((p * Cfg::BM + Cfg::frag_row(wm, mf) + g) * 8 + 2 * t));
+#pragma unroll
+        for (int nf = 0; nf < Cfg::NF; ++nf)
+            b[nf] = *reinterpret_cast<const double2*>(sB + ((p * Cfg::BN + wn * Cfg::WTN + nf * 8 + g) * 8 + 2 * t));
+#pragma unroll
+        for (int mf = 0; mf < Cfg::MF; ++mf)
+            if (mf >= lo && mf < hi) {
+#pragma unroll
+                for (int nf = 0; nf < Cfg::NF; ++nf) dmma884(acc[mf][nf][0], acc[mf][nf][1], a[mf].x, b[nf].x);
+            }
+#pragma unroll
+        for (int mf = 0; mf < Cfg::MF; ++mf)
+            if (mf >= lo && mf < hi) {
+#pragma unroll
+                for (int nf = 0; nf < Cfg::NF; ++nf) dmma884(acc[mf][nf][0], acc[mf][nf][1], a[mf].y, b[nf].y);
+            }
+    }
+
     // acc += A[0:BM, kb:ke] * Bt[0:BN, kb:ke]^T   (kb, ke multiples of BK; A/Bt point at the tile's first row)
+    // tri0 / rows_live (optional): A[r][k] == 0 for k > tri0 + r, and rows >= rows_live contribute nothing; the
+    // k8 panels that reach into that region only issue the MMAs of the fragments that can be non-zero.
+    template <bool TRI = false>
     __device__ static __forceinline__ void run(double (&acc)[Cfg::MF][Cfg::NF][2], const double* A, int64_t lda,
                                                int rowsA, const double* Bt, int64_t ldb, int rowsB, int kb, int ke,
-                                               double* smem) {
+                                               double* smem, int tri0 = 1 << 30, int rows_live = Cfg::BM) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const int g = lane >> 2, t = lane & 3;
         const int wm = warp / Cfg::WN, wn = warp % Cfg::WN;
         const int ktiles = (ke - kb) / Cfg::BK;
         Loader ld;
         ld.init(A, lda, rowsA, Bt, ldb, rowsB, kb, smem);
+        // live fragment range of this warp: frag_row(wm, mf) < rows_live  <=>  mf < hi
+        constexpr int FSTEP = Cfg::ILV ? 8 * Cfg::WM : 8;  // row distance between consecutive fragments of a warp
+        const int fbase = Cfg::frag_row(wm, 0);
+        int hi = (rows_live - fbase + FSTEP - 1) / FSTEP;
+        hi = hi < 0 ? 0 : (hi > Cfg::MF ? Cfg::MF : hi);
+        auto panel = [&](const double* sA, const double* sB, int p, int kp) {
+            // fragment mf is live at panel kp iff kp <= tri0 + frag_row + 7  <=>  mf >= (kp - tri0 - fbase - 7) / FSTEP
+            const int rel = kp - tri0 - fbase - 7;
+            const int lo = rel <= 0 ? 0 : (rel + FSTEP - 1) / FSTEP;
+            if (!TRI || (lo == 0 && hi == Cfg::MF))
+                mma_panel(acc, sA, sB, p, wm, wn, g, t);
+            else if (lo < hi)
+                mma_panel_range(acc, sA, sB, p, wm, wn, g, t, lo, hi);
+        };
 
 #pragma unroll
         for (int s = 0; s < Cfg::STAGES - 1; ++s) {
@@ -133,7 +183,15 @@ struct Mainloop {
             cp_async_commit();
         }
         int stage = 0;  // stage holding k-tile kt
-        for (int kt = 0; kt < ktiles; ++kt) {
+        // k-tiles below kt_full are full for every warp: they run the branch-free body (one basic block per
+        // k-tile, so that fragment loads are scheduled across the panels); only the rest pays for the range logic
+        int kt_full = ktiles;
+        if (TRI) {
+            kt_full = rows_live >= Cfg::BM ? (tri0 - kb) / Cfg::BK : 0;
+            kt_full = kt_full < 0 ? 0 : (kt_full > ktiles ? ktiles : kt_full);
+        }
+        int kt = 0;
+        for (; kt < kt_full; ++kt) {
             cp_async_wait<Cfg::STAGES - 2>();
             __syncthreads();  // k-tile kt has landed for everyone; everyone is done reading k-tile kt-1
             const double* sA = smem + stage * Cfg::STAGE_DOUBLES;
@@ -149,6 +207,25 @@ struct Mainloop {
 #pragma unroll
             for (int p = 1; p < Cfg::PANELS; ++p) mma_panel(acc, sA, sB, p, wm, wn, g, t);
             stage = stage + 1 == Cfg::STAGES ? 0 : stage + 1;
+        }
+        if (TRI) {
+            for (; kt < ktiles; ++kt) {
+                cp_async_wait<Cfg::STAGES - 2>();
+                __syncthreads();
+                const double* sA = smem + stage * Cfg::STAGE_DOUBLES;
+                const double* sB = sA + Cfg::BM * Cfg::BK;
+                const int kp0 = kb + kt * Cfg::BK;
+                panel(sA, sB, 0, kp0);
+                {
+                    int nk = kt + Cfg::STAGES - 1;
+                    int nstage = stage == 0 ? Cfg::STAGES - 1 : stage - 1;
+                    if (nk < ktiles) ld.issue(nk, nstage);
+                    cp_async_commit();
+                }
+#pragma unroll
+                for (int p = 1; p < Cfg::PANELS; ++p) panel(sA, sB, p, kp0 + 8 * p);
+                stage = stage + 1 == Cfg::STAGES ? 0 : stage + 1;
+            }
         }
         cp_async_wait<0>();
         __syncthreads();  // smem may be reused by the caller (next tile / epilogue)
@@ -212,7 +289,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(GemmArgs p) {
     const double* D = p.D ? p.D + z * p.strideD : nullptr;
 #pragma unroll
     for (int mf = 0; mf < Cfg::MF; ++mf) {
-        int row = i0 + wm * Cfg::WTM + mf * 8 + g;
+        int row = i0 + Cfg::frag_row(wm, mf) + g;
         if (row >= p.M) continue;
 #pragma unroll
         for (int nf = 0; nf < Cfg::NF; ++nf) {
@@ -239,7 +316,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(GemmArgs p) {
 // summing each finished BM x BN block of V into per-query registers.  V never leaves the SM.
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
-    trmm_sumsq_kernel(const double* __restrict__ Linv, int npad, const double* __restrict__ Kstar, int64_t ldk,
+    trmm_sumsq_kernel(const double* __restrict__ Linv, int n, int npad, const double* __restrict__ Kstar, int64_t ldk,
                       int64_t q_begin, int64_t M, double kk, double scale, int standardised,
                       double* __restrict__ var_out) {
     extern __shared__ __align__(16) double smem[];
@@ -254,14 +331,24 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
 #pragma unroll
     for (int nf = 0; nf < Cfg::NF; ++nf) colsum[nf][0] = colsum[nf][1] = 0.0;
 
-    for (int i0 = 0; i0 < npad; i0 += Cfg::BM) {
+    const int kmax = ((n + Cfg::BK - 1) / Cfg::BK) * Cfg::BK;  // K* columns >= n are zero
+    // Row blocks are aligned to the END of the matrix: a partial block (n mod BM rows) is the FIRST one, where the
+    // k range is shortest, instead of the last one, where it is longest.
+    // (n is first rounded up to the 8-row fragment granularity: the extra rows are identity rows of the padded
+    // Linv, which only meet zero columns of K*.)
+    const int n8 = (n + 7) & ~7;
+    const int r_first = n8 % Cfg::BM;
+    for (int i0 = 0; i0 < n8; i0 += (i0 == 0 && r_first) ? r_first : Cfg::BM) {
         double acc[Cfg::MF][Cfg::NF][2];
 #pragma unroll
         for (int mf = 0; mf < Cfg::MF; ++mf)
 #pragma unroll
             for (int nf = 0; nf < Cfg::NF; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
-        int ke = min(npad, i0 + Cfg::BM);
-        Mainloop<Cfg>::run(acc, Linv + (int64_t)i0 * npad, npad, min(Cfg::BM, npad - i0), Bt, ldk, Cfg::BN, 0, ke, smem);
+        const int rows_live = (i0 == 0 && r_first) ? r_first : Cfg::BM;
+        int ke = min(kmax, ((i0 + rows_live + Cfg::BK - 1) / Cfg::BK) * Cfg::BK);
+        // Linv is lower triangular: row i0 + r is zero beyond column i0 + r
+        Mainloop<Cfg>::template run<true>(acc, Linv + (int64_t)i0 * npad, npad, min(Cfg::BM, npad - i0), Bt, ldk, Cfg::BN, 0,
+                                          ke, smem, i0, rows_live);
 #pragma unroll
         for (int mf = 0; mf < Cfg::MF; ++mf)
 #pragma unroll
@@ -302,6 +389,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
 }
 
 using CfgBig = TileCfg<128, 128, 2, 4, 4>;   // 256 threads, warp tile 64x32, 128 KB smem
+using CfgTrmm = TileCfg<128, 128, 2, 4, 4, 16, true>;  // same, rows interleaved between the two warp rows
 using CfgSmall = TileCfg<64, 64, 2, 2, 4>;   // 128 threads, warp tile 32x32, 64 KB smem
 
 int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& args, int batch);

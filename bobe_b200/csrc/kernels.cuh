@@ -36,7 +36,7 @@ int32_t launch_prescale(cudaStream_t stream, const double* x, int64_t n, int64_t
                         double* xs, int64_t ld, int64_t xs_stride, int batch);
 
 // trmm + sumsq (gemm.cu) ---------------------------------------------------------------------------------
-int32_t launch_trmm_sumsq(cudaStream_t stream, const double* Linv, int npad, const double* Kstar, int64_t ldk,
+int32_t launch_trmm_sumsq(cudaStream_t stream, const double* Linv, int n, int npad, const double* Kstar, int64_t ldk,
                           int64_t rows_pad, int64_t q_begin, int64_t M, double kk, double scale, int standardised,
                           double* var_out);
 

@@ -114,7 +114,7 @@ def test_truth_gap_report():
 
 
 @pytest.mark.parametrize("kernel", ["rbf", "matern"])
-@pytest.mark.parametrize("n,d", [(1, 1), (2, 3), (63, 2), (64, 5), (65, 4), (129, 1), (200, 27), (321, 7)])
+@pytest.mark.parametrize("n,d", [(1, 1), (2, 3), (63, 2), (64, 5), (65, 4), (129, 1), (131, 2), (200, 27), (321, 7), (517, 6)])
 def test_edge_shapes(kernel, n, d):
     """Padding boundaries (npad multiples of 64), d = 1, d > 16, tiny n, ragged query counts."""
     from bobe_b200 import ops
