@@ -149,6 +149,42 @@ struct Mainloop {
             }
     }
 
+    // same, for the fragments mf >= lo where lo is uniform over the CTA: a jump into straight-line, unpredicated
+    // MMA code (a warp-dependent bound would cost a predicate and a WARPSYNC per fragment)
+    __device__ static __forceinline__ void mma_panel_from(double (&acc)[Cfg::MF][Cfg::NF][2], const double* sA,
+                                                          const double* sB, int p, int wm, int wn, int g, int t, int lo) {
+        static_assert(Cfg::MF <= 8, "fall-through table below covers 8 fragments");
+        double2 a[Cfg::MF], b[Cfg::NF];
+#pragma unroll
+        for (int mf = 0; mf < Cfg::MF; ++mf)
+            a[mf] = *reinterpret_cast<const double2*>(sA + ((p * Cfg::BM + Cfg::frag_row(wm, mf) + g) * 8 + 2 * t));
+#pragma unroll
+        for (int nf = 0; nf < Cfg::NF; ++nf)
+            b[nf] = *reinterpret_cast<const double2*>(sB + ((p * Cfg::BN + wn * Cfg::WTN + nf * 8 + g) * 8 + 2 * t));
+#define BOBE_FRAG(MFI, XY)                                                                                   \
+    if (MFI < Cfg::MF) {                                                                                     \
+        _Pragma("unroll") for (int nf = 0; nf < Cfg::NF; ++nf)                                               \
+            dmma884(acc[MFI < Cfg::MF ? MFI : 0][nf][0], acc[MFI < Cfg::MF ? MFI : 0][nf][1],                \
+                    a[MFI < Cfg::MF ? MFI : 0].XY, b[nf].XY);                                                \
+    }
+#define BOBE_PASS(XY)                                  \
+    switch (lo) {                                      \
+        case 0: BOBE_FRAG(0, XY) [[fallthrough]];      \
+        case 1: BOBE_FRAG(1, XY) [[fallthrough]];      \
+        case 2: BOBE_FRAG(2, XY) [[fallthrough]];      \
+        case 3: BOBE_FRAG(3, XY) [[fallthrough]];      \
+        case 4: BOBE_FRAG(4, XY) [[fallthrough]];      \
+        case 5: BOBE_FRAG(5, XY) [[fallthrough]];      \
+        case 6: BOBE_FRAG(6, XY) [[fallthrough]];      \
+        case 7: BOBE_FRAG(7, XY) break;                \
+        default: break;                                \
+    }
+        BOBE_PASS(x)
+        BOBE_PASS(y)
+#undef BOBE_PASS
+#undef BOBE_FRAG
+    }
+
     // acc += A[0:BM, kb:ke] * Bt[0:BN, kb:ke]^T   (kb, ke multiples of BK; A/Bt point at the tile's first row)
     // tri0 / rows_live (optional): A[r][k] == 0 for k > tri0 + r, and rows >= rows_live contribute nothing; the
     // k8 panels that reach into that region only issue the MMAs of the fragments that can be non-zero.
@@ -168,13 +204,22 @@ struct Mainloop {
         int hi = (rows_live - fbase + FSTEP - 1) / FSTEP;
         hi = hi < 0 ? 0 : (hi > Cfg::MF ? Cfg::MF : hi);
         auto panel = [&](const double* sA, const double* sB, int p, int kp) {
-            // fragment mf is live at panel kp iff kp <= tri0 + frag_row + 7  <=>  mf >= (kp - tri0 - fbase - 7) / FSTEP
-            const int rel = kp - tri0 - fbase - 7;
-            const int lo = rel <= 0 ? 0 : (rel + FSTEP - 1) / FSTEP;
-            if (!TRI || (lo == 0 && hi == Cfg::MF))
-                mma_panel(acc, sA, sB, p, wm, wn, g, t);
-            else if (lo < hi)
-                mma_panel_range(acc, sA, sB, p, wm, wn, g, t, lo, hi);
+            if (hi == Cfg::MF) {
+                // fragment mf of warp-row wm is live iff kp <= tri0 + frag_row(wm, mf) + 7.  The bound used is the one
+                // of the LAST warp row (CTA-uniform, so the jump needs no warp synchronisation); with interleaved rows
+                // the other warp rows then run at most one dead fragment.
+                constexpr int FLAST = Cfg::frag_row(Cfg::WM - 1, 0);
+                const int rel = kp - tri0 - FLAST - 7;
+                const int lo = rel <= 0 ? 0 : (rel + FSTEP - 1) / FSTEP;
+                if (lo == 0)
+                    mma_panel(acc, sA, sB, p, wm, wn, g, t);
+                else
+                    mma_panel_from(acc, sA, sB, p, wm, wn, g, t, lo);
+            } else {  // partial first row block: exact per-warp bounds, predicated
+                const int rel = kp - tri0 - fbase - 7;
+                const int lo = rel <= 0 ? 0 : (rel + FSTEP - 1) / FSTEP;
+                if (lo < hi) mma_panel_range(acc, sA, sB, p, wm, wn, g, t, lo, hi);
+            }
         };
 
 #pragma unroll
