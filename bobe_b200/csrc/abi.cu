@@ -256,7 +256,7 @@ extern "C" int32_t bobe_factorize(void* stream_, int32_t kind, const double* X, 
         return BOBE_E_ARG;
     }
     const int npad = (int)npad_of(n);
-    FactorBuffers fb{l.KB, L ? L : l.L, l.Lt, Linv ? Linv : l.Linv, l.U, l.Q, l.diag, l.stat, (int*)(l.stat + 2 * batch), 0};
+    FactorBuffers fb{l.KB, L ? L : l.L, l.Lt, Linv ? Linv : l.Linv, l.U, l.Q, l.diag, l.stat, (int*)(l.stat + 2 * batch), 0, 0};
     if (int32_t rc = launch_prescale(stream, X, n, d, ls, d, l.xs, npad, d * (int64_t)npad, (int)batch)) return rc;
     KmatArgs ka{};
     ka.xa = X; ka.xb = X; ka.ls = ls; ka.kv_ptr = kv; ka.out = fb.KB;
@@ -391,9 +391,9 @@ extern "C" int32_t bobe_fantasy_var(void* stream_, int32_t kind, const double* X
         return launch_kmat(stream, kind, a, 1);
     };
     auto apply_linv = [&](const double* Kin, int64_t rows_pad, double* Vout) {  // Vout[j][i] = sum_k Kin[j][k] Linv[i][k]
-        GemmArgs g{};
-        g.A = Kin; g.Bt = Linv; g.C = Vout; g.lda = g.ldb = g.ldc = npad;
-        g.M = (int)rows_pad; g.N = (int)npad; g.K = (int)npad; g.alpha = 1.0; g.flags = GEMM_B_LOWER;
+        GemmArgs g{};  // computed as V = Linv * Kin^T with only the transposed store (triangular operand = row operand)
+        g.A = Linv; g.Bt = Kin; g.C = nullptr; g.Ct = Vout; g.lda = g.ldb = g.ldct = npad;
+        g.M = (int)npad; g.N = (int)rows_pad; g.K = (int)npad; g.alpha = 1.0; g.flags = GEMM_A_LOWER;
         return launch_gemm_nt(stream, g, 1);
     };
     auto rows_sumsq = [&](const double* Vin, int64_t rows, double* o) {

@@ -68,10 +68,11 @@ struct Rec {
             g.alpha = 1.0;
             return g;
         };
-        {   // L21 = A21 * Linv11^T   (stored as L21 and as its transpose)
+        {   // L21 = A21 * Linv11^T, computed as its transpose L21^T = Linv11 * A21^T so that the triangular operand
+            // is the row operand (fragment-level skipping of its zeros); both orientations are stored either way
             GemmArgs g = base();
-            g.A = at(fb.KB, mid, b0); g.Bt = at(fb.Linv, b0, b0); g.C = at(fb.L, mid, b0); g.Ct = at(fb.Lt, b0, mid);
-            g.M = m2; g.N = m1; g.K = m1; g.flags = GEMM_B_LOWER;
+            g.A = at(fb.Linv, b0, b0); g.Bt = at(fb.KB, mid, b0); g.C = at(fb.Lt, b0, mid); g.Ct = at(fb.L, mid, b0);
+            g.M = m1; g.N = m2; g.K = m1; g.flags = GEMM_A_LOWER;
             gemm(g);
         }
         // Correction of the panel solve, only for ill-conditioned matrices (gate set by the leaves):
@@ -104,21 +105,29 @@ struct Rec {
             g.M = m2; g.N = m1; g.K = m2; g.flags = GEMM_A_LOWER;
             gemm(g);
         }
-        {   // Linv21 = -Q * Linv11   (stored as Linv21 and as U12 = Linv21^T)
+        {   // Linv21 = -Q * Linv11, computed as U12 = Linv21^T = -U11 * Q^T (triangular operand as the row operand)
             GemmArgs g = base();
-            g.A = fb.Q; g.lda = m1; g.strideA = qstride;
-            g.Bt = at(fb.U, b0, b0); g.C = at(fb.Linv, mid, b0); g.Ct = at(fb.U, b0, mid);
-            g.M = m2; g.N = m1; g.K = m1; g.alpha = -1.0; g.flags = GEMM_B_UPPER;
+            g.A = at(fb.U, b0, b0); g.Bt = fb.Q; g.ldb = m1; g.strideB = qstride;
+            g.C = at(fb.U, b0, mid); g.Ct = at(fb.Linv, mid, b0);
+            g.M = m1; g.N = m2; g.K = m1; g.alpha = -1.0; g.flags = GEMM_A_UPPER;
             gemm(g);
         }
     }
 };
 }  // namespace
 
-// zero the off-diagonal upper blocks of L/Linv and lower blocks of Lt/U (the GEMMs never write them)
-__global__ void zero_other_triangle_kernel(double* L, double* Lt, double* Linv, double* U, int npad) {
+// zero the off-diagonal upper blocks of L/Linv and lower blocks of Lt/U (the GEMMs never write them).
+// band > 0: only the blocks within `band` block columns of the diagonal.  A tile of a triangular operand is read up
+// to the end of the 128-wide k-tile that holds its diagonal, i.e. at most 127 columns beyond it (two 64-blocks);
+// blocks further out are never touched, so the internal (log-ML) path skips them.
+__global__ void zero_other_triangle_kernel(double* L, double* Lt, double* Linv, double* U, int npad, int band) {
     const int64_t zoff = (int64_t)blockIdx.z * npad * npad;
-    const int rb = blockIdx.y, cb = blockIdx.x;
+    const int rb = blockIdx.y;
+    int cb = blockIdx.x;
+    if (band > 0) {  // grid.x = 2 * band: block columns rb - band .. rb - 1 and rb + 1 .. rb + band
+        cb = cb < band ? rb - band + cb : rb + 1 + (cb - band);
+        if (cb < 0 || cb >= npad / NB) return;
+    }
     if (rb == cb) return;
     double* lo0 = (cb > rb) ? L : Lt;     // L, Linv: zero where col block > row block
     double* lo1 = (cb > rb) ? Linv : U;   // Lt, U: zero where col block < row block
@@ -139,7 +148,9 @@ int32_t factor_recursive(cudaStream_t stream, const FactorBuffers& fb, int npad,
     init_stat_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(fb.dstat, fb.gate, batch, fb.force_refine);
     if (int32_t rc = check_launch("init_stat_kernel")) return rc;
     if (nbk > 1) {
-        zero_other_triangle_kernel<<<dim3(nbk, nbk, batch), 256, 0, stream>>>(fb.L, fb.Lt, fb.Linv, fb.U, npad);
+        const int band = fb.zero_band > 0 && 2 * fb.zero_band < nbk ? fb.zero_band : 0;
+        zero_other_triangle_kernel<<<dim3(band ? 2 * band : nbk, nbk, batch), 256, 0, stream>>>(fb.L, fb.Lt, fb.Linv, fb.U,
+                                                                                              npad, band);
         if (int32_t rc = check_launch("zero_other_triangle_kernel")) return rc;
     }
     Rec r{stream, fb, npad, batch, (int64_t)npad * npad, factor_q_elems(npad)};

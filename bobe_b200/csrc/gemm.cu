@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 
 #include "gemm_nt.cuh"
 #include "kernels.cuh"
@@ -44,17 +45,28 @@ int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& a, int batch) {
     const int64_t big_ctas = (int64_t)((a.M + 127) / 128) * ((a.N + 127) / 128) * batch;
     static const int64_t small_below = env_int("BOBE_SMALL_TILE_CTAS", 2 * 148);
     bool small = (a.M <= 64 || a.N <= 64) || big_ctas < small_below;
-    if (small) {
-        using Cfg = CfgSmall;
-        if (int32_t rc = ensure_smem<gemm_nt_kernel<Cfg>>(Cfg::SMEM_BYTES)) return rc;
-        dim3 grid((a.N + Cfg::BN - 1) / Cfg::BN, (a.M + Cfg::BM - 1) / Cfg::BM, batch);
-        gemm_nt_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a);
-    } else {
-        using Cfg = CfgBig;
-        if (int32_t rc = ensure_smem<gemm_nt_kernel<Cfg>>(Cfg::SMEM_BYTES)) return rc;
-        dim3 grid((a.N + Cfg::BN - 1) / Cfg::BN, (a.M + Cfg::BM - 1) / Cfg::BM, batch);
-        gemm_nt_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a);
+    if (!a.C && !a.Ct) {
+        set_error("gemm_nt: no output");
+        return BOBE_E_ARG;
     }
+    const int mode = (a.flags & GEMM_A_LOWER) ? TRI_LOWER : ((a.flags & GEMM_A_UPPER) ? TRI_UPPER : TRI_NONE);
+    auto go = [&](auto cfg, auto mode_c) -> int32_t {
+        using Cfg = decltype(cfg);
+        constexpr int MODE = decltype(mode_c)::value;
+        if (int32_t rc = ensure_smem<gemm_nt_kernel<Cfg, MODE>>(Cfg::SMEM_BYTES)) return rc;
+        dim3 grid((a.N + Cfg::BN - 1) / Cfg::BN, (a.M + Cfg::BM - 1) / Cfg::BM, batch);
+        gemm_nt_kernel<Cfg, MODE><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a);
+        return BOBE_OK;
+    };
+    using M0 = std::integral_constant<int, TRI_NONE>;
+    using M1 = std::integral_constant<int, TRI_LOWER>;
+    using M2 = std::integral_constant<int, TRI_UPPER>;
+    int32_t rc;
+    if (small)
+        rc = mode == TRI_LOWER ? go(CfgSmall{}, M1{}) : (mode == TRI_UPPER ? go(CfgSmall{}, M2{}) : go(CfgSmall{}, M0{}));
+    else
+        rc = mode == TRI_LOWER ? go(CfgBig{}, M1{}) : (mode == TRI_UPPER ? go(CfgBig{}, M2{}) : go(CfgBig{}, M0{}));
+    if (rc) return rc;
     return check_launch("gemm_nt_kernel");
 }
 

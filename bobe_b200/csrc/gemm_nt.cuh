@@ -45,6 +45,8 @@ enum : int {
     GEMM_C_LOWER = 16,  // only tiles touching the lower triangle (j0 <= i0 + BM - 1) are computed
 };
 
+enum : int { TRI_NONE = 0, TRI_LOWER = 1, TRI_UPPER = 2 };  // what Mainloop::run knows about A inside a tile
+
 template <class Cfg>
 struct Mainloop {
     static constexpr int ROWS_PER_SLOT = Cfg::THREADS / (8 * Cfg::PANELS) * 2;  // rows between a thread's chunks
@@ -149,11 +151,12 @@ struct Mainloop {
             }
     }
 
-    // same, for the fragments mf >= lo where lo is uniform over the CTA: a jump into straight-line, unpredicated
-    // MMA code (a warp-dependent bound would cost a predicate and a WARPSYNC per fragment)
-    __device__ static __forceinline__ void mma_panel_from(double (&acc)[Cfg::MF][Cfg::NF][2], const double* sA,
-                                                          const double* sB, int p, int wm, int wn, int g, int t, int lo) {
-        static_assert(Cfg::MF <= 8, "fall-through table below covers 8 fragments");
+    // same, for the fragments mf >= lo (FROM) or mf < hi (UPTO) where the bound is uniform over the CTA: a jump into
+    // straight-line, unpredicated MMA code (a warp-dependent bound would cost a predicate and a WARPSYNC per fragment)
+    template <bool UPTO>
+    __device__ static __forceinline__ void mma_panel_jump(double (&acc)[Cfg::MF][Cfg::NF][2], const double* sA,
+                                                          const double* sB, int p, int wm, int wn, int g, int t, int bound) {
+        static_assert(Cfg::MF <= 8, "fall-through tables below cover 8 fragments");
         double2 a[Cfg::MF], b[Cfg::NF];
 #pragma unroll
         for (int mf = 0; mf < Cfg::MF; ++mf)
@@ -167,8 +170,8 @@ struct Mainloop {
             dmma884(acc[MFI < Cfg::MF ? MFI : 0][nf][0], acc[MFI < Cfg::MF ? MFI : 0][nf][1],                \
                     a[MFI < Cfg::MF ? MFI : 0].XY, b[nf].XY);                                                \
     }
-#define BOBE_PASS(XY)                                  \
-    switch (lo) {                                      \
+#define BOBE_PASS_FROM(XY)                             \
+    switch (bound) {                                   \
         case 0: BOBE_FRAG(0, XY) [[fallthrough]];      \
         case 1: BOBE_FRAG(1, XY) [[fallthrough]];      \
         case 2: BOBE_FRAG(2, XY) [[fallthrough]];      \
@@ -179,48 +182,81 @@ struct Mainloop {
         case 7: BOBE_FRAG(7, XY) break;                \
         default: break;                                \
     }
-        BOBE_PASS(x)
-        BOBE_PASS(y)
-#undef BOBE_PASS
+#define BOBE_PASS_UPTO(XY)                             \
+    switch (bound) {                                   \
+        case 8: BOBE_FRAG(7, XY) [[fallthrough]];      \
+        case 7: BOBE_FRAG(6, XY) [[fallthrough]];      \
+        case 6: BOBE_FRAG(5, XY) [[fallthrough]];      \
+        case 5: BOBE_FRAG(4, XY) [[fallthrough]];      \
+        case 4: BOBE_FRAG(3, XY) [[fallthrough]];      \
+        case 3: BOBE_FRAG(2, XY) [[fallthrough]];      \
+        case 2: BOBE_FRAG(1, XY) [[fallthrough]];      \
+        case 1: BOBE_FRAG(0, XY) break;                \
+        default: break;                                \
+    }
+        if (UPTO) {
+            BOBE_PASS_UPTO(x)
+            BOBE_PASS_UPTO(y)
+        } else {
+            BOBE_PASS_FROM(x)
+            BOBE_PASS_FROM(y)
+        }
+#undef BOBE_PASS_FROM
+#undef BOBE_PASS_UPTO
 #undef BOBE_FRAG
     }
 
     // acc += A[0:BM, kb:ke] * Bt[0:BN, kb:ke]^T   (kb, ke multiples of BK; A/Bt point at the tile's first row)
-    // tri0 / rows_live (optional): A[r][k] == 0 for k > tri0 + r, and rows >= rows_live contribute nothing; the
-    // k8 panels that reach into that region only issue the MMAs of the fragments that can be non-zero.
-    template <bool TRI = false>
+    // MODE tells what is known about A beyond the tile-level k range (tri0 = the tile's first row in operand
+    // coordinates):
+    //   TRI_LOWER  A[r][k] == 0 for k > tri0 + r: the LAST k-tiles reach above the diagonal, fragment mf of warp row
+    //              wm is dead from panel kp > tri0 + frag_row(wm, mf) + 7 on;
+    //   TRI_UPPER  A[r][k] == 0 for k < tri0 + r: the FIRST k-tiles start below the diagonal, the fragment is dead
+    //              while kp + 7 < tri0 + frag_row(wm, mf).
+    // Those k-tiles only issue the MMAs of the fragments that can be non-zero; all others run the branch-free body.
+    // rows_live < BM (TRI_LOWER only): rows beyond it contribute nothing at all (partial first block of trmm_sumsq).
+    template <int MODE = TRI_NONE>
     __device__ static __forceinline__ void run(double (&acc)[Cfg::MF][Cfg::NF][2], const double* A, int64_t lda,
                                                int rowsA, const double* Bt, int64_t ldb, int rowsB, int kb, int ke,
-                                               double* smem, int tri0 = 1 << 30, int rows_live = Cfg::BM) {
+                                               double* smem, int tri0 = 0, int rows_live = Cfg::BM) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const int g = lane >> 2, t = lane & 3;
         const int wm = warp / Cfg::WN, wn = warp % Cfg::WN;
         const int ktiles = (ke - kb) / Cfg::BK;
         Loader ld;
         ld.init(A, lda, rowsA, Bt, ldb, rowsB, kb, smem);
-        // live fragment range of this warp: frag_row(wm, mf) < rows_live  <=>  mf < hi
         constexpr int FSTEP = Cfg::ILV ? 8 * Cfg::WM : 8;  // row distance between consecutive fragments of a warp
+        constexpr int FLAST = Cfg::frag_row(Cfg::WM - 1, 0);  // first row of the last warp row
+        // per-warp live range for the partial-block case: frag_row(wm, mf) < rows_live  <=>  mf < hi
         const int fbase = Cfg::frag_row(wm, 0);
         int hi = (rows_live - fbase + FSTEP - 1) / FSTEP;
         hi = hi < 0 ? 0 : (hi > Cfg::MF ? Cfg::MF : hi);
-        auto panel = [&](const double* sA, const double* sB, int p, int kp) {
-            if (hi == Cfg::MF) {
-                // fragment mf of warp-row wm is live iff kp <= tri0 + frag_row(wm, mf) + 7.  The bound used is the one
-                // of the LAST warp row (CTA-uniform, so the jump needs no warp synchronisation); with interleaved rows
-                // the other warp rows then run at most one dead fragment.
-                constexpr int FLAST = Cfg::frag_row(Cfg::WM - 1, 0);
+
+        // The jump bounds are CTA-uniform: TRI_LOWER uses the bound of the LAST warp row, TRI_UPPER that of the FIRST
+        // (with interleaved rows the other warp rows then run at most one dead fragment).
+        auto panel_lower = [&](const double* sA, const double* sB, int p, int kp) {
+            if (rows_live >= Cfg::BM) {
                 const int rel = kp - tri0 - FLAST - 7;
                 const int lo = rel <= 0 ? 0 : (rel + FSTEP - 1) / FSTEP;
                 if (lo == 0)
                     mma_panel(acc, sA, sB, p, wm, wn, g, t);
                 else
-                    mma_panel_from(acc, sA, sB, p, wm, wn, g, t, lo);
-            } else {  // partial first row block: exact per-warp bounds, predicated
+                    mma_panel_jump<false>(acc, sA, sB, p, wm, wn, g, t, lo);
+            } else {  // partial block: exact per-warp bounds, predicated
                 const int rel = kp - tri0 - fbase - 7;
                 const int lo = rel <= 0 ? 0 : (rel + FSTEP - 1) / FSTEP;
                 if (lo < hi) mma_panel_range(acc, sA, sB, p, wm, wn, g, t, lo, hi);
             }
         };
+        auto panel_upper = [&](const double* sA, const double* sB, int p, int kp) {
+            const int rel = kp + 7 - tri0;  // fragment live iff mf * FSTEP <= rel (first warp row)
+            int up = rel < 0 ? 0 : rel / FSTEP + 1;
+            if (up >= Cfg::MF)
+                mma_panel(acc, sA, sB, p, wm, wn, g, t);
+            else
+                mma_panel_jump<true>(acc, sA, sB, p, wm, wn, g, t, up);
+        };
+        auto panel_full = [&](const double* sA, const double* sB, int p, int) { mma_panel(acc, sA, sB, p, wm, wn, g, t); };
 
 #pragma unroll
         for (int s = 0; s < Cfg::STAGES - 1; ++s) {
@@ -228,20 +264,14 @@ struct Mainloop {
             cp_async_commit();
         }
         int stage = 0;  // stage holding k-tile kt
-        // k-tiles below kt_full are full for every warp: they run the branch-free body (one basic block per
-        // k-tile, so that fragment loads are scheduled across the panels); only the rest pays for the range logic
-        int kt_full = ktiles;
-        if (TRI) {
-            kt_full = rows_live >= Cfg::BM ? (tri0 - kb) / Cfg::BK : 0;
-            kt_full = kt_full < 0 ? 0 : (kt_full > ktiles ? ktiles : kt_full);
-        }
         int kt = 0;
-        for (; kt < kt_full; ++kt) {
+        auto ktile = [&](auto&& panel) {
             cp_async_wait<Cfg::STAGES - 2>();
             __syncthreads();  // k-tile kt has landed for everyone; everyone is done reading k-tile kt-1
             const double* sA = smem + stage * Cfg::STAGE_DOUBLES;
             const double* sB = sA + Cfg::BM * Cfg::BK;
-            mma_panel(acc, sA, sB, 0, wm, wn, g, t);
+            const int kp0 = kb + kt * Cfg::BK;
+            panel(sA, sB, 0, kp0);
             {   // refill the stage freed by k-tile kt-1, issued BEHIND the first panel's MMAs so that the address
                 // arithmetic and the LDGSTS issue overlap with tensor work instead of idling the pipe
                 int nk = kt + Cfg::STAGES - 1;
@@ -250,28 +280,25 @@ struct Mainloop {
                 cp_async_commit();
             }
 #pragma unroll
-            for (int p = 1; p < Cfg::PANELS; ++p) mma_panel(acc, sA, sB, p, wm, wn, g, t);
+            for (int p = 1; p < Cfg::PANELS; ++p) panel(sA, sB, p, kp0 + 8 * p);
             stage = stage + 1 == Cfg::STAGES ? 0 : stage + 1;
+        };
+        int kt_full = ktiles;  // end of the branch-free k-tiles
+        if (MODE == TRI_UPPER) {
+            // k-tiles whose first panel still has a dead fragment: kp0 + 7 - tri0 < (MF - 1) * FSTEP
+            int kt_tri = (tri0 + (Cfg::MF - 1) * FSTEP - 7 - kb + Cfg::BK - 1) / Cfg::BK;
+            kt_tri = kt_tri < 0 ? 0 : (kt_tri > ktiles ? ktiles : kt_tri);
+            for (; kt < kt_tri; ++kt) ktile(panel_upper);
         }
-        if (TRI) {
-            for (; kt < ktiles; ++kt) {
-                cp_async_wait<Cfg::STAGES - 2>();
-                __syncthreads();
-                const double* sA = smem + stage * Cfg::STAGE_DOUBLES;
-                const double* sB = sA + Cfg::BM * Cfg::BK;
-                const int kp0 = kb + kt * Cfg::BK;
-                panel(sA, sB, 0, kp0);
-                {
-                    int nk = kt + Cfg::STAGES - 1;
-                    int nstage = stage == 0 ? Cfg::STAGES - 1 : stage - 1;
-                    if (nk < ktiles) ld.issue(nk, nstage);
-                    cp_async_commit();
-                }
-#pragma unroll
-                for (int p = 1; p < Cfg::PANELS; ++p) panel(sA, sB, p, kp0 + 8 * p);
-                stage = stage + 1 == Cfg::STAGES ? 0 : stage + 1;
-            }
+        if (MODE == TRI_LOWER) {
+            // k-tile kt is full iff its last panel kb + kt BK + 8 (PANELS - 1) <= tri0 + FLAST + 7
+            const int num = tri0 + FLAST + 7 - 8 * (Cfg::PANELS - 1) - kb;
+            kt_full = rows_live >= Cfg::BM ? (num < 0 ? 0 : num / Cfg::BK + 1) : 0;
+            kt_full = kt_full > ktiles ? ktiles : kt_full;
         }
+        for (; kt < kt_full; ++kt) ktile(panel_full);
+        if (MODE == TRI_LOWER)
+            for (; kt < ktiles; ++kt) ktile(panel_lower);
         cp_async_wait<0>();
         __syncthreads();  // smem may be reused by the caller (next tile / epilogue)
     }
@@ -294,7 +321,7 @@ __device__ __forceinline__ void tile_k_range(int flags, int i0, int j0, int BM, 
 struct GemmArgs {
     const double* A;
     const double* Bt;
-    double* C;
+    double* C;        // result (may be null if Ct is given)
     double* Ct;       // optional transposed copy of the result (may be null)
     const double* D;  // optional addend: C = alpha*A*Bt^T + D  (may alias C; null -> 0)
     const int* gate;  // optional per-batch switch: the launch is a no-op for batch entries with gate[z] == 0
@@ -306,7 +333,10 @@ struct GemmArgs {
 };
 
 // Batched NT GEMM with optional dual (normal + transposed) store.  grid = (tiles_n, tiles_m, batch).
-template <class Cfg>
+// MODE: TRI_LOWER needs GEMM_A_LOWER, TRI_UPPER needs GEMM_A_UPPER (fragment-level skipping inside the diagonal
+// k-tiles, see Mainloop::run).  A triangular B operand is brought into this form by the caller computing the
+// transposed product (the kernel stores both orientations anyway).
+template <class Cfg, int MODE>
 __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(GemmArgs p) {
     extern __shared__ __align__(16) double smem[];
     const int i0 = blockIdx.y * Cfg::BM, j0 = blockIdx.x * Cfg::BN;
@@ -324,12 +354,13 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(GemmArgs p) {
 #pragma unroll
         for (int nf = 0; nf < Cfg::NF; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
 
-    Mainloop<Cfg>::run(acc, A, p.lda, min(Cfg::BM, p.M - i0), Bt, p.ldb, min(Cfg::BN, p.N - j0), kb, ke, smem);
+    Mainloop<Cfg>::template run<MODE>(acc, A, p.lda, min(Cfg::BM, p.M - i0), Bt, p.ldb, min(Cfg::BN, p.N - j0), kb, ke, smem,
+                                      i0);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp / Cfg::WN, wn = warp % Cfg::WN;
-    double* C = p.C + z * p.strideC;
+    double* C = p.C ? p.C + z * p.strideC : nullptr;
     double* Ct = p.Ct ? p.Ct + z * p.strideCt : nullptr;
     const double* D = p.D ? p.D + z * p.strideD : nullptr;
 #pragma unroll
@@ -341,13 +372,12 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(GemmArgs p) {
             int col = j0 + wn * Cfg::WTN + nf * 8 + 2 * t;
             if (col >= p.N) continue;  // N is even, so col+1 < N too
             double v0 = p.alpha * acc[mf][nf][0], v1 = p.alpha * acc[mf][nf][1];
-            double2* dst = reinterpret_cast<double2*>(C + (int64_t)row * p.ldc + col);
             if (D) {
                 double2 old = *reinterpret_cast<const double2*>(D + (int64_t)row * p.ldd + col);
                 v0 += old.x;
                 v1 += old.y;
             }
-            *dst = make_double2(v0, v1);
+            if (C) *reinterpret_cast<double2*>(C + (int64_t)row * p.ldc + col) = make_double2(v0, v1);
             if (Ct) {
                 Ct[(int64_t)col * p.ldct + row] = v0;
                 Ct[(int64_t)(col + 1) * p.ldct + row] = v1;
@@ -392,7 +422,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
         const int rows_live = (i0 == 0 && r_first) ? r_first : Cfg::BM;
         int ke = min(kmax, ((i0 + rows_live + Cfg::BK - 1) / Cfg::BK) * Cfg::BK);
         // Linv is lower triangular: row i0 + r is zero beyond column i0 + r
-        Mainloop<Cfg>::template run<true>(acc, Linv + (int64_t)i0 * npad, npad, min(Cfg::BM, npad - i0), Bt, ldk, Cfg::BN, 0,
+        Mainloop<Cfg>::template run<TRI_LOWER>(acc, Linv + (int64_t)i0 * npad, npad, min(Cfg::BM, npad - i0), Bt, ldk, Cfg::BN, 0,
                                           ke, smem, i0, rows_live);
 #pragma unroll
         for (int mf = 0; mf < Cfg::MF; ++mf)
@@ -433,9 +463,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
     }
 }
 
-using CfgBig = TileCfg<128, 128, 2, 4, 4>;   // 256 threads, warp tile 64x32, 128 KB smem
-using CfgTrmm = TileCfg<128, 128, 2, 4, 4, 16, true>;  // same, rows interleaved between the two warp rows
-using CfgSmall = TileCfg<64, 64, 2, 2, 4>;   // 128 threads, warp tile 32x32, 64 KB smem
+// rows are interleaved between the two warp rows in every configuration (harmless for unstructured products)
+using CfgBig = TileCfg<128, 128, 2, 4, 4, 16, true>;   // 256 threads, warp tile 64x32, 128 KB smem
+using CfgTrmm = CfgBig;
+using CfgSmall = TileCfg<64, 64, 2, 2, 4, 16, true>;   // 128 threads, warp tile 32x32, 64 KB smem
 
 int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& args, int batch);
 

@@ -52,6 +52,7 @@ struct FactorBuffers {
     double* dstat; // (batch, 2) running min / max pivot
     int* gate;     // (batch) 1 once max/min pivot exceeds the refinement ratio
     int force_refine;
+    int zero_band;  // 0: zero the whole other triangle (L / Linv handed to the caller); 2: internal use only
 };
 int64_t factor_q_elems(int64_t npad);
 int32_t factor_recursive(cudaStream_t stream, const FactorBuffers& fb, int npad, int batch);

@@ -293,7 +293,7 @@ extern "C" int32_t bobe_mll_grad_batched(void* stream_, int32_t kind, const doub
         rc_all = [&]() -> int32_t {
             FactorBuffers fb{w + l.off_KB + r0 * m2, w + l.off_L + r0 * m2, w + l.off_Lt + r0 * m2,
                              w + l.off_Linv + r0 * m2, w + l.off_U + r0 * m2, w + l.off_Q + r0 * qel,
-                             w + l.off_diag + r0 * npad, w + l.off_stat + 2 * r0, (int*)(w + l.off_stat + 2 * R) + r0, 0};
+                             w + l.off_diag + r0 * npad, w + l.off_stat + 2 * r0, (int*)(w + l.off_stat + 2 * R) + r0, 0, 2};
             double* zws = w + l.off_z + (3 * r0 + si) * npad;  // each sub-batch: own padded y + 3 vectors per restart
             double *alpha = w + l.off_alpha + r0 * npad, *logdet = w + l.off_logdet + r0, *quad = w + l.off_quad + r0;
             double* partial = w + l.off_partial + r0 * l.ntile_pairs * (d + 1);
