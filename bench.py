@@ -232,9 +232,16 @@ def main():
     peaks = _peaks()
     achieved = flops_per_launch / (ms_k / 1e3) / 1e12
     chunks = -(-M // rows)
+    traffic = None  # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (same chunk shape)
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01", "trmm_sumsq_ncu.json")) as f:
+            j = json.load(f)
+        traffic = float(j["dram_bytes_read"]) + float(j["dram_bytes_write"])
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "kernel": "trmm_sumsq_kernel (FP64 DMMA.8x8x4; no tcgen05 f64 kind exists)",
                 "achieved": achieved, "peak": peaks["fp64_dgemm_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["fp64_dgemm_tflops"], "traffic": None,
+                "frac": achieved / peaks["fp64_dgemm_tflops"], "traffic": traffic,
                 "peak_source": peaks["src"], "flops_per_launch": flops_per_launch, "ms_per_launch": ms_k,
                 "share_of_step": chunks * ms_k / ms_step}
 
@@ -278,7 +285,7 @@ def main():
                            "parallelism": f"query-sharded x{world}, replicated factor"},
                 "e2e": {"value": e2e_value, "unit": "pts/s", "h2d_bytes_per_step": M * DIM * 8,
                         "d2h_bytes_per_step": M * 16, "ms_per_step": ms_e2e},
-                "gpu_launches": args.steps * chunks * 2,
+                "gpu_launches": args.steps * (chunks * 2 + 1),  # per step: prescale + (kmat + trmm_sumsq) per chunk
                 "clocks": clocks, "roofline": roofline, "secondary": secondary}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
