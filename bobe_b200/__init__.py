@@ -9,5 +9,6 @@ from .gp import GP, rbf_kernel, matern_kernel, kernel_diag, fast_update_cholesky
 from .acquisition import (AcquisitionFunction, EI, LogEI, WIPV, WIPStd, get_mc_samples, get_mc_points,  # noqa: F401
                           ACQUISITIONS)
 from .optim import optimize_scipy, optimize_optax, optimize_optax_vmap  # noqa: F401
+from .batching import SurrogatePool, lax_map  # noqa: F401
 
 __version__ = "0.1.0"

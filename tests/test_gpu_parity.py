@@ -299,3 +299,21 @@ def test_host_pipelined_predict_matches_device_path():
     ms, vs = gp.predict_batched(xh)  # standardised flavour through the same path
     assert vs.shape == (M, 1) and np.all(vs >= 1e-12)
     assert mixed_err(ms[:500], ref.predict_batched(xh[:500])[0], 1.0) < TOL_MEAN
+
+
+def test_surrogate_pool_on_device_matches_single_point_calls():
+    """lock-step walks through SurrogatePool see exactly the single-point surrogate values."""
+    from bobe_b200 import SurrogatePool, lax_map
+    ref, X, y, Xq, _, _, _ = make_case("M_matern_n300_d3")
+    gp = make_gp(ref)
+    pool = SurrogatePool(gp, size=16)
+    pts = np.random.default_rng(11).uniform(0, 1, (40, 4, 3))  # 40 walks x 4 points
+
+    def walk(i):
+        return [pool.loglike(p) for p in pts[i]]
+    got = np.array(pool.map(walk, range(40)))
+    want = ref.predict_mean_batched(pts.reshape(-1, 3)).reshape(40, 4)
+    assert mixed_err(got, want, ref.y_std) < TOL_MEAN
+    assert pool.n_points == 160 and pool.n_device_calls == 12  # 3 groups (16, 16, 8 walks) x 4 lock-step rounds
+    assert mixed_err(lax_map(gp, "predict_var_single", Xq[:300], batch_size=100), ref.predict_var_batched(Xq[:300]),
+                     ref.y_std ** 2) < TOL_VAR

@@ -226,3 +226,51 @@ def test_mc_points_selection():
     assert pts.shape == (16, 2)
     with pytest.raises(ValueError):
         get_mc_samples(GP(X, y), method="bogus")
+
+
+def test_surrogate_pool_batches_concurrent_single_point_calls():
+    """dynesty-style pool.map of walks that call loglike one point at a time."""
+    from bobe_b200.batching import SurrogatePool, lax_map
+    calls = []
+
+    def fn_batched(xs):
+        calls.append(xs.shape[0])
+        return -0.5 * np.sum((xs - 0.3) ** 2, axis=1)
+
+    pool = SurrogatePool(size=8, fn_batched=fn_batched)
+
+    def walk(seed):  # a proposal walk: a seed-dependent number of dependent single-point evaluations
+        rng = np.random.default_rng(seed)
+        x = rng.uniform(0, 1, 3)
+        best = pool.loglike(x)
+        for _ in range(5 + seed % 4):
+            y = np.clip(x + 0.1 * rng.normal(size=3), 0, 1)
+            v = pool.loglike(y)
+            if v > best:
+                x, best = y, v
+        return seed, x, best
+
+    res = pool.map(walk, range(20))
+    assert [r[0] for r in res] == list(range(20))
+    for seed, x, best in res:  # same answers as an unbatched run
+        assert abs(best - (-0.5 * np.sum((x - 0.3) ** 2))) < 1e-15
+    n_points = sum(6 + s % 4 for s in range(20))
+    assert pool.n_points == n_points and sum(calls) == n_points
+    assert pool.n_device_calls <= 3 * 9 and max(calls) == 8  # three groups of <= 8 walks, <= 9 rounds each
+    assert abs(pool.loglike(np.array([0.3, 0.3, 0.3]))) < 1e-15  # outside map: a batch of one
+
+    def boom(i):
+        pool.loglike(np.zeros(3))
+        if i == 3:
+            raise RuntimeError("walk failed")
+        return pool.loglike(np.ones(3))
+
+    with pytest.raises(RuntimeError, match="walk failed"):
+        pool.map(boom, range(6))
+
+    class FakeGP:
+        def predict_mean_batched(self, xs):
+            return np.sum(xs, axis=1)
+    assert np.allclose(lax_map(FakeGP(), "predict_mean_single", np.ones((5, 2)), batch_size=200), 2.0)
+    with pytest.raises(ValueError):
+        lax_map(FakeGP(), "fit", np.ones((5, 2)))
