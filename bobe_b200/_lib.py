@@ -32,6 +32,10 @@ SIGNATURES = {
     "bobe_predict_workspace_bytes": (_i64, [_i64, _i64, _i64, _i32]),
     "bobe_predict": (_i32, [_vp, _i32, _vp, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _i64, _f64, _f64, _i32, _vp,
                             _vp, _vp, _i64]),
+    "bobe_linv_transpose": (_i32, [_vp, _vp, _i64, _vp]),
+    "bobe_predict_grad_workspace_bytes": (_i64, [_i64, _i64, _i64]),
+    "bobe_predict_grad": (_i32, [_vp, _i32, _vp, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _i64, _f64, _f64, _i32,
+                                 _vp, _vp, _vp, _vp, _vp, _i64]),
     "bobe_fantasy_var_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64]),
     "bobe_fantasy_var": (_i32, [_vp, _i32, _vp, _i64, _i64, _vp, _f64, _f64, _vp, _f64, _vp, _i64, _vp, _i64, _i32,
                                 _vp, _vp, _i64]),

@@ -25,6 +25,33 @@ log = logging.getLogger("bobe_b200.acq")
 FD_STEP = 1e-6
 
 
+def _phi(u):
+    return np.exp(-0.5 * u * u) * 0.3989422804014327
+
+
+def _ndtr(u):
+    from scipy.special import ndtr
+    return ndtr(u)
+
+
+def _ei_ratios(u):
+    """(phi/h, Phi/h) with h(u) = phi(u) + u Phi(u), stable in both tails.
+
+    u > -1: direct.  u <= -1: through R = Phi/phi = sqrt(pi/2) erfcx(-u/sqrt2), h/phi = 1 + u R; below u = -50 the
+    cancellation in 1 + u R (-> 1/u^2) is replaced by its asymptotic series 1/u^2 - 3/u^4 + 15/u^6 - 105/u^8."""
+    from scipy.special import erfcx, ndtr
+    u = np.asarray(u, dtype=np.float64)
+    hi = u > -1.0
+    uh = np.where(hi, u, 0.0)
+    h = _phi(uh) + uh * ndtr(uh)
+    a_hi, b_hi = _phi(uh) / h, ndtr(uh) / h
+    ul = np.where(hi, -1.0, u)
+    R = 1.2533141373155003 * erfcx(-ul * 0.7071067811865476)
+    iu2 = 1.0 / (ul * ul)
+    den = np.where(ul < -50.0, iu2 * (1.0 + iu2 * (-3.0 + iu2 * (15.0 - 105.0 * iu2))), 1.0 + ul * R)
+    return np.where(hi, a_hi, 1.0 / den), np.where(hi, b_hi, R / den)
+
+
 def _fd_batched(fun_batched, lo=0.0, hi=1.0, h=FD_STEP):
     """(R, d) -> values (R,), gradients (R, d) by central differences, one batched call."""
 
@@ -64,9 +91,10 @@ class AcquisitionFunction:
                        verbose: bool = True, early_stop_patience: int = 25, rng=None) -> Tuple[np.ndarray, float]:
         raise NotImplementedError("Base class get_next() not implemented")
 
-    def _optimize(self, fun_batched, x0, gp, maxiter, n_restarts, verbose):
+    def _optimize(self, fun_batched, x0, gp, maxiter, n_restarts, verbose, vg_batched=None):
+        """``vg_batched``: analytic (values, gradients) for (R, d) points; default = batched central differences."""
         x0 = np.atleast_2d(np.asarray(x0, dtype=np.float64))
-        vg_b = _fd_batched(fun_batched)
+        vg_b = vg_batched if vg_batched is not None else _fd_batched(fun_batched)
         opts = dict(self.optimizer_options)
         return self.acq_optimize(fun=None, num_params=gp.ndim, x0=x0, bounds=[0, 1], optimizer_options=opts,
                                  maxiter=maxiter, n_restarts=min(n_restarts, x0.shape[0]), verbose=verbose,
@@ -123,6 +151,31 @@ class EI(AcquisitionFunction):
         """BOBE/acquisition.py:226-253 -- negative EI (the optimiser minimises)."""
         return self.fun_batched(np.atleast_2d(np.asarray(x, dtype=np.float64)), gp, best_y, zeta)[0]
 
+    def value_and_grad_batched(self, x, gp, best_y, zeta):
+        """Negated (log-)EI and its gradient w.r.t. x at (R, d) points -- ``jax.value_and_grad(self.fun)`` of
+        BOBE/optim.py:118,309, analytically: one ``bobe_predict_grad`` pass (standardised mean / variance and their
+        input gradients) + the closed-form partials of the epilogue (chain rule on the host, O(R d))."""
+        xs = np.atleast_2d(np.asarray(x, dtype=np.float64))
+        mu, var, dmu, dvar = gp.predict_grad_batched(xs, standardised=True)
+        floor = 1e-20 if self._which == "ei" else 1e-18  # jnp.clip(var, a_min=...), acquisition.py:247,324
+        clipped = var < floor
+        v = np.maximum(var, floor)
+        sigma = np.sqrt(v)
+        u = (mu - zeta - best_y) / sigma
+        val = ops.acq_ei(self._which, torch.as_tensor(mu, device=gp.device), torch.as_tensor(var, device=gp.device),
+                         float(best_y), float(zeta)).cpu().numpy()
+        if self._which == "ei":  # d(-EI)/dmu = -Phi(u), d(-EI)/dsigma = -phi(u)
+            d_mu = -_ndtr(u)
+            d_v = -_phi(u) / (2.0 * sigma)
+        else:  # log EI = log sigma + log h(u), h = phi + u Phi:  d/dmu = (Phi/h)/sigma,  d/dv = (phi/h)/(2 v)
+            phi_over_h, Phi_over_h = _ei_ratios(u)
+            d_mu = -Phi_over_h / sigma
+            d_v = -phi_over_h / (2.0 * v)
+        d_v = np.where(clipped, 0.0, d_v)
+        # u depends on v through sigma as well; the partials above already are the total derivatives in (mu, v)
+        grad = d_mu[:, None] * dmu + d_v[:, None] * dvar
+        return val, grad
+
     def get_next_point(self, gp, acq_kwargs, maxiter: int = 250, n_restarts: int = 20, verbose: bool = True,
                        early_stop_patience: int = 25, rng=None):
         """BOBE/acquisition.py:255-291."""
@@ -140,7 +193,7 @@ class EI(AcquisitionFunction):
         jitter = rng.normal(0., 0.005, size=x0_acq.shape)
         x0_acq = np.clip(x0_acq + jitter, 0., 1.)
         pts, vals = self._optimize(lambda xs: self.fun_batched(xs, gp, best_y, zeta), x0_acq, gp, maxiter, n_restarts,
-                                   verbose)
+                                   verbose, vg_batched=lambda xs: self.value_and_grad_batched(xs, gp, best_y, zeta))
         return pts, -vals  # we minimise -EI
 
 

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libbobe_b200.so")
-SOURCES = ["abi.cu", "gemm.cu", "kernel_matrix.cu", "factor.cu", "mll_grad.cu"]
+SOURCES = ["abi.cu", "gemm.cu", "kernel_matrix.cu", "factor.cu", "mll_grad.cu", "predict_grad.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
               "-Xcompiler", "-fPIC,-O2,-fvisibility=default", "-Xptxas", "-v"]
 

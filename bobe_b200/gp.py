@@ -241,6 +241,7 @@ class GP:
     def _invalidate(self):
         self._factor_ok = False
         self._X_dev = self._y_dev = self._ls_dev = self._L_dev = self._Linv_dev = self._alpha_dev = None
+        self._LinvT_dev = None
         self._cholesky_np = self._alphas_np = None
         self._info = 0
 
@@ -456,6 +457,47 @@ class GP:
         """BOBE/gp.py:491-493 -- ((M,), (M, 1))."""
         m, v = self._predict(x, True, True, True)
         return m, v.reshape(-1, 1)
+
+    # ---- input gradients (SURVEY.md 8f row 2) -----------------------------------------------------------------
+    def _ensure_linvT(self):
+        """Linv^T on the device, built once per factorisation (the variance gradient needs w = Linv^T (Linv k*))."""
+        self._ensure_factor()
+        if self._LinvT_dev is None:
+            self._LinvT_dev = ops.linv_transpose(self._Linv_dev, self.train_x.shape[0])
+        return self._LinvT_dev
+
+    def predict_grad_batched(self, x, standardised=False, want_mean=True, want_var=True):
+        """(mean, var, dmean/dx, dvar/dx) at (M, d) points: ``jax.value_and_grad`` of ``predict_mean_single`` /
+        ``predict_var_single`` (``standardised=False``) or of ``predict_single`` (``standardised=True``) with respect
+        to the query point -- the derivative the reference takes for NUTS on the surrogate
+        (``BOBE/samplers.py:268-285``) and for EI / LogEI optimisation (``BOBE/acquisition.py:281-290``).
+        Entries not requested are ``None``."""
+        as_t = _is_t(x)
+        if self.train_x.shape[0] == 0:
+            raise ValueError("GP has no training points")
+        xq = _to_dev(x, self.device)
+        if xq.dim() == 1:
+            xq = xq[None, :]
+        if xq.shape[1] != self.ndim:
+            raise ValueError(f"query points must have {self.ndim} columns")
+        self._ensure_factor()
+        linvT = self._ensure_linvT() if want_var else None
+        out = ops.predict_grad(self.kernel_name, self._X_dev, self._ls_dev, float(self.kernel_variance),
+                               float(self.noise), self._Linv_dev, linvT, self._alpha_dev, xq, float(self.y_mean),
+                               float(self.y_std), want_mean, want_var, standardised)
+        if as_t:
+            return out if x.is_cuda else tuple(o.cpu() if o is not None else None for o in out)
+        return tuple(o.cpu().numpy() if o is not None else None for o in out)
+
+    def predict_mean_value_and_grad(self, x):
+        """``jax.value_and_grad(gp.predict_mean_single)(x)``: un-standardised mean and its (d,) gradient."""
+        m, _, dm, _ = self.predict_grad_batched(np.atleast_2d(x) if not _is_t(x) else x, False, True, False)
+        return m[0], dm[0]
+
+    def predict_var_value_and_grad(self, x):
+        """``jax.value_and_grad(gp.predict_var_single)(x)``."""
+        _, v, _, dv = self.predict_grad_batched(np.atleast_2d(x) if not _is_t(x) else x, False, False, True)
+        return v[0], dv[0]
 
     # ---- update ------------------------------------------------------------------------------------------
     def update(self, new_x, new_y):

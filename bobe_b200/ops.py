@@ -136,6 +136,39 @@ def predict(kind: str, X, ls, kv: float, noise: float, Linv, alpha, Xq, y_mean: 
     return mean, var
 
 
+def linv_transpose(Linv, n: int) -> torch.Tensor:
+    """Linv^T (npad, npad) from the padded inverse factor of ``factorize``."""
+    Linv = _chk(Linv, "Linv")
+    out = torch.empty_like(Linv)
+    with torch.cuda.device(Linv.device):
+        check(lib.bobe_linv_transpose(_stream(), Linv.data_ptr(), n, out.data_ptr()), "bobe_linv_transpose")
+    return out
+
+
+def predict_grad(kind: str, X, ls, kv: float, noise: float, Linv, LinvT, alpha, Xq, y_mean: float, y_std: float,
+                 want_mean: bool = True, want_var: bool = True, standardised: bool = False):
+    """(mean, var, dmean/dx, dvar/dx) at Xq (M, d) -- value_and_grad of BOBE/gp.py:450-489 w.r.t. the query point."""
+    X, ls, Xq = _chk(X, "X"), _chk(ls, "ls"), _chk(Xq, "Xq")
+    n, d = X.shape
+    M = Xq.shape[0]
+    dev = X.device
+    mode = (_lib.PREDICT_MEAN if want_mean else 0) | (_lib.PREDICT_VAR if want_var else 0) | \
+           (_lib.PREDICT_STANDARDISED if standardised else 0)
+    new = lambda *shape: torch.empty(shape, dtype=torch.float64, device=dev)
+    mean, dmean = (new(M), new(M, d)) if want_mean else (None, None)
+    var, dvar = (new(M), new(M, d)) if want_var else (None, None)
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.bobe_predict_grad_workspace_bytes(n, d, M), dev)
+        check(lib.bobe_predict_grad(_stream(), KIND[kind], X.data_ptr(), n, d, ls.data_ptr(), float(kv), float(noise),
+                                    ptr(_chk(Linv, "Linv")) if want_var else None,
+                                    ptr(_chk(LinvT, "LinvT")) if want_var else None,
+                                    ptr(_chk(alpha, "alpha")) if want_mean else None, Xq.data_ptr(), M, float(y_mean),
+                                    float(y_std), mode, ptr(mean), ptr(var), ptr(dmean), ptr(dvar), ws.data_ptr(),
+                                    ws.numel()), "bobe_predict_grad")
+    return mean, var, dmean, dvar
+
+
 def fantasy_var(kind: str, X, ls, kv: float, noise: float, Linv, y_std: float, Xmc, Xcand=None, reduce: str = "none"):
     """Fantasy variance at the MC points for each candidate -- BOBE/gp.py:552-576, acquisition.py:438-465."""
     X, ls, Xmc, Linv = _chk(X, "X"), _chk(ls, "ls"), _chk(Xmc, "Xmc"), _chk(Linv, "Linv")

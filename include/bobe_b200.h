@@ -91,6 +91,22 @@ int32_t bobe_predict(void* stream, int32_t kind, const double* X, int64_t n, int
                      double y_mean, double y_std, int32_t mode, double* mean_out, double* var_out, void* ws,
                      int64_t ws_bytes);
 
+/* LinvT = Linv^T (npad, npad) -- the second orientation of the inverse factor, which the input gradient of the
+ * variance needs for w = K^-1 k* = Linv^T (Linv k*); built once per factorisation and cached by the caller. */
+int32_t bobe_linv_transpose(void* stream, const double* Linv, int64_t n, double* LinvT);
+
+/* posterior mean / variance AND their gradients with respect to the query point
+ * -- what jax.grad / jax.value_and_grad of predict_mean_single / predict_var_single / predict_single
+ *    (BOBE/gp.py:450-489) yield where the reference differentiates the surrogate: NUTS BOBE/samplers.py:268-285,
+ *    EI / LogEI optimisation BOBE/acquisition.py:281-290 via BOBE/optim.py:118,309.
+ * Same mode bits and value semantics as bobe_predict; dmean_out / dvar_out are (M, d).  The gradient of the
+ * variance is zero where the floor / clip of BOBE/gp.py:465,487-488 is active. */
+int64_t bobe_predict_grad_workspace_bytes(int64_t n, int64_t d, int64_t M);
+int32_t bobe_predict_grad(void* stream, int32_t kind, const double* X, int64_t n, int64_t d, const double* ls, double kv,
+                          double noise, const double* Linv, const double* LinvT, const double* alpha, const double* Xq,
+                          int64_t M, double y_mean, double y_std, int32_t mode, double* mean_out, double* var_out,
+                          double* dmean_out, double* dvar_out, void* ws, int64_t ws_bytes);
+
 /* fantasy variance at n_mc Monte-Carlo points for C candidate points
  * -- GP.fantasy_var BOBE/gp.py:552-576 (fast_update_cholesky :181-197 folded in algebraically) and the
  *    WIPV / WIPStd reductions BOBE/acquisition.py:438-440,463-465, candidate sweep :390-397.

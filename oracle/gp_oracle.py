@@ -382,6 +382,46 @@ class OracleGP:
         m, v = self.predict_batched(np.atleast_2d(x))
         return float(m[0]), v[0]
 
+    def predict_grad_batched(self, x, standardised=False):
+        """(mean, var, dmean/dx, dvar/dx): the reverse-mode derivative of predict_mean_single / predict_var_single
+        (standardised=False, BOBE/gp.py:450-466) or predict_single (standardised=True, BOBE/gp.py:476-489) with
+        respect to the query point, as jax.grad yields at BOBE/samplers.py:268-285 and BOBE/optim.py:118,309.
+
+          dk(x, x_j)/dx = -G_j (x - x_j) / l^2,  G = k (RBF) or kv 5/3 (1 + sqrt5 r) exp(-sqrt5 r) (Matern; 0 where the
+          1e-30 clamp of gp.py:162 is active);  dmean = sum_j alpha_j dk_j;  dvar = -2 sum_j (K^-1 k*)_j dk_j, zero
+          where the clip / where floor of gp.py:465,487-488 is active.  Pinned by central differences in
+          tests/test_oracle.py.
+        """
+        x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+        ls, kv = self.lengthscales, self.kernel_variance
+        xs, qs = self.train_x / ls, x / ls
+        q = dist_sq(qs, xs)  # (M, n)
+        if self.kernel_name == "rbf":
+            k = kv * np.exp(-0.5 * q)
+            G = k
+        else:
+            clamped = q < 1e-30
+            r = np.sqrt(np.where(clamped, 1e-30, q))
+            e = np.exp(-SQRT5 * r)
+            k = kv * (1.0 + r * (SQRT5 + r * 5.0 / 3.0)) * e
+            G = np.where(clamped, 0.0, kv * (5.0 / 3.0) * (1.0 + SQRT5 * r) * e)
+        alpha = self.alphas.ravel()
+        mean = k @ alpha
+        vv = sla.solve_triangular(self.cholesky, k.T, lower=True, check_finite=False)
+        var = (kv + self.noise) - np.sum(vv * vv, axis=0)
+        w = sla.solve_triangular(self.cholesky.T, vv, lower=False, check_finite=False).T  # (M, n) = K^-1 k*
+        diff = (x[:, None, :] - self.train_x[None, :, :]) / (ls * ls)  # (M, n, d)
+        dmean = -np.einsum("mj,mjk->mk", alpha[None, :] * G, diff)
+        dvar = 2.0 * np.einsum("mj,mjk->mk", w * G, diff)
+        if standardised:
+            var = np.where(np.isnan(var), SAFE_NOISE_FLOOR, var)
+        floored = ~(var > SAFE_NOISE_FLOOR)
+        var = np.where(var < SAFE_NOISE_FLOOR, SAFE_NOISE_FLOOR, var)
+        dvar = np.where(floored[:, None], 0.0, dvar)
+        if standardised:
+            return mean, var, dmean, dvar
+        return mean * self.y_std + self.y_mean, var * self.y_std**2, dmean * self.y_std, dvar * self.y_std**2
+
     # -- update --------------------------------------------------------------------------------
     def update(self, new_x, new_y):
         """BOBE/gp.py:495-541 -- dedupe (isclose atol 1e-6 rtol 1e-4 on all dims), re-standardise, re-factor."""

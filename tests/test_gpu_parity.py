@@ -317,3 +317,52 @@ def test_surrogate_pool_on_device_matches_single_point_calls():
     assert pool.n_points == 160 and pool.n_device_calls == 12  # 3 groups (16, 16, 8 walks) x 4 lock-step rounds
     assert mixed_err(lax_map(gp, "predict_var_single", Xq[:300], batch_size=100), ref.predict_var_batched(Xq[:300]),
                      ref.y_std ** 2) < TOL_VAR
+
+
+@pytest.mark.parametrize("name", ["A_banana_rbf_n100_d2", "M_matern_n300_d3", "B_rbf_n500_d6"])
+def test_input_gradients_match_oracle(name):
+    """d mean / dx and d var / dx (bobe_predict_grad) against the oracle's analytic gradient
+    (itself pinned by central differences in tests/test_oracle.py); values must equal the value-only call bitwise."""
+    ref, X, y, Xq, _, _, _ = make_case(name)
+    gp = make_gp(ref)
+    xq = Xq[:257]
+    for std in (False, True):
+        mean, var, dm, dv = gp.predict_grad_batched(xq, standardised=std)
+        rm, rv, rdm, rdv = ref.predict_grad_batched(xq, standardised=std)
+        if std:
+            m0, v0 = gp.predict_batched(xq)
+        else:
+            m0, v0 = gp.predict_mean_batched(xq), gp.predict_var_batched(xq)
+        assert np.array_equal(mean, m0) and np.array_equal(var, np.ravel(v0))
+        ms, vs = (1.0, 1.0) if std else (ref.y_std, ref.y_std ** 2)
+        assert mixed_err(dm, rdm, max(float(np.abs(rdm).max()), ms)) < TOL_GRAD
+        assert mixed_err(dv, rdv, max(float(np.abs(rdv).max()), vs)) < TOL_GRAD
+    # single-point value_and_grad flavours and the floor: zero variance gradient at a training point
+    m, g = gp.predict_mean_value_and_grad(xq[0])
+    assert g.shape == (X.shape[1],) and abs(m - ref.predict_mean_single(xq[0])) <= TOL_MEAN * max(abs(m), ref.y_std)
+    gp0 = make_gp(O.OracleGP(X, y, kernel=ref.kernel_name, noise=1e-14, lengthscales=ref.lengthscales))
+    _, v, _, dv = gp0.predict_grad_batched(X[:3], standardised=True)
+    assert np.all(dv[v <= 1e-12] == 0.0)
+
+
+@pytest.mark.parametrize("cls_name", ["EI", "LogEI"])
+def test_acquisition_analytic_gradient(cls_name):
+    """Analytic d(-EI)/dx and d(-LogEI)/dx (one bobe_predict_grad pass + closed-form partials) against central
+    differences of the value path, including far-tail points for LogEI."""
+    import bobe_b200
+    ref, X, y, Xq, _, _, _ = make_case("M_matern_n300_d3")
+    gp = make_gp(ref)
+    acq = getattr(bobe_b200, cls_name)()
+    best = float(ref.train_y.max())
+    for b in ((best,) if cls_name == "EI" else (best, best + 30.0)):  # best + 30: u ~ -100 .. -1000 (tail branch)
+        xs = Xq[:64]
+        val, grad = acq.value_and_grad_batched(xs, gp, b, 0.01)
+        assert np.allclose(val, acq.fun_batched(xs, gp, b, 0.01), rtol=1e-12, atol=1e-300)
+        h = 1e-6
+        for k in range(3):
+            e = np.zeros(3); e[k] = h
+            fd = (acq.fun_batched(xs + e, gp, b, 0.01) - acq.fun_batched(xs - e, gp, b, 0.01)) / (2 * h)
+            scale = np.maximum(np.abs(fd), np.abs(grad).max() * 1e-3)
+            # sigma ~ 1e-4 near 300 points in 3-D: |d log EI| ~ 1e5 .. 1e6 with curvature to match, so for LogEI the
+            # difference quotient is the noisy side of the comparison
+            assert np.max(np.abs(grad[:, k] - fd) / scale) < (2e-5 if cls_name == "EI" else 3e-4)

@@ -247,3 +247,31 @@ def test_golden_fixtures_are_reproduced_by_the_oracle(name):
         pl = gp.log_prior_and_grad(x0[0])[0]
         assert abs((-gold["neg_mll"][0] - pl) - float(gold["truth_mll"])) < 1e-8 * X.shape[0]
         assert mixed_err(gold["mean_std"][:32], gold["truth_mean_std"], 1.0) < 1e-9
+
+
+@pytest.mark.parametrize("kernel", ["rbf", "matern"])
+def test_oracle_input_gradients_match_central_differences(kernel):
+    """Pins OracleGP.predict_grad_batched against central differences of the oracle's own
+    predict_mean / predict_var, both flavours."""
+    rng = np.random.default_rng(5)
+    n, d = 60, 3
+    X = rng.uniform(0, 1, (n, d))
+    y = np.sin(4 * X.sum(1, keepdims=True)) + 0.3 * X[:, :1]
+    gp = O.OracleGP(X, y, kernel=kernel, noise=1e-6, lengthscales=np.array([0.4, 0.7, 0.55]), kernel_variance=1.3)
+    xq = rng.uniform(0.05, 0.95, (7, d))
+    h = 1e-5  # |alpha| ~ 3e3 here: the difference quotient itself is only good to ~1e-7 relative
+    for std in (False, True):
+        mean, var, dm, dv = gp.predict_grad_batched(xq, standardised=std)
+        f = (lambda z: gp.predict_batched(z)) if std else (lambda z: (gp.predict_mean_batched(z), gp.predict_var_batched(z)))
+        m0, v0 = f(xq)
+        assert np.allclose(mean, m0, rtol=1e-9, atol=1e-9) and np.allclose(var, np.ravel(v0), rtol=1e-8, atol=1e-12)
+        for k in range(d):
+            e = np.zeros(d); e[k] = h
+            mp, vp = f(xq + e); mm, vm = f(xq - e)
+            assert np.allclose(dm[:, k], (np.ravel(mp) - np.ravel(mm)) / (2 * h), rtol=5e-6, atol=1e-6)
+            assert np.allclose(dv[:, k], (np.ravel(vp) - np.ravel(vm)) / (2 * h), rtol=5e-5, atol=1e-7)
+    # at a training point the variance sits on the floor: zero gradient, like jnp.clip / jnp.where
+    _, v, _, dv = gp.predict_grad_batched(X[:2], standardised=True)
+    gp0 = O.OracleGP(X, y, kernel=kernel, noise=1e-14, lengthscales=np.array([0.4, 0.7, 0.55]), kernel_variance=1.3)
+    _, v, _, dv = gp0.predict_grad_batched(X[:2], standardised=True)
+    assert np.all(dv[v <= 1e-12] == 0.0)
