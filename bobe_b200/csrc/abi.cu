@@ -272,6 +272,32 @@ extern "C" int32_t bobe_factorize(void* stream_, int32_t kind, const double* X, 
                                 info);
 }
 
+// ---- rank-b append ------------------------------------------------------------------------------------------
+extern "C" int64_t bobe_factor_append_workspace_bytes(int64_t n_new, int64_t d) {
+    (void)d;
+    if (n_new <= 0) return 0;
+    return append_ws_doubles(npad_of(n_new)) * 8 + 256;
+}
+
+extern "C" int32_t bobe_factor_append(void* stream_, int32_t kind, const double* X, const double* y, int64_t n_old,
+                                      int64_t b, int64_t d, const double* ls, double kv, double noise, double* L,
+                                      double* Linv, double* alpha, int32_t* info, void* ws, int64_t ws_bytes) {
+    if (!X || !y || !ls || !L || !Linv || !alpha || !info || !ws || n_old < 0 || b <= 0 || d <= 0 || d > BOBE_MAX_DIM) {
+        set_error("factor_append: bad arguments");
+        return BOBE_E_ARG;
+    }
+    if (ws_bytes < bobe_factor_append_workspace_bytes(n_old + b, d)) {
+        set_error("factor_append: workspace too small (%lld < %lld)", (long long)ws_bytes,
+                  (long long)bobe_factor_append_workspace_bytes(n_old + b, d));
+        return BOBE_E_WORKSPACE;
+    }
+    if (!aligned16(L) || !aligned16(Linv)) {
+        set_error("factor_append: L / Linv must be 16-byte aligned");
+        return BOBE_E_ARG;
+    }
+    return factor_append((cudaStream_t)stream_, kind, X, y, n_old, b, d, ls, kv, noise, L, Linv, alpha, info, align256(ws));
+}
+
 // ---- predict --------------------------------------------------------------------------------------------
 extern "C" int64_t bobe_predict_workspace_bytes(int64_t n, int64_t d, int64_t M, int32_t mode) {
     if (M <= 0 || n <= 0 || d <= 0) return 256;

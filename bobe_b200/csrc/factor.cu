@@ -279,4 +279,135 @@ int32_t launch_solve_vectors(cudaStream_t stream, const FactorBuffers& fb, const
     return check_launch("solve_vectors");
 }
 
+// ---- rank-b append: GP.update without the O(n^3) rebuild -------------------------------------
+// With the hyper-parameters unchanged (BOBE/gp.py:541 re-factors the whole matrix), appending point m to a factor of
+// the first m points is exactly one more step of the recursion above with a 1-row second block:
+//   v = Linv k  (+ the panel correction  v += Linv (k - L v));   delta^2 = k** - v.v;
+//   L[m] = [v^T, delta];   Linv[m] = [-(v^T Linv) / delta, 1 / delta]
+// i.e. O(m^2) per point; alpha is then re-solved for the (re-standardised) targets of all points, with the same
+// refinement step the batched factorisation applies to ill-conditioned matrices.
+__global__ void __launch_bounds__(256) vec_sub_kernel(const double* a, const double* b, double* out, int n) {
+    int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) out[i] = a[i] - b[i];
+}
+
+// delta from v, row m of L;  scal[0] = delta, scal[1] = 1 / delta;  *info |= 1 if the pivot is not positive
+__global__ void __launch_bounds__(256) append_row_L_kernel(const double* __restrict__ v, int m, int npad, double kk,
+                                                           double* __restrict__ L, double* __restrict__ scal,
+                                                           int32_t* __restrict__ info) {
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < m; i += 256) {
+        double vi = v[i];
+        s = fma(vi, vi, s);
+        L[(int64_t)m * npad + i] = vi;
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        const double d2 = kk - t;
+        const double dl = sqrt(d2);  // NaN for a negative pivot, like the reference's jnp.sqrt (BOBE/gp.py:187)
+        if (!(d2 > 0.0) || isinf(d2)) *info = 1;
+        L[(int64_t)m * npad + m] = dl;
+        scal[0] = dl;
+        scal[1] = 1.0 / dl;
+    }
+}
+
+// out[j] = scale * sum_{i=j}^{m-1} x[i] Mtx[i][j]   (x^T times a lower-triangular matrix; one thread per column,
+// consecutive threads read consecutive addresses of each row).  scale_ptr (device) overrides scale when given.
+__global__ void __launch_bounds__(128) vecmat_lower_kernel(const double* __restrict__ Mtx, const double* __restrict__ x,
+                                                           int m, int npad, double scale,
+                                                           const double* __restrict__ scale_ptr, int accumulate,
+                                                           double* __restrict__ out) {
+    const int j = blockIdx.x * 128 + threadIdx.x;
+    if (j >= m) return;
+    double s0 = 0.0, s1 = 0.0;
+    int i = j;
+    for (; i + 1 < m; i += 2) {
+        s0 = fma(x[i], Mtx[(int64_t)i * npad + j], s0);
+        s1 = fma(x[i + 1], Mtx[(int64_t)(i + 1) * npad + j], s1);
+    }
+    if (i < m) s0 = fma(x[i], Mtx[(int64_t)i * npad + j], s0);
+    const double sc = scale_ptr ? -scale_ptr[1] : scale;
+    double r = sc * (s0 + s1);
+    if (accumulate) r += out[j];
+    out[j] = r;
+}
+
+__global__ void append_diag_Linv_kernel(double* Linv, int m, int npad, const double* scal) {
+    Linv[(int64_t)m * npad + m] = scal[1];
+}
+
+int64_t append_ws_doubles(int64_t npad) { return 8 * npad + 64 * npad + 64; }
+
+int32_t factor_append(cudaStream_t stream, int kind, const double* X, const double* y, int64_t n_old, int64_t b, int64_t d,
+                      const double* ls, double kv, double noise, double* L, double* Linv, double* alpha, int32_t* info,
+                      double* ws) {
+    const int npad = (int)npad_of(n_old + b);
+    double* kbuf = ws;                    // (64, npad): row 0 is k(x_m, X); the tile kernel needs 64 padded rows
+    double* v = kbuf + 64 * (int64_t)npad;
+    double* tmp = v + npad;
+    double* r = tmp + npad;
+    double* ypad = r + npad;
+    double* z = ypad + npad;
+    double* k0a = z + npad;
+    double* scal = k0a + npad;            // delta, 1/delta
+    const double kk = kv + noise;
+    if (cudaMemsetAsync(info, 0, sizeof(int32_t), stream) != cudaSuccess) {
+        set_error("factor_append: memset failed");
+        return BOBE_E_CUDA;
+    }
+    const dim3 mv_grid((npad + 7) / 8, 1);
+    for (int64_t p = 0; p < b; ++p) {
+        const int m = (int)(n_old + p);
+        if (cudaMemsetAsync(kbuf, 0, (size_t)npad * 8, stream) != cudaSuccess) {
+            set_error("factor_append: memset failed");
+            return BOBE_E_CUDA;
+        }
+        KmatArgs ka{};
+        ka.xa = X + (int64_t)m * d; ka.xb = X; ka.ls = ls; ka.kv = kv; ka.noise = noise; ka.out = kbuf;
+        ka.n1 = 1; ka.n2 = m; ka.d = d; ka.ldo = npad; ka.rows_pad = 64; ka.cols_pad = round_up(m, 64);
+        ka.store_rows = 1; ka.store_cols = ka.cols_pad; ka.vec_ok = 1;
+        if (m > 0)
+            if (int32_t rc = launch_kmat(stream, kind, ka, 1)) return rc;
+        // v = Linv k;  tmp = L v;  r = k - tmp;  v += Linv r     (rows >= m of the padded factors are identity rows and
+        // k is zero there, so the padded part of every vector stays zero)
+        matvec_tri_kernel<<<mv_grid, 256, 0, stream>>>(Linv, kbuf, 0, v, 0, npad, 0, 0, nullptr);
+        matvec_tri_kernel<<<mv_grid, 256, 0, stream>>>(L, v, 0, tmp, 0, npad, 0, 0, nullptr);
+        vec_sub_kernel<<<(npad + 255) / 256, 256, 0, stream>>>(kbuf, tmp, r, npad);
+        matvec_tri_kernel<<<mv_grid, 256, 0, stream>>>(Linv, r, 0, v, 0, npad, 0, 1, nullptr);
+        append_row_L_kernel<<<1, 256, 0, stream>>>(v, m, npad, kk, L, scal, info);
+        if (m > 0) vecmat_lower_kernel<<<(m + 127) / 128, 128, 0, stream>>>(Linv, v, m, npad, 0.0, scal, 0, Linv + (int64_t)m * npad);
+        append_diag_Linv_kernel<<<1, 1, 0, stream>>>(Linv, m, npad, scal);
+        if (int32_t rc = check_launch("factor_append row")) return rc;
+    }
+    // alpha = Linv^T (Linv y), then one refinement step against the rebuilt K:  alpha += K^-1 (y - K alpha)
+    const int n = (int)(n_old + b);
+    pad_y_kernel<<<(npad + 255) / 256, 256, 0, stream>>>(y, n, npad, ypad);
+    matvec_tri_kernel<<<mv_grid, 256, 0, stream>>>(Linv, ypad, 0, z, 0, npad, 0, 0, nullptr);
+    if (cudaMemsetAsync(alpha, 0, (size_t)npad * 8, stream) != cudaSuccess) {
+        set_error("factor_append: memset failed");
+        return BOBE_E_CUDA;
+    }
+    vecmat_lower_kernel<<<(n + 127) / 128, 128, 0, stream>>>(Linv, z, n, npad, 1.0, nullptr, 0, alpha);
+    {
+        KmatArgs ka{};
+        ka.xa = X; ka.xb = X; ka.ls = ls; ka.kv = kv; ka.alpha = alpha; ka.mean_out = k0a;
+        ka.n1 = n; ka.n2 = n; ka.d = d; ka.rows_pad = npad; ka.cols_pad = npad; ka.mean_standardised = 1;
+        if (cudaMemsetAsync(k0a, 0, (size_t)npad * 8, stream) != cudaSuccess) {
+            set_error("factor_append: memset failed");
+            return BOBE_E_CUDA;
+        }
+        if (int32_t rc = launch_kmat(stream, kind, ka, 1)) return rc;
+        residual_kernel<<<dim3((npad + 255) / 256, 1), 256, 0, stream>>>(ypad, k0a, alpha, noise, n, npad, r, nullptr);
+        matvec_tri_kernel<<<mv_grid, 256, 0, stream>>>(Linv, r, 0, z, 0, npad, 0, 0, nullptr);
+        vecmat_lower_kernel<<<(n + 127) / 128, 128, 0, stream>>>(Linv, z, n, npad, 1.0, nullptr, 1, alpha);
+    }
+    return check_launch("factor_append alpha");
+}
+
 }  // namespace bobe

@@ -71,4 +71,10 @@ int32_t launch_solve_vectors(cudaStream_t stream, const FactorBuffers& fb, const
                              int64_t n, int npad, int batch, double* z_ws, double* alpha, double* logdet,
                              double* quad, int32_t* info);
 
+// rank-b append to padded (npad(n_old + b)) factors L / Linv, alpha re-solved for all n_old + b targets (factor.cu)
+int64_t append_ws_doubles(int64_t npad);
+int32_t factor_append(cudaStream_t stream, int kind, const double* X, const double* y, int64_t n_old, int64_t b, int64_t d,
+                      const double* ls, double kv, double noise, double* L, double* Linv, double* alpha, int32_t* info,
+                      double* ws);
+
 }  // namespace bobe

@@ -522,7 +522,33 @@ class GP:
                 log.warning("Training targets have zero variance. Setting std to 1.0 to avoid division by zero.")
                 self.y_std = 1.0
             self.train_y = (train_y_original - self.y_mean) / self.y_std
-            self.recompute_cholesky()
+            n_old = self.train_x.shape[0] - new_pts_to_add.shape[0]
+            if not (self.incremental_update and self._append_factor(n_old)):
+                self.recompute_cholesky()
+
+    incremental_update = True  # GP.update extends the factor in O(b n^2) instead of re-factorising
+
+    def _append_factor(self, n_old) -> bool:
+        """Rank-b extension of the device factor after ``update`` appended rows to ``train_x`` (hyper-parameters are
+        unchanged there, BOBE/gp.py:541).  Returns False (caller re-factorises) when there is no valid factor to
+        extend or an appended pivot is not positive."""
+        if not (self._factor_ok and n_old > 0 and torch.cuda.is_available()):
+            return False
+        if int(self._info_dev.reshape(-1)[0].item()) != 0:
+            return False
+        dev = self.device
+        X = _to_dev(self.train_x, dev)
+        y = _to_dev(self.train_y.reshape(-1), dev)
+        L, Linv, alpha, info = ops.factor_append(self.kernel_name, X, y, n_old, self._ls_dev,
+                                                 float(self.kernel_variance), float(self.noise), self._L_dev,
+                                                 self._Linv_dev)
+        if int(info.item()) != 0:
+            return False
+        self._X_dev, self._y_dev = X, y
+        self._L_dev, self._Linv_dev, self._alpha_dev, self._info_dev = L, Linv, alpha, info
+        self._LinvT_dev = None
+        self._cholesky_np = self._alphas_np = None
+        return True
 
     # ---- fantasy variance ------------------------------------------------------------------------------
     def fantasy_var(self, new_x, mc_points, k_train_mc=None):

@@ -85,6 +85,37 @@ def factorize(kind: str, X, y, ls, kv, noise: float, want_L: bool = True):
     return L, Linv, alpha, logdet, quad, info
 
 
+def factor_append(kind: str, X, y, n_old: int, ls, kv: float, noise: float, L, Linv):
+    """Extend the padded factors of the first ``n_old`` rows of X by the remaining rows, in O(b n^2), and re-solve
+    alpha for all targets ``y`` -- GP.update (BOBE/gp.py:495-541) without the full re-factorisation.
+
+    ``L`` / ``Linv`` are the padded (npad(n_old), npad(n_old)) factors; returns ``(L, Linv, alpha, info)`` padded to
+    npad(n) -- the same buffers, extended in place, when the padded size does not change."""
+    X, y, ls, L, Linv = _chk(X, "X"), _chk(y, "y").reshape(-1), _chk(ls, "ls"), _chk(L, "L"), _chk(Linv, "Linv")
+    n, d = X.shape
+    b = n - n_old
+    if b <= 0:
+        raise ValueError("factor_append: nothing to append")
+    p_new, p_old = npad(n), L.shape[0]
+    dev = X.device
+    if p_new != p_old:  # grow: identity-padded copies (O(n^2) traffic, still no O(n^3) work)
+        def grow(A):
+            out = torch.zeros((p_new, p_new), dtype=torch.float64, device=dev)
+            out[:p_old, :p_old] = A
+            idx = torch.arange(p_old, p_new, device=dev)
+            out[idx, idx] = 1.0
+            return out
+        L, Linv = grow(L), grow(Linv)
+    alpha = torch.empty(p_new, dtype=torch.float64, device=dev)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.bobe_factor_append_workspace_bytes(n, d), dev)
+        check(lib.bobe_factor_append(_stream(), KIND[kind], X.data_ptr(), y.data_ptr(), n_old, b, d, ls.data_ptr(),
+                                     float(kv), float(noise), L.data_ptr(), Linv.data_ptr(), alpha.data_ptr(),
+                                     info.data_ptr(), ws.data_ptr(), ws.numel()), "bobe_factor_append")
+    return L, Linv, alpha, info
+
+
 def mll_grad_batched(kind: str, X, y, log_params, has_kv: bool, fixed_kv: float, noise: float,
                      max_batch: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """log p(y | theta_r) and d/d theta for R restarts -- BOBE/gp.py:385-398 via BOBE/optim.py:309."""

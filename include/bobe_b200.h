@@ -70,6 +70,16 @@ int32_t bobe_factorize(void* stream, int32_t kind, const double* X, const double
                        const double* ls, const double* kv, double noise, int64_t batch, double* L, double* Linv,
                        double* alpha, double* logdet, double* quad, int32_t* info, void* ws, int64_t ws_bytes);
 
+/* Rank-b append: the factorisation of the first n_old points, held in buffers already sized for the padded
+ * npad(n_old + b) (identity beyond n_old), is extended IN PLACE by the points n_old .. n_old+b-1 of X, and alpha is
+ * re-solved for the targets y of all n_old + b points -- GP.update, BOBE/gp.py:495-541, whose hyper-parameters are
+ * unchanged and whose O(n^3) re-factorisation (:541) this replaces by O(b n^2) work; also the kriging-believer
+ * updates of BOBE/acquisition.py:182-194.  info (device int32): 1 if an appended pivot is not positive. */
+int64_t bobe_factor_append_workspace_bytes(int64_t n_new, int64_t d);
+int32_t bobe_factor_append(void* stream, int32_t kind, const double* X, const double* y, int64_t n_old, int64_t b,
+                           int64_t d, const double* ls, double kv, double noise, double* L, double* Linv, double* alpha,
+                           int32_t* info, void* ws, int64_t ws_bytes);
+
 /* log marginal likelihood and its gradient w.r.t. the log-parameters, for R restarts at once
  * -- value_and_grad of the data term of GP.neg_mll, BOBE/gp.py:385-398 + gp_mll :170-178, as called at
  * BOBE/optim.py:118,211,309.  log_params is (R, P) device, layout [log l_1..log l_d, log kv?, log tausq?]

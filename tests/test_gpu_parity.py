@@ -366,3 +366,41 @@ def test_acquisition_analytic_gradient(cls_name):
             # sigma ~ 1e-4 near 300 points in 3-D: |d log EI| ~ 1e5 .. 1e6 with curvature to match, so for LogEI the
             # difference quotient is the noisy side of the comparison
             assert np.max(np.abs(grad[:, k] - fd) / scale) < (2e-5 if cls_name == "EI" else 3e-4)
+
+
+@pytest.mark.parametrize("kernel,n0,b", [("rbf", 120, 1), ("matern", 126, 5), ("matern", 300, 8), ("rbf", 63, 3)])
+def test_incremental_update_matches_full_refactorisation(kernel, n0, b):
+    """GP.update extends the factor by rank-b appends (O(b n^2)); factor, alpha and predictions
+    must match a GP rebuilt from scratch on the same points (the reference's behaviour, BOBE/gp.py:541) -- including
+    updates that cross a 64-padding boundary and the re-standardisation of all targets."""
+    from bobe_b200 import GP
+    rng = np.random.default_rng(n0 + b)
+    d = 3
+    X = rng.uniform(0, 1, (n0 + b, d))
+    y = np.sin(3 * X.sum(1, keepdims=True)) + 0.5 * X[:, :1] ** 2
+    ls = np.array([0.5, 0.8, 0.65])
+    gp = GP(X[:n0], y[:n0], kernel=kernel, noise=1e-6, lengthscales=ls, kernel_variance=1.4)
+    _ = gp.cholesky  # factor exists before the update
+    gp.update(X[n0:], y[n0:])
+    full = GP(X, y, kernel=kernel, noise=1e-6, lengthscales=ls, kernel_variance=1.4)
+    full.incremental_update = False
+    ref = O.OracleGP(X, y, kernel=kernel, noise=1e-6, lengthscales=ls, kernel_variance=1.4)
+    # update() reconstitutes the raw targets from the standardised ones (BOBE/gp.py:530-539): equal up to rounding
+    assert gp.train_x.shape == (n0 + b, d) and abs(gp.y_mean - ref.y_mean) < 1e-14 and abs(gp.y_std - ref.y_std) < 1e-14
+    scale = float(np.abs(ref.cholesky).max())
+    assert mixed_err(gp.cholesky, ref.cholesky, scale) < 1e-9 and np.allclose(np.triu(gp.cholesky, 1), 0)
+    assert mixed_err(gp.cholesky, full.cholesky, scale) < 1e-10
+    assert mixed_err(gp.alphas, ref.alphas, float(np.abs(ref.alphas).max())) < 1e-8
+    Xq = rng.uniform(0, 1, (500, d))
+    m1, v1 = gp.predict_mean_var_batched(Xq)
+    assert mixed_err(m1, ref.predict_mean_batched(Xq), ref.y_std) < TOL_MEAN
+    assert mixed_err(v1, ref.predict_var_batched(Xq), ref.y_std ** 2) < TOL_VAR
+    # a second update on top of the first, then a duplicate (dropped, BOBE/gp.py:517)
+    x2 = rng.uniform(0, 1, (2, d))
+    y2 = np.sin(3 * x2.sum(1, keepdims=True))
+    gp.update(np.vstack([x2, X[:1]]), np.vstack([y2, y[:1]]))
+    ref.update(np.vstack([x2, X[:1]]), np.vstack([y2, y[:1]]))
+    assert gp.train_x.shape[0] == n0 + b + 2
+    m2, v2 = gp.predict_mean_var_batched(Xq)
+    assert mixed_err(m2, ref.predict_mean_batched(Xq), ref.y_std) < TOL_MEAN
+    assert mixed_err(v2, ref.predict_var_batched(Xq), ref.y_std ** 2) < TOL_VAR
