@@ -10,5 +10,6 @@ from .acquisition import (AcquisitionFunction, EI, LogEI, WIPV, WIPStd, get_mc_s
                           ACQUISITIONS)
 from .optim import optimize_scipy, optimize_optax, optimize_optax_vmap  # noqa: F401
 from .batching import SurrogatePool, lax_map  # noqa: F401
+from .clf_gp import GPwithClassifier  # noqa: F401
 
 __version__ = "0.1.0"

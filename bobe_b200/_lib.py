@@ -43,6 +43,8 @@ SIGNATURES = {
                                 _vp, _vp, _i64]),
     "bobe_chol_append": (_i32, [_vp, _vp, _i64, _i64, _vp, _f64, _vp, _i64]),
     "bobe_acq_ei": (_i32, [_vp, _i32, _vp, _vp, _i64, _f64, _f64, _vp]),
+    "bobe_svm_mask_workspace_bytes": (_i64, [_i64, _i64]),
+    "bobe_svm_mask": (_i32, [_vp, _vp, _i64, _i64, _vp, _f64, _f64, _vp, _i64, _f64, _f64, _vp, _vp, _vp, _vp, _i64]),
     "bobe_bench_trmm_sumsq": (_i32, [_vp, _vp, _i64, _vp, _i64, _f64, _vp]),
 }
 

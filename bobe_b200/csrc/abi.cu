@@ -505,6 +505,61 @@ extern "C" int32_t bobe_acq_ei(void* stream, int32_t which, const double* mean, 
     return check_launch("acq_ei_kernel");
 }
 
+// ---- SVM feasibility mask (GPwithClassifier) ------------------------------------------------------------------
+namespace {
+__global__ void fill_kernel(double* p, int64_t n, double v) {
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+// jnp.where(clf_probs >= threshold, value, fill) with clf_probs = (decision >= 0), BOBE/clf_gp.py:173-205
+__global__ void svm_mask_kernel(const double* __restrict__ dec, int64_t M, double minus_inf, double var_fill,
+                                double* __restrict__ mean, double* __restrict__ var) {
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= M) return;
+    const bool feasible = dec[i] >= 0.0;
+    if (mean && !feasible) mean[i] = minus_inf;
+    if (var && !feasible) var[i] = var_fill;
+}
+}  // namespace
+
+extern "C" int64_t bobe_svm_mask_workspace_bytes(int64_t d, int64_t M) {
+    if (d <= 0 || M <= 0) return 256;
+    return (round_up(d, 32) + round_up(M, 32)) * 8 + 256;
+}
+
+extern "C" int32_t bobe_svm_mask(void* stream_, const double* sv, int64_t n_sv, int64_t d, const double* dual_coef,
+                                 double intercept, double gamma, const double* Xq, int64_t M, double minus_inf,
+                                 double var_fill, double* mean_inout, double* var_inout, double* decision_out, void* ws,
+                                 int64_t ws_bytes) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!sv || !dual_coef || !Xq || !ws || n_sv <= 0 || d <= 0 || d > BOBE_MAX_DIM || M < 0 || !(gamma > 0.0)) {
+        set_error("svm_mask: bad arguments");
+        return BOBE_E_ARG;
+    }
+    if (M == 0) return BOBE_OK;
+    if (ws_bytes < bobe_svm_mask_workspace_bytes(d, M)) {
+        set_error("svm_mask: workspace too small");
+        return BOBE_E_WORKSPACE;
+    }
+    double* ls = align256(ws);
+    double* dec = decision_out ? decision_out : ls + round_up(d, 32);
+    // exp(-gamma |x - s|^2) = exp(-1/2 |x - s|^2 / l^2) with l = 1 / sqrt(2 gamma): the SVM decision function
+    // (BOBE/clf.py:188-209) is an isotropic RBF kernel-row product, i.e. the fused mean pass of the kernel-matrix kernel
+    fill_kernel<<<(unsigned)((d + 255) / 256), 256, 0, stream>>>(ls, d, 1.0 / sqrt(2.0 * gamma));
+    if (int32_t rc = check_launch("fill_kernel")) return rc;
+    const int64_t RCH = 64 * 32768;
+    for (int64_t r0 = 0; r0 < M; r0 += RCH) {
+        const int64_t rows = (M - r0 < RCH) ? M - r0 : RCH;
+        KmatArgs a{};
+        a.xa = Xq + r0 * d; a.xb = sv; a.ls = ls; a.kv = 1.0; a.alpha = dual_coef; a.mean_out = dec + r0;
+        a.n1 = rows; a.n2 = n_sv; a.d = d; a.rows_pad = round_up(rows, 64); a.cols_pad = round_up(n_sv, 64);
+        a.y_mean = intercept; a.y_std = 1.0; a.mean_standardised = 0;
+        if (int32_t rc = launch_kmat(stream, BOBE_KERNEL_RBF, a, 1)) return rc;
+    }
+    svm_mask_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(dec, M, minus_inf, var_fill, mean_inout, var_inout);
+    return check_launch("svm_mask_kernel");
+}
+
 extern "C" int32_t bobe_bench_trmm_sumsq(void* stream, const double* Linv, int64_t n, const double* kstar,
                                          int64_t rows_pad, double kk, double* var_out) {
     if (!Linv || !kstar || !var_out || n <= 0 || rows_pad <= 0) {

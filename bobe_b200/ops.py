@@ -242,3 +242,21 @@ def acq_ei(which: str, mean, var, best_y: float, zeta: float) -> torch.Tensor:
         check(lib.bobe_acq_ei(_stream(), _lib.ACQ_EI if which == "ei" else _lib.ACQ_LOGEI, mean.data_ptr(),
                               var.data_ptr(), mean.numel(), float(best_y), float(zeta), out.data_ptr()), "bobe_acq_ei")
     return out
+
+
+def svm_mask(sv, dual_coef, intercept: float, gamma: float, Xq, mean=None, var=None, minus_inf: float = -1e5,
+             var_fill: float = 1e-12, want_decision: bool = False):
+    """RBF-SVM decision function at Xq and the ``jnp.where`` mask of BOBE/clf_gp.py:173-205 applied IN PLACE to
+    ``mean`` / ``var`` (either may be None).  Returns the decision values if asked for."""
+    sv, dual_coef, Xq = _chk(sv, "sv"), _chk(dual_coef, "dual_coef").reshape(-1), _chk(Xq, "Xq")
+    n_sv, d = sv.shape
+    M = Xq.shape[0]
+    dev = Xq.device
+    dec = torch.empty(M, dtype=torch.float64, device=dev) if want_decision else None
+    ptr = lambda t: _chk(t, "mean/var").data_ptr() if t is not None else None
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.bobe_svm_mask_workspace_bytes(d, M), dev)
+        check(lib.bobe_svm_mask(_stream(), sv.data_ptr(), n_sv, d, dual_coef.data_ptr(), float(intercept), float(gamma),
+                                Xq.data_ptr(), M, float(minus_inf), float(var_fill), ptr(mean), ptr(var),
+                                dec.data_ptr() if dec is not None else None, ws.data_ptr(), ws.numel()), "bobe_svm_mask")
+    return dec

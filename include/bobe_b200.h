@@ -136,6 +136,15 @@ int32_t bobe_chol_append(void* stream, const double* L, int64_t n, int64_t ldl, 
 int32_t bobe_acq_ei(void* stream, int32_t which, const double* mean, const double* var, int64_t M, double best_y,
                     double zeta, double* out);
 
+/* SVM feasibility mask of GPwithClassifier -- BOBE/clf_gp.py:173-205 (predict_*_single: jnp.where(clf_probs >=
+ * threshold, value, fill)) with the RBF-SVM decision function of BOBE/clf.py:188-214:
+ *   decision_q = sum_j dual_coef_j exp(-gamma |sv_j - x_q|^2) + intercept;   infeasible (decision < 0):
+ *   mean_inout[q] = minus_inf, var_inout[q] = var_fill.   Any of mean_inout / var_inout / decision_out may be NULL. */
+int64_t bobe_svm_mask_workspace_bytes(int64_t d, int64_t M);
+int32_t bobe_svm_mask(void* stream, const double* sv, int64_t n_sv, int64_t d, const double* dual_coef, double intercept,
+                      double gamma, const double* Xq, int64_t M, double minus_inf, double var_fill, double* mean_inout,
+                      double* var_inout, double* decision_out, void* ws, int64_t ws_bytes);
+
 /* ---- measurement hook (bench.py only; not part of the drop-in surface) -------------------------------------
  * Launches exactly the dominant kernel of bobe_predict (the fused triangular multiply + column sum of squares)
  * once over `rows_pad` queries whose K* panel (rows_pad, npad) is already in `kstar`, so that bench.py can time

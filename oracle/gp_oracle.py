@@ -544,6 +544,25 @@ def logei_values(mu, var, best_y, zeta):
     return -(log_ei_helper(u) + np.log(sigma))
 
 
+def svm_decision(x, support_vectors, dual_coef, intercept, gamma):
+    """BOBE/clf.py:188-209 -- RBF-SVM decision function sum_j dual_j exp(-gamma |sv_j - x|^2) + intercept, (M,)."""
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    return np.exp(-gamma * dist_sq(x, np.asarray(support_vectors))) @ np.asarray(dual_coef).ravel() + intercept
+
+
+def clf_masked_predict(gp: "OracleGP", x, clf_params, minus_inf=-1e5, standardised=False):
+    """BOBE/clf_gp.py:173-205 -- where(clf_probs >= threshold, value, fill) with probs = (decision >= 0)."""
+    dec = svm_decision(x, clf_params['support_vectors'], clf_params['dual_coef'], clf_params['intercept'],
+                       clf_params['gamma_eff'])
+    ok = dec >= 0
+    if standardised:
+        m, v = gp.predict_batched(x)
+        v = v.ravel()
+    else:
+        m, v = gp.predict_mean_batched(x), gp.predict_var_batched(x)
+    return np.where(ok, m, minus_inf), np.where(ok, v, SAFE_NOISE_FLOOR), dec
+
+
 def wipv_values(gp: OracleGP, cand_x, mc_points, std=False):
     """BOBE/acquisition.py:438-440,463-465 for a set of candidates: mean_j fantasy_var (or of its sqrt)."""
     var = gp.fantasy_var_shared(cand_x, mc_points)

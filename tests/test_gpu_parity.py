@@ -404,3 +404,45 @@ def test_incremental_update_matches_full_refactorisation(kernel, n0, b):
     m2, v2 = gp.predict_mean_var_batched(Xq)
     assert mixed_err(m2, ref.predict_mean_batched(Xq), ref.y_std) < TOL_MEAN
     assert mixed_err(v2, ref.predict_var_batched(Xq), ref.y_std ** 2) < TOL_VAR
+
+
+def test_gp_with_svm_classifier_mask_and_state(tmp_path):
+    """SURVEY.md 8f row 4: GPwithClassifier (SVM) -- the mask is applied on the device as an epilogue of bobe_predict;
+    decision values, masked predictions and the state round trip against the oracle restatement."""
+    from bobe_b200 import GPwithClassifier
+    rng = np.random.default_rng(2)
+    n, d = 400, 3
+    X = rng.uniform(0, 1, (n, d))
+    y = -0.5 * np.sum(((X - 0.5) / 0.05) ** 2, axis=1, keepdims=True)  # steep: many points far below the best value
+    gp = GPwithClassifier(X, y, clf_type="svm", clf_use_size=10, clf_threshold=20.0, gp_threshold=60.0, kernel="rbf",
+                          lengthscales=np.full(d, 0.3), kernel_variance=1.0, lengthscale_prior=None)
+    assert gp.use_clf and gp.clf_params is not None and gp.npoints < n  # GP trained on the subset only
+    keep = y.ravel() > y.max() - 60.0
+    ref = O.OracleGP(X[keep], y[keep], kernel="rbf", lengthscales=np.full(d, 0.3), kernel_variance=1.0)
+    xq = rng.uniform(0.2, 0.8, (2000, d))
+    dec = gp.clf_decision(xq)
+    rdec = O.svm_decision(xq, gp.clf_params['support_vectors'], gp.clf_params['dual_coef'], gp.clf_params['intercept'],
+                          gp.clf_params['gamma_eff'])
+    assert np.allclose(dec, rdec, rtol=1e-10, atol=1e-9 * np.abs(rdec).max())
+    sel = np.abs(rdec) > 1e-6 * np.abs(rdec).max()  # away from the boundary the mask must agree exactly
+    for std in (False, True):
+        rm, rv, _ = O.clf_masked_predict(ref, xq, gp.clf_params, standardised=std)
+        if std:
+            m, v = gp.predict_batched(xq)
+            v = v.ravel()
+        else:
+            m, v = gp.predict_mean_batched(xq), gp.predict_var_batched(xq)
+        assert 0 < np.sum(rm[sel] == -1e5) < sel.sum()  # both classes present
+        assert np.array_equal(m[sel] == -1e5, rm[sel] == -1e5)
+        ok = sel & (rm != -1e5)
+        assert mixed_err(m[ok], rm[ok], 1.0 if std else ref.y_std) < TOL_MEAN
+        assert mixed_err(v[ok], rv[ok], 1.0 if std else ref.y_std ** 2) < TOL_VAR
+        assert np.all(v[sel & (rm == -1e5)] == 1e-12)
+    assert gp.predict_mean_single(np.full(d, 0.01)) == -1e5  # far corner: infeasible
+    gp.save(str(tmp_path / "clfgp"))
+    gp2 = GPwithClassifier.load(str(tmp_path / "clfgp.npz"))
+    assert gp2.use_clf and np.array_equal(gp2.predict_mean_batched(xq[:100]), gp.predict_mean_batched(xq[:100]))
+    gp.update(np.full((1, d), 0.5), np.array([[0.0]]))  # new best point: both sets re-selected
+    assert gp.clf_data_size == n + 1 and gp.train_x.shape[0] == np.sum(np.append(y.ravel(), 0.0) > -60.0)
+    with pytest.raises(NotImplementedError):
+        GPwithClassifier(X, y, clf_type="nn")

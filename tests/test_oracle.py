@@ -275,3 +275,18 @@ def test_oracle_input_gradients_match_central_differences(kernel):
     gp0 = O.OracleGP(X, y, kernel=kernel, noise=1e-14, lengthscales=np.array([0.4, 0.7, 0.55]), kernel_variance=1.3)
     _, v, _, dv = gp0.predict_grad_batched(X[:2], standardised=True)
     assert np.all(dv[v <= 1e-12] == 0.0)
+
+
+def test_oracle_svm_decision_matches_sklearn():
+    """Pins the restated SVM decision function (BOBE/clf.py:188-209) against scikit-learn's own decision_function --
+    the third-party routine the reference extracts its parameters from (clf.py:42-47)."""
+    from sklearn.svm import SVC
+    rng = np.random.default_rng(0)
+    X = rng.uniform(0, 1, (200, 4))
+    labels = (np.sum((X - 0.5) ** 2, axis=1) < 0.2).astype(int)
+    clf = SVC(kernel="rbf", gamma="scale", C=1e7).fit(X, labels)
+    xq = rng.uniform(0, 1, (300, 4))
+    dec = O.svm_decision(xq, clf.support_vectors_, clf.dual_coef_[0], float(clf.intercept_[0]), float(clf._gamma))
+    ref = clf.decision_function(xq)
+    assert np.allclose(dec, ref, rtol=1e-9, atol=1e-6 * np.abs(ref).max())
+    assert np.array_equal(dec >= 0, clf.predict(xq) == 1)
