@@ -35,8 +35,8 @@ int64_t env_int(const char* name, int64_t dflt) {
 
 int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& a, int batch) {
     if (a.M <= 0 || a.N <= 0 || batch <= 0) return BOBE_OK;
-    if ((a.K % 16) || (a.N % 2) || (a.lda % 2) || (a.ldb % 2) || (a.ldc % 2)) {
-        set_error("gemm_nt: K must be a multiple of 16 and N/ld even (M=%d N=%d K=%d)", a.M, a.N, a.K);
+    if ((a.K % 32) || (a.N % 2) || (a.lda % 2) || (a.ldb % 2) || (a.ldc % 2)) {
+        set_error("gemm_nt: K must be a multiple of 32 and N/ld even (M=%d N=%d K=%d)", a.M, a.N, a.K);
         return BOBE_E_ARG;
     }
     // 128x128 tiles are the efficient ones, but the lower levels of the recursion are latency-bound chains of small

@@ -464,7 +464,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
 }
 
 // rows are interleaved between the two warp rows in every configuration (harmless for unstructured products)
-using CfgBig = TileCfg<128, 128, 2, 4, 4, 16, true>;   // 256 threads, warp tile 64x32, 128 KB smem
+// tools/gemm_tune.cu sweep (profiles/r01/gemm_tune.txt): 16 warps (4 per scheduler) with 32-wide k-tiles beat the
+// 8-warp / 16-wide configuration by 5 % (2.40 -> 2.28 ms per 18,944-query chunk): twice the warps to cover the
+// MMA and LDS latencies, half the barriers per flop.
+using CfgBig = TileCfg<128, 128, 4, 4, 3, 32, true>;   // 512 threads, warp tile 32x32, 3 stages x 64 KB = 192 KB smem
 using CfgTrmm = CfgBig;
 using CfgSmall = TileCfg<64, 64, 2, 2, 4, 16, true>;   // 128 threads, warp tile 32x32, 64 KB smem
 

@@ -13,7 +13,7 @@ void run(const char* name, const double* Linv, int npad, const double* K, double
     float best = 1e30f;
     for (int it = 0; it < 6; ++it) {
         cudaEventRecord(e0);
-        trmm_sumsq_kernel<Cfg><<<rows / Cfg::BN, Cfg::THREADS, Cfg::SMEM_BYTES>>>(Linv, npad, K, npad, 0, rows, 1.0, 1.0, 0, out);
+        trmm_sumsq_kernel<Cfg><<<rows / Cfg::BN, Cfg::THREADS, Cfg::SMEM_BYTES>>>(Linv, n, npad, K, npad, 0, rows, 1.0, 1.0, 0, out);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (it && ms < best) best = ms;
     }
@@ -34,15 +34,16 @@ int main() {
     std::vector<double> hk((size_t)maxrows * npad);
     for (size_t i = 0; i < hk.size(); ++i) hk[i] = ((i * 2654435761u) % 1000) * 1e-3;
     cudaMemcpy(K, hk.data(), sizeof(double) * hk.size(), cudaMemcpyHostToDevice);
-    run<TileCfg<128, 128, 2, 4, 4, 16>>("128x128 w2x4 s4 bk16", Linv, npad, K, out, n);
-    run<TileCfg<128, 128, 2, 4, 3, 32>>("128x128 w2x4 s3 bk32", Linv, npad, K, out, n);
-    run<TileCfg<128, 128, 4, 4, 4, 16>>("128x128 w4x4 s4 bk16", Linv, npad, K, out, n);
-    run<TileCfg<128, 128, 4, 4, 3, 32>>("128x128 w4x4 s3 bk32", Linv, npad, K, out, n);
-    run<TileCfg<128, 128, 4, 2, 4, 16>>("128x128 w4x2 s4 bk16", Linv, npad, K, out, n);
-    run<TileCfg<128, 256, 4, 4, 4, 16>>("128x256 w4x4 s4 bk16", Linv, npad, K, out, n);
-    run<TileCfg<256, 128, 4, 4, 4, 16>>("256x128 w4x4 s4 bk16", Linv, npad, K, out, n);
-    run<TileCfg<128, 256, 4, 4, 2, 32>>("128x256 w4x4 s2 bk32", Linv, npad, K, out, n);
-    run<TileCfg<128, 64, 2, 2, 4, 16>>("128x64 w2x2 s4 bk16", Linv, npad, K, out, n);
-    run<TileCfg<128, 64, 4, 2, 4, 32>>("128x64 w4x2 s4 bk32", Linv, npad, K, out, n);
+    run<TileCfg<128, 128, 2, 4, 4, 16, true>>("128x128 w2x4 s4 bk16 ilv", Linv, npad, K, out, n);
+    run<TileCfg<128, 128, 2, 4, 4, 16, false>>("128x128 w2x4 s4 bk16", Linv, npad, K, out, n);
+    run<TileCfg<128, 128, 2, 4, 3, 32, true>>("128x128 w2x4 s3 bk32 ilv", Linv, npad, K, out, n);
+    run<TileCfg<128, 128, 4, 4, 4, 16, true>>("128x128 w4x4 s4 bk16 ilv", Linv, npad, K, out, n);
+    run<TileCfg<128, 128, 4, 4, 3, 32, true>>("128x128 w4x4 s3 bk32 ilv", Linv, npad, K, out, n);
+    run<TileCfg<128, 128, 4, 2, 4, 16, true>>("128x128 w4x2 s4 bk16 ilv", Linv, npad, K, out, n);
+    run<TileCfg<128, 128, 8, 2, 3, 32, true>>("128x128 w8x2 s3 bk32 ilv", Linv, npad, K, out, n);
+    run<TileCfg<128, 128, 2, 8, 3, 32, true>>("128x128 w2x8 s3 bk32 ilv", Linv, npad, K, out, n);
+    run<TileCfg<128, 128, 4, 4, 3, 32, false>>("128x128 w4x4 s3 bk32", Linv, npad, K, out, n);
+    run<TileCfg<128, 128, 4, 4, 2, 32, true>>("128x128 w4x4 s2 bk32 ilv", Linv, npad, K, out, n);
+    run<TileCfg<128, 128, 4, 4, 6, 16, true>>("128x128 w4x4 s6 bk16 ilv", Linv, npad, K, out, n);
     return 0;
 }
