@@ -332,8 +332,11 @@ extern "C" int32_t bobe_predict(void* stream_, int32_t kind, const double* X, in
     double* xs = align256(ws);  // (d, npad) = X^T / l, built once per call
     double* kstar = want_var ? xs + round_up(d * npad, 32) : nullptr;
     if (int32_t rc = launch_prescale(stream, X, n, d, ls, 0, xs, npad, 0, 1)) return rc;
-    for (int64_t q0 = 0; q0 < M; q0 += QCHUNK) {
-        int64_t rows = (M - q0 < QCHUNK) ? M - q0 : QCHUNK;
+    // mean only: no K* panel to bound, so the rows go out in launches as large as the grid allows (more CTAs per SM
+    // for the kernel-matrix kernel); with the variance, one 148 x 128-query chunk per trmm_sumsq launch
+    const int64_t step = want_var ? QCHUNK : (int64_t)64 * 32768;
+    for (int64_t q0 = 0; q0 < M; q0 += step) {
+        int64_t rows = (M - q0 < step) ? M - q0 : step;
         int64_t rows_pad = round_up(rows, 128);
         KmatArgs a{};
         a.xa = Xq + q0 * d; a.xb = X; a.ls = ls; a.kv = kv; a.noise = noise;

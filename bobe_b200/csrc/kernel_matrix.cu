@@ -1,6 +1,8 @@
 // Fused kernel-matrix builds: K(X,X)+noise*I for the factorisation (batched over hyper-parameter sets) and
 // K(X*,X) panels for prediction, with the predictive mean (alpha-dot) folded into the same pass.
 // Restates BOBE/gp.py:80-96 (dist_sq by direct differences), :124-154 (RBF), :156-168 (Matern-5/2).
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace bobe {
@@ -8,7 +10,6 @@ namespace bobe {
 constexpr int KT = 64;    // tile edge (rows and columns)
 constexpr int KLD = 66;   // smem row stride (doubles): even, so 16-byte vector reads stay aligned
 constexpr int KTHREADS = 128;
-constexpr int KROWS = 4;  // rows of a thread's 8 x 4 tile whose kernel values are evaluated together
 
 // One CTA (128 threads as 8 x 16) computes 64 x 64 tiles of K: thread (ty, tx) owns rows 8 ty .. 8 ty + 7 and the
 // columns {2 tx, 2 tx + 1, 32 + 2 tx, 33 + 2 tx} -- 32 independent distance accumulators per thread, fed per
@@ -23,8 +24,12 @@ constexpr int KROWS = 4;  // rows of a thread's 8 x 4 tile whose kernel values a
 //     so a column tile is d rows of 512 contiguous bytes that cp.async drops straight into the (double-buffered)
 //     compute layout: no per-tile divisions, one __syncthreads per tile.  Without PRE (the generic entry point,
 //     which has no workspace) the raw rows are staged and divided in the kernel.
-template <int KIND, bool PRE>
-__global__ void __launch_bounds__(KTHREADS, 2) kmat_kernel(KmatArgs p) {
+//   * KROWS = rows of a thread's 8 x 4 tile whose kernel values are evaluated together.  KROWS = 4 (16 values in lock
+//     step, ~240 registers, 2 CTAs/SM) is the faster one when the grid cannot put more than two CTAs on an SM anyway
+//     (a predict chunk is exactly 296 row tiles); KROWS = 2 fits 168 registers = 3 CTAs/SM and wins on large grids
+//     (mean-only sweeps, the batched K(X,X) builds).
+template <int KIND, bool PRE, int KROWS>
+__global__ void __launch_bounds__(KTHREADS, KROWS == 4 ? 2 : 3) kmat_kernel(KmatArgs p) {
     extern __shared__ __align__(16) double sm[];
     const int d = (int)p.d;
     double* sa = sm;                 // [d][KLD] scaled rows of xa
@@ -248,24 +253,26 @@ int32_t launch_kmat(cudaStream_t stream, int kind, const KmatArgs& a, int batch)
         return BOBE_E_ARG;
     }
     dim3 grid((unsigned)splits, (unsigned)row_tiles, (unsigned)batch);
-    int32_t rc;
-    if (kind == BOBE_KERNEL_RBF) {
-        if (pre) {
-            if ((rc = ensure_smem<kmat_kernel<BOBE_KERNEL_RBF, true>>(smem))) return rc;
-            kmat_kernel<BOBE_KERNEL_RBF, true><<<grid, KTHREADS, smem, stream>>>(a);
-        } else {
-            if ((rc = ensure_smem<kmat_kernel<BOBE_KERNEL_RBF, false>>(smem))) return rc;
-            kmat_kernel<BOBE_KERNEL_RBF, false><<<grid, KTHREADS, smem, stream>>>(a);
-        }
-    } else {
-        if (pre) {
-            if ((rc = ensure_smem<kmat_kernel<BOBE_KERNEL_MATERN52, true>>(smem))) return rc;
-            kmat_kernel<BOBE_KERNEL_MATERN52, true><<<grid, KTHREADS, smem, stream>>>(a);
-        } else {
-            if ((rc = ensure_smem<kmat_kernel<BOBE_KERNEL_MATERN52, false>>(smem))) return rc;
-            kmat_kernel<BOBE_KERNEL_MATERN52, false><<<grid, KTHREADS, smem, stream>>>(a);
-        }
-    }
+    // three CTAs per SM only materialise when the grid offers them
+    const bool wide = (int64_t)grid.x * grid.y * grid.z >= 3 * 148;
+    auto go = [&](auto kind_c, auto pre_c, auto kr_c) -> int32_t {
+        constexpr int K_ = decltype(kind_c)::value;
+        constexpr bool P_ = decltype(pre_c)::value;
+        constexpr int R_ = decltype(kr_c)::value;
+        if (int32_t rc = ensure_smem<kmat_kernel<K_, P_, R_>>(smem)) return rc;
+        kmat_kernel<K_, P_, R_><<<grid, KTHREADS, smem, stream>>>(a);
+        return BOBE_OK;
+    };
+    using std::integral_constant;
+    auto by_rows = [&](auto kind_c, auto pre_c) -> int32_t {
+        return wide ? go(kind_c, pre_c, integral_constant<int, 2>{}) : go(kind_c, pre_c, integral_constant<int, 4>{});
+    };
+    auto by_pre = [&](auto kind_c) -> int32_t {
+        return pre ? by_rows(kind_c, integral_constant<bool, true>{}) : by_rows(kind_c, integral_constant<bool, false>{});
+    };
+    int32_t rc = kind == BOBE_KERNEL_RBF ? by_pre(integral_constant<int, BOBE_KERNEL_RBF>{})
+                                         : by_pre(integral_constant<int, BOBE_KERNEL_MATERN52>{});
+    if (rc) return rc;
     return check_launch("kmat_kernel");
 }
 
