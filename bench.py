@@ -281,11 +281,11 @@ def main():
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "n": N_TRAIN, "d": DIM, "kernel": KERNEL, "m_per_gpu": M,
-                           "l2": "inputs larger than L2 (128 MB of queries + 310 MB K* scratch per chunk sweep)",
+                           "l2": "inputs larger than L2 (128 MB of queries + 930 MB K* scratch per 3-chunk sweep)",
                            "parallelism": f"query-sharded x{world}, replicated factor"},
                 "e2e": {"value": e2e_value, "unit": "pts/s", "h2d_bytes_per_step": M * DIM * 8,
                         "d2h_bytes_per_step": M * 16, "ms_per_step": ms_e2e},
-                "gpu_launches": args.steps * (chunks * 2 + 1),  # per step: prescale + (kmat + trmm_sumsq) per chunk
+                "gpu_launches": args.steps * (chunks + -(-chunks // 3) + 1),  # per step: prescale + trmm_sumsq per chunk + kmat per 3 chunks
                 "clocks": clocks, "roofline": roofline, "secondary": secondary}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline

@@ -8,7 +8,8 @@ using namespace bobe;
 
 namespace {
 
-constexpr int64_t QCHUNK = 148 * 128;  // queries per predict chunk: one 128-query tile per SM
+constexpr int64_t QCHUNK = 148 * 128;  // queries per trmm_sumsq launch: one 128-query tile per SM
+constexpr int64_t KCHUNKS = 3;         // chunks per kernel-matrix launch: 888 CTAs = two full waves at 3 CTAs/SM
 
 inline double* align256(void* p) { return (double*)(((uintptr_t)p + 255) & ~(uintptr_t)255); }
 inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
@@ -302,7 +303,8 @@ extern "C" int32_t bobe_factor_append(void* stream_, int32_t kind, const double*
 extern "C" int64_t bobe_predict_workspace_bytes(int64_t n, int64_t d, int64_t M, int32_t mode) {
     if (M <= 0 || n <= 0 || d <= 0) return 256;
     int64_t bytes = round_up(d * npad_of(n), 32) * 8 + 512;  // scaled, transposed training inputs
-    if (mode & BOBE_PREDICT_VAR) bytes += round_up(M < QCHUNK ? M : QCHUNK, 128) * npad_of(n) * 8;  // K* panel
+    if (mode & BOBE_PREDICT_VAR)  // K* panel of up to KCHUNKS chunks
+        bytes += round_up(M < KCHUNKS * QCHUNK ? M : KCHUNKS * QCHUNK, 128) * npad_of(n) * 8;
     return bytes;
 }
 
@@ -333,8 +335,9 @@ extern "C" int32_t bobe_predict(void* stream_, int32_t kind, const double* X, in
     double* kstar = want_var ? xs + round_up(d * npad, 32) : nullptr;
     if (int32_t rc = launch_prescale(stream, X, n, d, ls, 0, xs, npad, 0, 1)) return rc;
     // mean only: no K* panel to bound, so the rows go out in launches as large as the grid allows (more CTAs per SM
-    // for the kernel-matrix kernel); with the variance, one 148 x 128-query chunk per trmm_sumsq launch
-    const int64_t step = want_var ? QCHUNK : (int64_t)64 * 32768;
+    // for the kernel-matrix kernel); with the variance, the K* panel of KCHUNKS chunks is built by one launch and
+    // consumed by one trmm_sumsq launch per 148 x 128-query chunk
+    const int64_t step = want_var ? KCHUNKS * QCHUNK : (int64_t)64 * 32768;
     for (int64_t q0 = 0; q0 < M; q0 += step) {
         int64_t rows = (M - q0 < step) ? M - q0 : step;
         int64_t rows_pad = round_up(rows, 128);
@@ -349,9 +352,12 @@ extern "C" int32_t bobe_predict(void* stream_, int32_t kind, const double* X, in
         a.y_mean = y_mean; a.y_std = y_std; a.mean_standardised = standardised;
         if (int32_t rc = launch_kmat(stream, kind, a, 1)) return rc;
         if (want_var) {
-            if (int32_t rc = launch_trmm_sumsq(stream, Linv, (int)n, (int)npad, kstar, npad, rows_pad, q0, M, kv + noise,
-                                               y_std * y_std, standardised, var_out))
-                return rc;
+            for (int64_t c0 = 0; c0 < rows_pad; c0 += QCHUNK) {
+                const int64_t crows = (rows_pad - c0 < QCHUNK) ? rows_pad - c0 : QCHUNK;
+                if (int32_t rc = launch_trmm_sumsq(stream, Linv, (int)n, (int)npad, kstar + c0 * npad, npad, crows, q0 + c0, M,
+                                                   kv + noise, y_std * y_std, standardised, var_out))
+                    return rc;
+            }
         }
     }
     return BOBE_OK;
