@@ -84,5 +84,62 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(BobeFantasyVar, FantasyImpl,
                                   .Arg<F64>().Arg<F64>().Attr<int64_t>("kind").Attr<double>("kv").Attr<double>("noise")
                                   .Attr<double>("y_std").Attr<int64_t>("reduce").Ret<F64>()
                                   .Ret<ffi::Buffer<ffi::U8>>());
+
+// value + input gradients: the backward rule of the custom_vjp around bobe_predict (BOBE/samplers.py:268-285,
+// BOBE/optim.py:118,309 differentiate predict_*_single with respect to x)
+static ffi::Error PredictGradImpl(cudaStream_t s, F64 X, F64 ls, F64 Linv, F64 LinvT, F64 alpha, F64 Xq, int64_t kind,
+                                  double kv, double noise, double y_mean, double y_std, int64_t mode, RF64 mean, RF64 var,
+                                  RF64 dmean, RF64 dvar, RU8 ws) {
+  int64_t n = X.dimensions()[0], d = X.dimensions()[1], M = Xq.dimensions()[0];
+  return status(bobe_predict_grad(s, (int32_t)kind, X.typed_data(), n, d, ls.typed_data(), kv, noise, Linv.typed_data(),
+                                  LinvT.typed_data(), alpha.typed_data(), Xq.typed_data(), M, y_mean, y_std,
+                                  (int32_t)mode, mean->typed_data(), var->typed_data(), dmean->typed_data(),
+                                  dvar->typed_data(), ws->untyped_data(), (int64_t)ws->size_bytes()));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(BobePredictGrad, PredictGradImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<F64>().Arg<F64>().Arg<F64>()
+                                  .Arg<F64>().Arg<F64>().Arg<F64>().Attr<int64_t>("kind").Attr<double>("kv")
+                                  .Attr<double>("noise").Attr<double>("y_mean").Attr<double>("y_std")
+                                  .Attr<int64_t>("mode").Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>()
+                                  .Ret<ffi::Buffer<ffi::U8>>());
+
+static ffi::Error LinvTransposeImpl(cudaStream_t s, F64 Linv, int64_t n, RF64 LinvT) {
+  return status(bobe_linv_transpose(s, Linv.typed_data(), n, LinvT->typed_data()));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(BobeLinvTranspose, LinvTransposeImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<F64>().Attr<int64_t>("n")
+                                  .Ret<F64>());
+
+// GP.update without the rebuild: L / Linv are donated (input_output_aliases on the Python side) and extended in place
+static ffi::Error FactorAppendImpl(cudaStream_t s, F64 X, F64 y, F64 ls, F64 L_in, F64 Linv_in, int64_t kind,
+                                   int64_t n_old, double kv, double noise, RF64 L, RF64 Linv, RF64 alpha, RI32 info,
+                                   RU8 ws) {
+  int64_t n = X.dimensions()[0], d = X.dimensions()[1];
+  (void)L_in; (void)Linv_in;  // aliased to the results
+  return status(bobe_factor_append(s, (int32_t)kind, X.typed_data(), y.typed_data(), n_old, n - n_old, d,
+                                   ls.typed_data(), kv, noise, L->typed_data(), Linv->typed_data(), alpha->typed_data(),
+                                   info->typed_data(), ws->untyped_data(), (int64_t)ws->size_bytes()));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(BobeFactorAppend, FactorAppendImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<F64>().Arg<F64>().Arg<F64>()
+                                  .Arg<F64>().Arg<F64>().Attr<int64_t>("kind").Attr<int64_t>("n_old").Attr<double>("kv")
+                                  .Attr<double>("noise").Ret<F64>().Ret<F64>().Ret<F64>()
+                                  .Ret<ffi::Buffer<ffi::S32>>().Ret<ffi::Buffer<ffi::U8>>());
+
+// GPwithClassifier mask (BOBE/clf_gp.py:173-205): mean / var are donated and masked in place
+static ffi::Error SvmMaskImpl(cudaStream_t s, F64 sv, F64 dual, F64 Xq, F64 mean_in, F64 var_in, double intercept,
+                              double gamma, double minus_inf, double var_fill, RF64 mean, RF64 var, RF64 decision,
+                              RU8 ws) {
+  int64_t n_sv = sv.dimensions()[0], d = sv.dimensions()[1], M = Xq.dimensions()[0];
+  (void)mean_in; (void)var_in;
+  return status(bobe_svm_mask(s, sv.typed_data(), n_sv, d, dual.typed_data(), intercept, gamma, Xq.typed_data(), M,
+                              minus_inf, var_fill, mean->typed_data(), var->typed_data(), decision->typed_data(),
+                              ws->untyped_data(), (int64_t)ws->size_bytes()));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(BobeSvmMask, SvmMaskImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<F64>().Arg<F64>().Arg<F64>()
+                                  .Arg<F64>().Arg<F64>().Attr<double>("intercept").Attr<double>("gamma")
+                                  .Attr<double>("minus_inf").Attr<double>("var_fill").Ret<F64>().Ret<F64>().Ret<F64>()
+                                  .Ret<ffi::Buffer<ffi::U8>>());
 #endif
 #endif
