@@ -446,3 +446,31 @@ def test_gp_with_svm_classifier_mask_and_state(tmp_path):
     assert gp.clf_data_size == n + 1 and gp.train_x.shape[0] == np.sum(np.append(y.ravel(), 0.0) > -60.0)
     with pytest.raises(NotImplementedError):
         GPwithClassifier(X, y, clf_type="nn")
+
+
+@pytest.mark.parametrize("d", [33, 64, 144])
+def test_large_input_dimension(d):
+    """d up to BOBE_MAX_DIM = 144 (shared-memory staging of one 64-row tile per operand); above it a clean error."""
+    from bobe_b200 import ops
+    from bobe_b200._lib import BobeNativeError
+    rng = np.random.default_rng(d)
+    n = 150
+    X = rng.uniform(0, 1, (n, d))
+    y = np.sin(X.sum(1, keepdims=True))
+    ls = rng.uniform(1.5, 3.0, d)
+    for kernel in ("rbf", "matern"):
+        ref = O.OracleGP(X, y, kernel=kernel, noise=1e-6, lengthscales=ls)
+        gp = make_gp(ref)
+        Xq = rng.uniform(0, 1, (300, d))
+        mean, var = gp.predict_mean_var_batched(Xq)
+        assert mixed_err(mean, ref.predict_mean_batched(Xq), ref.y_std) < TOL_MEAN
+        assert mixed_err(var, ref.predict_var_batched(Xq), ref.y_std ** 2) < TOL_VAR
+        x0 = np.log(np.concatenate([ls, [1.0]]))[None, :]
+        v, g = gp.neg_mll_and_grad_batched(x0)
+        vr, gr = ref.neg_mll_and_grad(x0[0])
+        assert abs(v[0] - vr) <= TOL_MLL * max(abs(vr), n)
+        check_grad(g[0], gr)
+    if d == 144:
+        with pytest.raises(BobeNativeError):
+            ops.kernel_matrix("rbf", T(rng.uniform(0, 1, (8, 145))), T(rng.uniform(0, 1, (8, 145))), T(np.ones(145)), 1.0,
+                              0.0, False)
