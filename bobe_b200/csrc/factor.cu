@@ -159,8 +159,8 @@ int32_t factor_recursive(cudaStream_t stream, const FactorBuffers& fb, int npad,
 }
 
 int32_t launch_kinv(cudaStream_t stream, const FactorBuffers& fb, int npad, int batch) {
-    GemmArgs g{};
-    g.A = fb.U; g.Bt = fb.U; g.C = fb.KB; g.Ct = fb.KB;
+    GemmArgs g{};  // only the lower 128-tiles (diagonal tiles in full) are written: all the gradient kernel reads
+    g.A = fb.U; g.Bt = fb.U; g.C = fb.KB; g.Ct = nullptr;
     g.lda = g.ldb = g.ldc = g.ldct = npad;
     g.strideA = g.strideB = g.strideC = g.strideCt = (int64_t)npad * npad;
     g.M = g.N = g.K = npad; g.alpha = 1.0;

@@ -56,7 +56,7 @@ struct FactorBuffers {
 };
 int64_t factor_q_elems(int64_t npad);
 int32_t factor_recursive(cudaStream_t stream, const FactorBuffers& fb, int npad, int batch);
-int32_t launch_kinv(cudaStream_t stream, const FactorBuffers& fb, int npad, int batch);  // KB <- U U^T (full symmetric)
+int32_t launch_kinv(cudaStream_t stream, const FactorBuffers& fb, int npad, int batch);  // KB <- U U^T (lower 128-tiles)
 struct SolveArgs {  // what the alpha refinement needs to rebuild K alpha
     int kind;
     const double* X;
