@@ -158,20 +158,34 @@ struct LeafIO {
     int npad, o;  // o = first row/column of the block
 };
 
-// global -> smem: 64x64 block at (row r0, col c0) of KB; lower_only zeroes the strict upper part
-__device__ __forceinline__ void leaf_load(double* S, const double* Kz, int npad, int r0, int c0, bool lower_only) {
-    for (int idx = threadIdx.x; idx < 64 * 64; idx += LEAF_THREADS) {
-        int r = idx >> 6, c = idx & 63;
-        S[r * SLD + c] = (!lower_only || c <= r) ? Kz[(int64_t)(r0 + r) * npad + c0 + c] : 0.0;
+// global -> smem: 64x64 block at (row r0, col c0) of KB, as 16-byte cp.async copies (all blocks of a leaf are issued
+// back to back and waited for once, so the leaf pays ONE global-load latency instead of one per element batch).
+// The strict upper part of a diagonal block is copied as it is: chol_inv_64 never reads it.
+__device__ __forceinline__ void leaf_load_async(double* S, const double* Kz, int npad, int r0, int c0) {
+    for (int idx = threadIdx.x; idx < 64 * 32; idx += LEAF_THREADS) {
+        int r = idx >> 5, c = (idx & 31) * 2;
+        cp_async16(S + r * SLD + c, Kz + (int64_t)(r0 + r) * npad + c0 + c, true);
     }
 }
-// smem block -> global at (r0, c0), plus its transpose into Gt at (c0, r0)
-__device__ __forceinline__ void leaf_store(const double* S, double* G, double* Gt, int npad, int r0, int c0) {
+// smem block -> global at (r0, c0), plus its transpose into Gt at (c0, r0).  The transpose goes through a staging
+// buffer T with an odd row stride (65): reading S down a column directly would put all 32 lanes on two banks.
+constexpr int TLD = 65;
+__device__ __forceinline__ void leaf_store(const double* S, double* T, double* G, double* Gt, int npad, int r0, int c0) {
+    for (int idx = threadIdx.x; idx < 64 * 32; idx += LEAF_THREADS) {  // direct copy, 16 bytes per lane
+        int r = idx >> 5, c = (idx & 31) * 2;
+        double2 v = *reinterpret_cast<const double2*>(S + r * SLD + c);
+        *reinterpret_cast<double2*>(G + (int64_t)(r0 + r) * npad + c0 + c) = v;
+    }
+    for (int idx = threadIdx.x; idx < 64 * 64; idx += LEAF_THREADS) {  // T[c][r] = S[r][c], lanes along c
+        int r = idx >> 6, c = idx & 63;
+        T[c * TLD + r] = S[r * SLD + c];
+    }
+    __syncthreads();
     for (int idx = threadIdx.x; idx < 64 * 64; idx += LEAF_THREADS) {
         int r = idx >> 6, c = idx & 63;
-        G[(int64_t)(r0 + r) * npad + c0 + c] = S[r * SLD + c];
-        Gt[(int64_t)(c0 + r) * npad + r0 + c] = S[c * SLD + r];
+        Gt[(int64_t)(c0 + r) * npad + r0 + c] = T[r * TLD + c];
     }
+    __syncthreads();  // T is reused by the next block
 }
 
 // running extreme pivots of this matrix (leaves of one matrix run in stream order: no atomics needed).
@@ -204,15 +218,18 @@ __global__ void __launch_bounds__(LEAF_THREADS) leaf64_kernel(LeafIO io) {
     double* invd = rowb + 128;    // [64]
     double* dd = invd + 64;       // [64]
     const int64_t z = blockIdx.z, zoff = z * (int64_t)io.npad * io.npad;
-    leaf_load(A, io.KB + zoff, io.npad, io.o, io.o, true);
+    double* T = dd + 64;          // [64][TLD] transpose staging
+    leaf_load_async(A, io.KB + zoff, io.npad, io.o, io.o);
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
     chol_inv_64(A, W, colb, rowb, invd, dd);
-    leaf_store(A, io.L + zoff, io.Lt + zoff, io.npad, io.o, io.o);
-    leaf_store(W, io.Linv + zoff, io.U + zoff, io.npad, io.o, io.o);
+    leaf_store(A, T, io.L + zoff, io.Lt + zoff, io.npad, io.o, io.o);
+    leaf_store(W, T, io.Linv + zoff, io.U + zoff, io.npad, io.o, io.o);
     if (threadIdx.x < 64) io.diag[z * io.npad + io.o + threadIdx.x] = dd[threadIdx.x];
     leaf_update_stats(io, dd, 64, z);
 }
-constexpr int LEAF64_SMEM = (2 * 64 * SLD + 2 * 128 + 2 * 64) * 8;
+constexpr int LEAF64_SMEM = (2 * 64 * SLD + 2 * 128 + 2 * 64 + 64 * TLD) * 8;
 
 // 128x128 block = [A11 .; A21 A22]:
 //   (L11, X11) = chol_inv(A11);  L21 = A21 X11^T [+ gated correction];  A22 -= L21 L21^T;
@@ -232,9 +249,11 @@ __global__ void __launch_bounds__(LEAF_THREADS) leaf128_kernel(LeafIO io) {
     const int64_t z = blockIdx.z, zoff = z * (int64_t)io.npad * io.npad;
     const int o = io.o, npad = io.npad;
     const double* Kz = io.KB + zoff;
-    leaf_load(B0, Kz, npad, o, o, true);
-    leaf_load(B2, Kz, npad, o + 64, o, false);
-    leaf_load(B3, Kz, npad, o + 64, o + 64, true);
+    leaf_load_async(B0, Kz, npad, o, o);
+    leaf_load_async(B2, Kz, npad, o + 64, o);
+    leaf_load_async(B3, Kz, npad, o + 64, o + 64);
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
     chol_inv_64(B0, B1, colb, rowb, invd, dd);
     const bool refine = leaf_update_stats(io, dd, 64, z);
@@ -248,18 +267,19 @@ __global__ void __launch_bounds__(LEAF_THREADS) leaf128_kernel(LeafIO io) {
     }
     mma64<true>(B5, B5, -1.0, B3, B3);  // A22 -= L21 L21^T
     __syncthreads();
+    leaf_store(B5, B2, io.L + zoff, io.Lt + zoff, npad, o + 64, o);  // L21 (B2 = A21 / residual is dead: staging)
     chol_inv_64(B3, B4, colb, rowb, invd + 64, dd + 64);
     leaf_update_stats(io, dd + 64, 64, z);
     mma64<false>(B4, B5, 1.0, B2, nullptr);  // T = X22 L21
-    leaf_store(B5, io.L + zoff, io.Lt + zoff, npad, o + 64, o);  // L21 (B5 is read-only in this phase)
     __syncthreads();
     mma64<false>(B2, B1, -1.0, B5, nullptr);  // X21 = -T X11
     __syncthreads();
-    leaf_store(B0, io.L + zoff, io.Lt + zoff, npad, o, o);
-    leaf_store(B3, io.L + zoff, io.Lt + zoff, npad, o + 64, o + 64);
-    leaf_store(B1, io.Linv + zoff, io.U + zoff, npad, o, o);
-    leaf_store(B4, io.Linv + zoff, io.U + zoff, npad, o + 64, o + 64);
-    leaf_store(B5, io.Linv + zoff, io.U + zoff, npad, o + 64, o);
+    // B2 (T) is dead from here on and serves as the transpose staging buffer
+    leaf_store(B0, B2, io.L + zoff, io.Lt + zoff, npad, o, o);
+    leaf_store(B3, B2, io.L + zoff, io.Lt + zoff, npad, o + 64, o + 64);
+    leaf_store(B1, B2, io.Linv + zoff, io.U + zoff, npad, o, o);
+    leaf_store(B4, B2, io.Linv + zoff, io.U + zoff, npad, o + 64, o + 64);
+    leaf_store(B5, B2, io.Linv + zoff, io.U + zoff, npad, o + 64, o);
     if (threadIdx.x < 128) io.diag[z * npad + o + threadIdx.x] = dd[threadIdx.x];
 }
 constexpr int LEAF128_SMEM = (6 * 64 * SLD + 2 * 128 + 2 * 128) * 8;
