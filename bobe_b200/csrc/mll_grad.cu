@@ -142,24 +142,26 @@ __global__ void __launch_bounds__(256) mll_grad_tile_kernel(const double* __rest
     }
 }
 
-__global__ void mll_finish_kernel(const double* __restrict__ partial, int ntiles, int d, int P, int has_kv, int64_t n,
-                                  const double* __restrict__ logdet, const double* __restrict__ quad,
-                                  const int32_t* __restrict__ info, double* __restrict__ val,
-                                  double* __restrict__ grad) {
+// one warp per parameter: lanes stride over the tile partials (fixed order per lane, fixed shuffle tree: deterministic)
+__global__ void __launch_bounds__(256) mll_finish_kernel(const double* __restrict__ partial, int ntiles, int d, int P,
+                                                         int has_kv, int64_t n, const double* __restrict__ logdet,
+                                                         const double* __restrict__ quad,
+                                                         const int32_t* __restrict__ info, double* __restrict__ val,
+                                                         double* __restrict__ grad) {
     const int64_t z = blockIdx.x;
-    const int j = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int np1 = d + 1;
-    if (j < P) {
+    for (int j = warp; j < P; j += 8) {
         double g = 0.0;
         if (j < d || (has_kv && j == d)) {
             double s = 0.0;
-            for (int t = 0; t < ntiles; ++t) s += partial[(z * ntiles + t) * np1 + j];
-            g = 0.5 * s;
+            for (int t = lane; t < ntiles; t += 32) s += partial[(z * ntiles + t) * np1 + j];
+            g = 0.5 * warp_sum(s);
         }
         if (info[z]) g = nan("");
-        grad[z * P + j] = g;
+        if (lane == 0) grad[z * P + j] = g;
     }
-    if (j == 0) val[z] = -0.5 * quad[z] - logdet[z] - 0.5 * (double)n * 1.8378770664093454835606594728112;
+    if (threadIdx.x == 0) val[z] = -0.5 * quad[z] - logdet[z] - 0.5 * (double)n * 1.8378770664093454835606594728112;
 }
 
 constexpr int MLL_MAX_STREAMS = 8;

@@ -407,8 +407,9 @@ class GP:
         stage = [torch.empty((rows, d), dtype=torch.float64, device=dev) for _ in range(2)]
         copied = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
-        mean_h = torch.empty(M, dtype=torch.float64).pin_memory() if want_mean else None
-        var_h = torch.empty(M, dtype=torch.float64).pin_memory() if want_var else None
+        # straight from torch's caching pinned allocator (no pageable allocation + copy as .pin_memory() would do)
+        mean_h = torch.empty(M, dtype=torch.float64, pin_memory=True) if want_mean else None
+        var_h = torch.empty(M, dtype=torch.float64, pin_memory=True) if want_var else None
         for i, s in enumerate(range(0, M, rows)):
             e, b = min(M, s + rows), i & 1
             with torch.cuda.stream(copy):
