@@ -143,6 +143,21 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _ensure_native():
+    """The in-tree .so normally travels with the repo snapshot; if it is missing, local rank 0 builds it (nvcc) and
+    the other ranks wait for the file.  There is no fallback: without the library the import below fails loudly."""
+    from bobe_b200.build import LIB_PATH, build_native
+    if os.path.exists(LIB_PATH):
+        return
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        build_native(force=False)
+    else:
+        t0 = time.time()
+        while not os.path.exists(LIB_PATH) and time.time() - t0 < 900:
+            time.sleep(2.0)
+        time.sleep(2.0)  # let the linker finish writing
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -155,6 +170,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    _ensure_native()
     import torch
     import torch.distributed as tdist
     from bobe_b200 import GP, ops, _lib
