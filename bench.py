@@ -146,11 +146,15 @@ def run_reference(args):
 def _ensure_native():
     """The in-tree .so normally travels with the repo snapshot; if it is missing, local rank 0 builds it (nvcc) and
     the other ranks wait for the file.  There is no fallback: without the library the import below fails loudly."""
-    from bobe_b200.build import LIB_PATH, build_native
+    LIB_PATH = os.path.join(ROOT, "bobe_b200", "lib", "libbobe_b200.so")
     if os.path.exists(LIB_PATH):
         return
     if int(os.environ.get("LOCAL_RANK", "0")) == 0:
-        build_native(force=False)
+        import importlib.util  # by path: importing bobe_b200.build would import the package, which needs the library
+        spec = importlib.util.spec_from_file_location("bobe_b200_build", os.path.join(ROOT, "bobe_b200", "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build_native(force=False)
     else:
         t0 = time.time()
         while not os.path.exists(LIB_PATH) and time.time() - t0 < 900:

@@ -8,11 +8,20 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def _load_build_module(root):
+    """bobe_b200/build.py loaded by PATH: importing it as bobe_b200.build would run bobe_b200/__init__, which refuses
+    to import without the native library -- the very thing this module creates."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bobe_b200_build", os.path.join(root, "bobe_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     # the native library must exist before bobe_b200 is imported (no CPU fallback); nvcc cross-compiles here
-    from bobe_b200.build import build_native
-    build_native(force=False)
+    _load_build_module(ROOT).build_native(force=False)
 
 
 def pytest_collection_modifyitems(config, items):
