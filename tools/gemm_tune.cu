@@ -34,16 +34,11 @@ int main() {
     std::vector<double> hk((size_t)maxrows * npad);
     for (size_t i = 0; i < hk.size(); ++i) hk[i] = ((i * 2654435761u) % 1000) * 1e-3;
     cudaMemcpy(K, hk.data(), sizeof(double) * hk.size(), cudaMemcpyHostToDevice);
-    run<TileCfg<128, 128, 2, 4, 4, 16, true>>("128x128 w2x4 s4 bk16 ilv", Linv, npad, K, out, n);
-    run<TileCfg<128, 128, 2, 4, 4, 16, false>>("128x128 w2x4 s4 bk16", Linv, npad, K, out, n);
-    run<TileCfg<128, 128, 2, 4, 3, 32, true>>("128x128 w2x4 s3 bk32 ilv", Linv, npad, K, out, n);
-    run<TileCfg<128, 128, 4, 4, 4, 16, true>>("128x128 w4x4 s4 bk16 ilv", Linv, npad, K, out, n);
     run<TileCfg<128, 128, 4, 4, 3, 32, true>>("128x128 w4x4 s3 bk32 ilv", Linv, npad, K, out, n);
-    run<TileCfg<128, 128, 4, 2, 4, 16, true>>("128x128 w4x2 s4 bk16 ilv", Linv, npad, K, out, n);
-    run<TileCfg<128, 128, 8, 2, 3, 32, true>>("128x128 w8x2 s3 bk32 ilv", Linv, npad, K, out, n);
-    run<TileCfg<128, 128, 2, 8, 3, 32, true>>("128x128 w2x8 s3 bk32 ilv", Linv, npad, K, out, n);
-    run<TileCfg<128, 128, 4, 4, 3, 32, false>>("128x128 w4x4 s3 bk32", Linv, npad, K, out, n);
-    run<TileCfg<128, 128, 4, 4, 2, 32, true>>("128x128 w4x4 s2 bk32 ilv", Linv, npad, K, out, n);
-    run<TileCfg<128, 128, 4, 4, 6, 16, true>>("128x128 w4x4 s6 bk16 ilv", Linv, npad, K, out, n);
+    run<TileCfg<256, 64, 8, 2, 4, 16, true>>("256x64 w8x2 s4 bk16 ilv", Linv, npad, K, out, n);
+    run<TileCfg<256, 64, 8, 2, 2, 32, true>>("256x64 w8x2 s2 bk32 ilv", Linv, npad, K, out, n);
+    run<TileCfg<256, 64, 4, 4, 4, 16, true>>("256x64 w4x4 s4 bk16 ilv", Linv, npad, K, out, n);
+    run<TileCfg<256, 64, 4, 4, 2, 32, true>>("256x64 w4x4 s2 bk32 ilv", Linv, npad, K, out, n);
+    run<TileCfg<256, 64, 8, 2, 5, 16, true>>("256x64 w8x2 s5 bk16 ilv", Linv, npad, K, out, n);
     return 0;
 }
