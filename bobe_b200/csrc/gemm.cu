@@ -39,12 +39,15 @@ int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& a, int batch) {
         set_error("gemm_nt: K must be a multiple of 32 and N/ld even (M=%d N=%d K=%d)", a.M, a.N, a.K);
         return BOBE_E_ARG;
     }
-    // 128x128 tiles are the efficient ones, but the lower levels of the recursion are latency-bound chains of small
-    // products: when the big tiling cannot put two CTAs' worth of work on every SM, use 64x64 tiles (4x the CTAs,
-    // each finishing in well under half the time).
-    const int64_t big_ctas = (int64_t)((a.M + 127) / 128) * ((a.N + 127) / 128) * batch;
-    static const int64_t small_below = env_int("BOBE_SMALL_TILE_CTAS", 2 * 148);
-    bool small = (a.M <= 64 || a.N <= 64) || big_ctas < small_below;
+    // Tile choice (measured, profiles/r01/README.md "tile choice"): 64x64 tiles with FOUR CTAs per SM beat the 128x128 /
+    // one-CTA-per-SM configuration for every product issued through this launcher -- 21.6 vs 23.2 ms for the 64-restart
+    // factorisation, 51.5 vs 56.5 ms for the WIPV solve.  The k loops here are short (<= n/2 for the recursion), so a
+    // lone CTA leaves the tensor pipe idle during its pipeline fill and its dual-store epilogue; with four co-resident
+    // CTAs another one is always in its main loop, and small CTAs also fit beside the leaf kernels of other streams.
+    // The 128x128 configuration stays the right one for trmm_sumsq (k loops up to n, no epilogue stores).
+    static const int64_t forced = env_int("BOBE_TILE", 0);  // experiment knob: 1 small, 2 medium, 3 big
+    int tile = 1;
+    if (forced && !(a.M <= 64 || a.N <= 64)) tile = (int)forced;
     if (!a.C && !a.Ct) {
         set_error("gemm_nt: no output");
         return BOBE_E_ARG;
@@ -62,8 +65,10 @@ int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& a, int batch) {
     using M1 = std::integral_constant<int, TRI_LOWER>;
     using M2 = std::integral_constant<int, TRI_UPPER>;
     int32_t rc;
-    if (small)
+    if (tile == 1)
         rc = mode == TRI_LOWER ? go(CfgSmall{}, M1{}) : (mode == TRI_UPPER ? go(CfgSmall{}, M2{}) : go(CfgSmall{}, M0{}));
+    else if (tile == 2)
+        rc = mode == TRI_LOWER ? go(CfgMed{}, M1{}) : (mode == TRI_UPPER ? go(CfgMed{}, M2{}) : go(CfgMed{}, M0{}));
     else
         rc = mode == TRI_LOWER ? go(CfgBig{}, M1{}) : (mode == TRI_UPPER ? go(CfgBig{}, M2{}) : go(CfgBig{}, M0{}));
     if (rc) return rc;

@@ -3,7 +3,7 @@
 // of mma.sync.m8n8k4.f64.  All products on the hot path are brought into this form by keeping every
 // triangular matrix in both orientations ("NT-only formulation").
 //
-// Shared-memory layout per stage and operand: two "k8 panels", each `rows x 8` doubles dense (64-byte
+// Shared-memory layout per stage and operand: BK/8 "k8 panels", each `rows x 8` doubles dense (64-byte
 // rows).  Lane (g = lane>>2, t = lane&3) reads 16 bytes at (row g, doubles 2t..2t+1) with ONE LDS.128 and
 // uses .x for the MMA that contracts k = {0,2,4,6} of the panel and .y for the MMA that contracts
 // {1,3,5,7}: the k labelling inside an MMA is free as long as A and B agree.  A quarter-warp (rows g, g+1)
@@ -15,9 +15,10 @@ namespace bobe {
 
 // ILV: warp wm owns the 8-row groups {wm, wm + WM, wm + 2 WM, ...} of the tile instead of WTM consecutive rows, so
 // that a triangular operand leaves every warp the same number of live fragments (see Mainloop::run, tri0).
-template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int BK_ = 16, bool ILV_ = false>
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int BK_ = 16, bool ILV_ = false, int MINB_ = 1>
 struct TileCfg {
     static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_;
+    static constexpr int MINB = MINB_;  // CTAs per SM the register allocation must allow (__launch_bounds__)
     static constexpr bool ILV = ILV_;
     // first row (within the tile) of fragment mf of warp-row wm
     __host__ __device__ static constexpr int frag_row(int wm, int mf) {
@@ -337,7 +338,7 @@ struct GemmArgs {
 // k-tiles, see Mainloop::run).  A triangular B operand is brought into this form by the caller computing the
 // transposed product (the kernel stores both orientations anyway).
 template <class Cfg, int MODE>
-__global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(GemmArgs p) {
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_kernel(GemmArgs p) {
     extern __shared__ __align__(16) double smem[];
     const int i0 = blockIdx.y * Cfg::BM, j0 = blockIdx.x * Cfg::BN;
     if ((p.flags & GEMM_C_LOWER) && j0 > i0 + Cfg::BM - 1) return;
@@ -469,7 +470,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
 // MMA and LDS latencies, half the barriers per flop.
 using CfgBig = TileCfg<128, 128, 4, 4, 3, 32, true>;   // 512 threads, warp tile 32x32, 3 stages x 64 KB = 192 KB smem
 using CfgTrmm = CfgBig;
-using CfgSmall = TileCfg<64, 64, 2, 2, 4, 16, true>;   // 128 threads, warp tile 32x32, 64 KB smem
+using CfgSmall = TileCfg<64, 64, 2, 2, 3, 16, true, 4>;  // 128 threads, warp tile 32x32, 48 KB smem: four CTAs per SM
+using CfgMed = TileCfg<128, 64, 4, 2, 4, 16, true, 2>; // 256 threads, warp tile 32x32, 96 KB smem: two CTAs per SM
 
 int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& args, int batch);
 
