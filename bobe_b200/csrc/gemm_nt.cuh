@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_kernel(GemmAr
 // One CTA owns BN queries and sweeps all row blocks of Linv (a lower-triangular NT product), squaring and
 // summing each finished BM x BN block of V into per-query registers.  V never leaves the SM.
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, 1)
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
     trmm_sumsq_kernel(const double* __restrict__ Linv, int n, int npad, const double* __restrict__ Kstar, int64_t ldk,
                       int64_t q_begin, int64_t M, double kk, double scale, int standardised,
                       double* __restrict__ var_out) {

@@ -7,7 +7,7 @@ using namespace bobe;
 
 template <class Cfg>
 void run(const char* name, const double* Linv, int npad, const double* K, double* out, int n) {
-    int rows = 148 * Cfg::BN;
+    int rows = 148 * 128;  // same chunk for every configuration (grid = rows / BN CTAs)
     cudaFuncSetAttribute(trmm_sumsq_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e30f;
@@ -35,10 +35,10 @@ int main() {
     for (size_t i = 0; i < hk.size(); ++i) hk[i] = ((i * 2654435761u) % 1000) * 1e-3;
     cudaMemcpy(K, hk.data(), sizeof(double) * hk.size(), cudaMemcpyHostToDevice);
     run<TileCfg<128, 128, 4, 4, 3, 32, true>>("128x128 w4x4 s3 bk32 ilv", Linv, npad, K, out, n);
-    run<TileCfg<256, 64, 8, 2, 4, 16, true>>("256x64 w8x2 s4 bk16 ilv", Linv, npad, K, out, n);
-    run<TileCfg<256, 64, 8, 2, 2, 32, true>>("256x64 w8x2 s2 bk32 ilv", Linv, npad, K, out, n);
-    run<TileCfg<256, 64, 4, 4, 4, 16, true>>("256x64 w4x4 s4 bk16 ilv", Linv, npad, K, out, n);
-    run<TileCfg<256, 64, 4, 4, 2, 32, true>>("256x64 w4x4 s2 bk32 ilv", Linv, npad, K, out, n);
-    run<TileCfg<256, 64, 8, 2, 5, 16, true>>("256x64 w8x2 s5 bk16 ilv", Linv, npad, K, out, n);
+    run<TileCfg<128, 64, 4, 2, 4, 16, true, 2>>("128x64 w4x2 s4 bk16 ilv x2", Linv, npad, K, out, n);
+    run<TileCfg<128, 64, 4, 2, 3, 16, true, 2>>("128x64 w4x2 s3 bk16 ilv x2", Linv, npad, K, out, n);
+    run<TileCfg<128, 64, 2, 2, 3, 16, true, 3>>("128x64 w2x2 s3 bk16 ilv x3", Linv, npad, K, out, n);
+    run<TileCfg<64, 64, 2, 2, 3, 16, true, 4>>("64x64 w2x2 s3 bk16 ilv x4", Linv, npad, K, out, n);
+    run<TileCfg<128, 128, 4, 4, 2, 32, true>>("128x128 w4x4 s2 bk32 ilv", Linv, npad, K, out, n);
     return 0;
 }
