@@ -1,5 +1,6 @@
 // Tile-configuration sweep for the fused triangular-multiply + sum-of-squares kernel (development aid).
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include "../bobe_b200/csrc/gemm_nt.cuh"
 namespace bobe { void set_error(const char*, ...) {} int32_t check_launch(const char*) { return 0; } }
@@ -23,8 +24,8 @@ void run(const char* name, const double* Linv, int npad, const double* K, double
            fl / best / 1e9, cudaGetErrorString(e));
 }
 
-int main() {
-    const int n = 2000, npad = 2048;
+int main(int argc, char** argv) {
+    const int n = argc > 1 ? atoi(argv[1]) : 2000, npad = ((n + 63) / 64) * 64;
     const int maxrows = 148 * 256;
     std::vector<double> h((size_t)npad * npad, 0.0);
     for (int i = 0; i < npad; ++i) for (int j = 0; j <= i; ++j) h[(size_t)i * npad + j] = (i == j) ? 1.0 : 1e-3 * ((i * 131 + j * 7) % 97 - 48);
@@ -40,5 +41,7 @@ int main() {
     run<TileCfg<128, 64, 2, 2, 3, 16, true, 3>>("128x64 w2x2 s3 bk16 ilv x3", Linv, npad, K, out, n);
     run<TileCfg<64, 64, 2, 2, 3, 16, true, 4>>("64x64 w2x2 s3 bk16 ilv x4", Linv, npad, K, out, n);
     run<TileCfg<128, 128, 4, 4, 2, 32, true>>("128x128 w4x4 s2 bk32 ilv", Linv, npad, K, out, n);
+    run<TileCfg<64, 128, 2, 4, 3, 16, true, 2>>("64x128 w2x4 s3 bk16 ilv x2", Linv, npad, K, out, n);
+    run<TileCfg<64, 64, 2, 2, 4, 16, true, 3>>("64x64 w2x2 s4 bk16 ilv x3", Linv, npad, K, out, n);
     return 0;
 }
