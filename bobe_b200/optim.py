@@ -265,6 +265,9 @@ def optimize_optax(fun: Callable = None, fun_args=(), fun_kwargs={}, num_params:
     else:
         scaled_vg = value_and_grad
 
+    if batched_value_and_grad is not None and not (fun_args or fun_kwargs):
+        return _optax_lockstep(batched_value_and_grad, x0, bounds_arr, lr, early_stop_patience, maxiter)
+
     global_best_f, global_best_params = np.inf, None
     for x_init in x0:  # BOBE/optim.py:128-136
         try:
@@ -290,6 +293,54 @@ def optimize_optax(fun: Callable = None, fun_args=(), fun_kwargs={}, num_params:
                     break
         if best_f < global_best_f:
             global_best_f, global_best_params = best_f, params
+    best = scale_from_unit(global_best_params, bounds_arr) if bounds_arr is not None else global_best_params
+    return np.array(best), float(global_best_f)
+
+
+def _optax_lockstep(batched_value_and_grad, x0, bounds_arr, lr, early_stop_patience, maxiter):
+    """The sequential per-restart Adam loops of BOBE/optim.py:128-160 advanced in lock step: the restarts never
+    interact, so stepping all still-active ones with one batched evaluation gives exactly the trajectories of the
+    sequential loops (per-restart patience, per-restart stop, the winner's LAST iterate is returned, :158-160) with
+    R times fewer device calls."""
+    R = x0.shape[0]
+    span = (bounds_arr[1] - bounds_arr[0]) if bounds_arr is not None else 1.0
+
+    def scaled(us):
+        xs = scale_from_unit(us, bounds_arr) if bounds_arr is not None else us
+        v, g = batched_value_and_grad(xs)
+        return np.asarray(v, dtype=np.float64), np.asarray(g, dtype=np.float64) * span
+
+    global_best_f, global_best_params = np.inf, None
+    try:  # initial sweep over x0 (:128-136)
+        v0, _ = scaled(x0)
+        for r in range(R):
+            if np.isfinite(v0[r]) and v0[r] < global_best_f:
+                global_best_f, global_best_params = float(v0[r]), x0[r].copy()
+    except Exception as e:
+        log.warning(f"  Initial points failed with an error: {e}")
+    params = x0.copy()
+    m, v = np.zeros_like(params), np.zeros_like(params)
+    best_f = np.full(R, np.inf)
+    patience = np.full(R, early_stop_patience, dtype=np.int64)
+    active = np.ones(R, dtype=bool)
+    b1, b2, eps = 0.9, 0.999, 1e-8
+    for t in range(1, maxiter + 1):
+        idx = np.where(active)[0]
+        if idx.size == 0:
+            break
+        vals, grads = scaled(params[idx])
+        m[idx] = b1 * m[idx] + (1 - b1) * grads
+        v[idx] = b2 * v[idx] + (1 - b2) * grads * grads
+        step = lr * (m[idx] / (1 - b1**t)) / (np.sqrt(v[idx] / (1 - b2**t)) + eps)
+        new = params[idx] - step
+        params[idx] = np.clip(new, 0.0, 1.0) if bounds_arr is not None else new
+        improved = vals < best_f[idx]
+        best_f[idx] = np.where(improved, vals, best_f[idx])
+        patience[idx] = np.where(improved, early_stop_patience, patience[idx] - 1)
+        active[idx] = patience[idx] != 0
+    for r in range(R):  # same winner rule and order as the sequential loop
+        if best_f[r] < global_best_f:
+            global_best_f, global_best_params = float(best_f[r]), params[r]
     best = scale_from_unit(global_best_params, bounds_arr) if bounds_arr is not None else global_best_params
     return np.array(best), float(global_best_f)
 

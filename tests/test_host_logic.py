@@ -274,3 +274,29 @@ def test_surrogate_pool_batches_concurrent_single_point_calls():
     assert np.allclose(lax_map(FakeGP(), "predict_mean_single", np.ones((5, 2)), batch_size=200), 2.0)
     with pytest.raises(ValueError):
         lax_map(FakeGP(), "fit", np.ones((5, 2)))
+
+
+def test_optax_lockstep_equals_sequential_restarts():
+    """optimize_optax with a batched objective advances all restarts in lock step; the result must be exactly that of
+    the reference's sequential per-restart loops (BOBE/optim.py:128-160), including per-restart patience stops."""
+    def vg(x):  # a bumpy bowl: different restarts stop at different iterations
+        x = np.asarray(x, dtype=np.float64)
+        f = np.sum((x - 1.3) ** 2) + 0.3 * np.sin(5 * x[0]) * np.cos(3 * x[1])
+        g = 2 * (x - 1.3)
+        g[0] += 1.5 * np.cos(5 * x[0]) * np.cos(3 * x[1])
+        g[1] -= 0.9 * np.sin(5 * x[0]) * np.sin(3 * x[1])
+        return float(f), g
+    calls = []
+
+    def vg_b(xs):
+        calls.append(len(xs))
+        out = [vg(x) for x in np.atleast_2d(xs)]
+        return np.array([o[0] for o in out]), np.stack([o[1] for o in out])
+    x0 = np.random.default_rng(0).uniform(0, 1, (6, 2))
+    opts = {"name": "adam", "lr": 5e-2, "early_stop_patience": 5}
+    seq = optim.optimize_optax(num_params=2, bounds=[0, 4], x0=x0, maxiter=300, n_restarts=6, optimizer_options=dict(opts),
+                               value_and_grad=vg)
+    lock = optim.optimize_optax(num_params=2, bounds=[0, 4], x0=x0, maxiter=300, n_restarts=6,
+                                optimizer_options=dict(opts), batched_value_and_grad=vg_b)
+    assert np.array_equal(seq[0], lock[0]) and seq[1] == lock[1]
+    assert calls[0] == 6 and min(calls) < 6 and len(calls) <= 301  # restarts retire one by one; one call per step
