@@ -300,11 +300,71 @@ extern "C" int32_t bobe_factor_append(void* stream_, int32_t kind, const double*
 }
 
 // ---- predict --------------------------------------------------------------------------------------------
+namespace {
+constexpr int SMALL_M = 16;  // up to this many queries the variance goes through the matrix-vector path below
+
+// V[q][i] = sum_{k <= i} Linv[i][k] K*[q][k] for a handful of queries: one warp per row of Linv, the row is read once
+// and dotted with every query's K* row.  A single 128-query tile of trmm_sumsq would run the whole triangular product
+// on ONE SM (1.5 ms at n = 1500); this spreads the n^2/2 multiply-adds of a single-point call over the machine.
+template <int MQ>
+__global__ void __launch_bounds__(256) linv_apply_small_kernel(const double* __restrict__ Linv, int n, int npad,
+                                                               const double* __restrict__ Kstar, int64_t ldk, int M,
+                                                               double* __restrict__ V) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const double* l = Linv + (int64_t)row * npad;
+    double acc[MQ];
+#pragma unroll
+    for (int q = 0; q < MQ; ++q) acc[q] = 0.0;
+    for (int k = lane; k <= row; k += 32) {
+        const double lv = l[k];
+#pragma unroll
+        for (int q = 0; q < MQ; ++q)
+            if (q < M) acc[q] = fma(lv, Kstar[q * ldk + k], acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < MQ; ++q) {
+        const double s = warp_sum(acc[q]);
+        if (lane == 0 && q < M) V[(int64_t)q * npad + row] = s;
+    }
+}
+
+// var[q] = kk - sum_i V[q][i]^2 with the floor / scale semantics of trmm_sumsq_kernel (one CTA per query, fixed order)
+__global__ void __launch_bounds__(256) small_var_kernel(const double* __restrict__ V, int n, int npad, double kk,
+                                                        double scale, int standardised, double* __restrict__ var_out) {
+    __shared__ double red[8];
+    const int q = blockIdx.x;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const double v = V[(int64_t)q * npad + i];
+        s = fma(v, v, s);
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        double var = kk - t;
+        if (standardised) {  // BOBE/gp.py:487-488
+            if (isnan(var)) var = SAFE_FLOOR;
+            if (var < SAFE_FLOOR) var = SAFE_FLOOR;
+        } else {  // BOBE/gp.py:465-466
+            if (var < SAFE_FLOOR) var = SAFE_FLOOR;
+            var *= scale;
+        }
+        var_out[q] = var;
+    }
+}
+}  // namespace
+
 extern "C" int64_t bobe_predict_workspace_bytes(int64_t n, int64_t d, int64_t M, int32_t mode) {
     if (M <= 0 || n <= 0 || d <= 0) return 256;
     int64_t bytes = round_up(d * npad_of(n), 32) * 8 + 512;  // scaled, transposed training inputs
-    if (mode & BOBE_PREDICT_VAR)  // K* panel of up to KCHUNKS chunks
+    if (mode & BOBE_PREDICT_VAR) {  // K* panel of up to KCHUNKS chunks + row-split partial sums of one chunk
         bytes += round_up(M < KCHUNKS * QCHUNK ? M : KCHUNKS * QCHUNK, 128) * npad_of(n) * 8;
+        bytes += TRMM_MAX_SPLIT * round_up(M < QCHUNK ? M : QCHUNK, 128) * 8;
+    }
     return bytes;
 }
 
@@ -333,6 +393,7 @@ extern "C" int32_t bobe_predict(void* stream_, int32_t kind, const double* X, in
     }
     double* xs = align256(ws);  // (d, npad) = X^T / l, built once per call
     double* kstar = want_var ? xs + round_up(d * npad, 32) : nullptr;
+    double* partial = want_var ? kstar + round_up(M < KCHUNKS * QCHUNK ? M : KCHUNKS * QCHUNK, 128) * npad : nullptr;
     if (int32_t rc = launch_prescale(stream, X, n, d, ls, 0, xs, npad, 0, 1)) return rc;
     // mean only: no K* panel to bound, so the rows go out in launches as large as the grid allows (more CTAs per SM
     // for the kernel-matrix kernel); with the variance, the K* panel of KCHUNKS chunks is built by one launch and
@@ -351,11 +412,18 @@ extern "C" int32_t bobe_predict(void* stream_, int32_t kind, const double* X, in
         a.store_rows = rows_pad; a.store_cols = npad; a.vec_ok = 1;
         a.y_mean = y_mean; a.y_std = y_std; a.mean_standardised = standardised;
         if (int32_t rc = launch_kmat(stream, kind, a, 1)) return rc;
-        if (want_var) {
+        if (want_var && M <= SMALL_M) {  // a handful of queries: matrix-vector path (V in rows 64.. of the K* panel)
+            double* V = kstar + 64 * npad;
+            linv_apply_small_kernel<SMALL_M><<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(Linv, (int)n, (int)npad, kstar, npad,
+                                                                                       (int)M, V);
+            small_var_kernel<<<(unsigned)M, 256, 0, stream>>>(V, (int)n, (int)npad, kv + noise, y_std * y_std, standardised,
+                                                            var_out);
+            if (int32_t rc = check_launch("small-M variance")) return rc;
+        } else if (want_var) {
             for (int64_t c0 = 0; c0 < rows_pad; c0 += QCHUNK) {
                 const int64_t crows = (rows_pad - c0 < QCHUNK) ? rows_pad - c0 : QCHUNK;
                 if (int32_t rc = launch_trmm_sumsq(stream, Linv, (int)n, (int)npad, kstar + c0 * npad, npad, crows, q0 + c0, M,
-                                                   kv + noise, y_std * y_std, standardised, var_out))
+                                                   kv + noise, y_std * y_std, standardised, var_out, partial))
                     return rc;
             }
         }

@@ -75,18 +75,57 @@ int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& a, int batch) {
     return check_launch("gemm_nt_kernel");
 }
 
+// var = kk - sum over the row-split partial sums, with the floor / scale semantics of the fused path
+__global__ void __launch_bounds__(256) trmm_finish_kernel(const double* __restrict__ partial, int64_t ld, int split,
+                                                          int64_t rows, int64_t q_begin, int64_t M, double kk, double scale,
+                                                          int standardised, double* __restrict__ var_out) {
+    const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t q = q_begin + c;
+    if (c >= rows || q >= M) return;
+    double s = 0.0;
+    for (int g = 0; g < split; ++g) s += partial[(int64_t)g * ld + c];
+    double var = kk - s;
+    if (standardised) {
+        if (isnan(var)) var = SAFE_FLOOR;
+        if (var < SAFE_FLOOR) var = SAFE_FLOOR;
+    } else {
+        if (var < SAFE_FLOOR) var = SAFE_FLOOR;
+        var *= scale;
+    }
+    var_out[q] = var;
+}
+
 int32_t launch_trmm_sumsq(cudaStream_t stream, const double* Linv, int n, int npad, const double* Kstar, int64_t ldk,
                           int64_t rows_pad, int64_t q_begin, int64_t M, double kk, double scale, int standardised,
-                          double* var_out) {
+                          double* var_out, double* partial) {
     using Cfg = CfgTrmm;
     if (rows_pad % Cfg::BN) {
         set_error("trmm_sumsq: query chunk must be padded to %d", Cfg::BN);
         return BOBE_E_ARG;
     }
-    if (int32_t rc = ensure_smem<trmm_sumsq_kernel<Cfg>>(Cfg::SMEM_BYTES)) return rc;
-    dim3 grid(rows_pad / Cfg::BN);
-    trmm_sumsq_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(Linv, n, npad, Kstar, ldk, q_begin, M, kk,
-                                                                         scale, standardised, var_out);
+    if (int32_t rc = ensure_smem<trmm_sumsq_kernel<Cfg, false>>(Cfg::SMEM_BYTES)) return rc;
+    if (int32_t rc = ensure_smem<trmm_sumsq_kernel<Cfg, true>>(Cfg::SMEM_BYTES)) return rc;
+    const int qtiles = (int)(rows_pad / Cfg::BN);
+    const int nblk = (((n + 7) & ~7) + Cfg::BM - 1) / Cfg::BM;
+    // too few query tiles for 148 SMs: split the row blocks of Linv over several CTAs per tile (TRMM_MAX_SPLIT rows of
+    // `partial`, each rows_pad long)
+    int split = 1;
+    if (partial && qtiles < 74 && nblk > 1) {
+        split = 148 / qtiles;
+        split = split > nblk ? nblk : split;
+        split = split > TRMM_MAX_SPLIT ? TRMM_MAX_SPLIT : split;
+    }
+    dim3 grid(qtiles, split);
+    if (split > 1)
+        trmm_sumsq_kernel<Cfg, true><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(Linv, n, npad, Kstar, ldk, q_begin, M, kk,
+                                                                                   scale, standardised, var_out, partial,
+                                                                                   rows_pad);
+    else
+        trmm_sumsq_kernel<Cfg, false><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(Linv, n, npad, Kstar, ldk, q_begin, M, kk,
+                                                                                    scale, standardised, var_out, nullptr, 0);
+    if (split > 1)
+        trmm_finish_kernel<<<(unsigned)((rows_pad + 255) / 256), 256, 0, stream>>>(partial, rows_pad, split, rows_pad, q_begin, M,
+                                                                                 kk, scale, standardised, var_out);
     return check_launch("trmm_sumsq_kernel");
 }
 

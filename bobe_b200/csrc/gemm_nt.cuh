@@ -390,11 +390,14 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_kernel(GemmAr
 // ---- predictive variance: var_j = kk - sum_i ( sum_{k<=i} Linv[i][k] Kstar[j][k] )^2 -----------------------
 // One CTA owns BN queries and sweeps all row blocks of Linv (a lower-triangular NT product), squaring and
 // summing each finished BM x BN block of V into per-query registers.  V never leaves the SM.
-template <class Cfg>
+template <class Cfg, bool SPLIT = false>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
     trmm_sumsq_kernel(const double* __restrict__ Linv, int n, int npad, const double* __restrict__ Kstar, int64_t ldk,
                       int64_t q_begin, int64_t M, double kk, double scale, int standardised,
-                      double* __restrict__ var_out) {
+                      double* __restrict__ var_out, double* __restrict__ partial, int64_t partial_ld) {
+    // SPLIT ("row split", gridDim.y > 1, used when there are too few query tiles to fill the machine): CTA (x, y) only sweeps
+    // the row blocks y, y + gridDim.y, ... and writes its partial column sums to partial[y][query]; a finishing kernel
+    // adds them in fixed order.
     extern __shared__ __align__(16) double smem[];
     __shared__ double red[Cfg::WM][Cfg::BN];
     const int j0 = blockIdx.x * Cfg::BN;
@@ -414,13 +417,16 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
     // Linv, which only meet zero columns of K*.)
     const int n8 = (n + 7) & ~7;
     const int r_first = n8 % Cfg::BM;
-    for (int i0 = 0; i0 < n8; i0 += (i0 == 0 && r_first) ? r_first : Cfg::BM) {
+    const int first = r_first ? r_first : Cfg::BM;       // rows of block 0
+    const int nblk = (n8 + Cfg::BM - 1) / Cfg::BM;
+    for (int b = SPLIT ? blockIdx.y : 0; b < nblk; b += SPLIT ? gridDim.y : 1) {
+        const int i0 = b == 0 ? 0 : first + (b - 1) * Cfg::BM;
         double acc[Cfg::MF][Cfg::NF][2];
 #pragma unroll
         for (int mf = 0; mf < Cfg::MF; ++mf)
 #pragma unroll
             for (int nf = 0; nf < Cfg::NF; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
-        const int rows_live = (i0 == 0 && r_first) ? r_first : Cfg::BM;
+        const int rows_live = b == 0 ? first : Cfg::BM;
         int ke = min(kmax, ((i0 + rows_live + Cfg::BK - 1) / Cfg::BK) * Cfg::BK);
         // Linv is lower triangular: row i0 + r is zero beyond column i0 + r
         Mainloop<Cfg>::template run<TRI_LOWER>(acc, Linv + (int64_t)i0 * npad, npad, min(Cfg::BM, npad - i0), Bt, ldk, Cfg::BN, 0,
@@ -450,7 +456,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
 #pragma unroll
         for (int w = 0; w < Cfg::WM; ++w) s += red[w][c];
         int64_t q = q_begin + j0 + c;
-        if (q < M) {
+        if (SPLIT) {
+            partial[(int64_t)blockIdx.y * partial_ld + j0 + c] = s;
+        } else if (q < M) {
             double var = kk - s;
             if (standardised) {  // predict_single, BOBE/gp.py:487-488: NaN -> floor, then < floor -> floor
                 if (isnan(var)) var = SAFE_FLOOR;

@@ -36,9 +36,11 @@ int32_t launch_prescale(cudaStream_t stream, const double* x, int64_t n, int64_t
                         double* xs, int64_t ld, int64_t xs_stride, int batch);
 
 // trmm + sumsq (gemm.cu) ---------------------------------------------------------------------------------
+constexpr int TRMM_MAX_SPLIT = 32;  // rows of the `partial` scratch (each as long as the query chunk)
+// partial: optional scratch of TRMM_MAX_SPLIT * rows_pad doubles; enables the row split for under-filled launches
 int32_t launch_trmm_sumsq(cudaStream_t stream, const double* Linv, int n, int npad, const double* Kstar, int64_t ldk,
                           int64_t rows_pad, int64_t q_begin, int64_t M, double kk, double scale, int standardised,
-                          double* var_out);
+                          double* var_out, double* partial = nullptr);
 
 // factorisation (factor.cu) -----------------------------------------------------------------------------
 struct FactorBuffers {

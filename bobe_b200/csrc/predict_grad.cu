@@ -191,8 +191,9 @@ extern "C" int32_t bobe_predict_grad(void* stream_, int32_t kind, const double* 
                 if (int32_t rc = launch_kmat(stream, kind, a, 1)) return rc;
         }
         if (want_var) {
+            // (W is free until the triangular products below: it lends its first rows to the row-split partial sums)
             if (int32_t rc = launch_trmm_sumsq(stream, Linv, (int)n, (int)npad, l.kstar, npad, rows_pad, q0, M, kv + noise,
-                                               y_std * y_std, standardised, var_out))
+                                               y_std * y_std, standardised, var_out, npad >= TRMM_MAX_SPLIT ? l.W : nullptr))
                 return rc;
             // w = K^-1 k* as two triangular products (triangular operand = row operand, transposed store):
             //   V[q][i] = sum_k Linv[i][k] K*[q][k]  (into Cm's buffer, free until the coefficient pass)

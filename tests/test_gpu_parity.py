@@ -210,10 +210,16 @@ def test_headline_shape_properties():
     mean, var = gp.predict_mean_var_batched(Xq)
     assert mean.is_cuda and var.is_cuda and mean.shape == (M,)
     assert torch.isfinite(mean).all() and (var > 0).all() and (var <= (1 + 1e-8) * ref.y_std ** 2 * 1.0000001).all()
-    # any split of the query set gives bitwise identical results (no cross-query coupling, deterministic reductions)
+    # any split of the query set gives the same results (no cross-query coupling, deterministic reductions): bitwise
+    # for the mean; the variance of a tail chunk with < 74 query tiles goes through the row-split reduction (partial
+    # sums per row-block group added in fixed order), which can differ from the fused order in the last bit
     m1, v1 = gp.predict_mean_var_batched(Xq[:33_333])
     m2, v2 = gp.predict_mean_var_batched(Xq[33_333:])
-    assert torch.equal(torch.cat([m1, m2]), mean) and torch.equal(torch.cat([v1, v2]), var)
+    assert torch.equal(torch.cat([m1, m2]), mean)
+    assert float(((torch.cat([v1, v2]) - var).abs() / var).max()) < 1e-12
+    full = 3 * 148 * 128  # whole chunks only: the fused path on both sides, bitwise
+    _, va = gp.predict_mean_var_batched(Xq[:full])
+    assert torch.equal(va[:148 * 128], gp.predict_mean_var_batched(Xq[:148 * 128])[1])
     mean_b, var_b = gp.predict_mean_var_batched(Xq)
     assert torch.equal(mean_b, mean) and torch.equal(var_b, var)  # run-to-run determinism
     idx = np.random.default_rng(12).choice(M, 200, replace=False)

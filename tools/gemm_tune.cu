@@ -14,7 +14,7 @@ void run(const char* name, const double* Linv, int npad, const double* K, double
     float best = 1e30f;
     for (int it = 0; it < 6; ++it) {
         cudaEventRecord(e0);
-        trmm_sumsq_kernel<Cfg><<<rows / Cfg::BN, Cfg::THREADS, Cfg::SMEM_BYTES>>>(Linv, n, npad, K, npad, 0, rows, 1.0, 1.0, 0, out);
+        trmm_sumsq_kernel<Cfg><<<rows / Cfg::BN, Cfg::THREADS, Cfg::SMEM_BYTES>>>(Linv, n, npad, K, npad, 0, rows, 1.0, 1.0, 0, out, nullptr, 0);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (it && ms < best) best = ms;
     }
