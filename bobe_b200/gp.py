@@ -268,6 +268,8 @@ class GP:
                                                            self._ls_dev[None, :], kv, float(self.noise))
         self._L_dev, self._Linv_dev, self._alpha_dev = L[0], Linv[0], alpha[0]
         self._logdet, self._quad, self._info_dev = logdet, quad, info
+        self._factor_hp = (np.array(self.lengthscales, dtype=np.float64).copy(), float(self.kernel_variance),
+                           float(self.noise), self.kernel_name)
         self._factor_ok = True
 
     @property
@@ -534,6 +536,11 @@ class GP:
         unchanged there, BOBE/gp.py:541).  Returns False (caller re-factorises) when there is no valid factor to
         extend or an appended pivot is not positive."""
         if not (self._factor_ok and n_old > 0 and torch.cuda.is_available()):
+            return False
+        hp = getattr(self, "_factor_hp", None)  # the factor must belong to the CURRENT hyper-parameters (a caller may have
+        if hp is None or not (np.array_equal(hp[0], np.asarray(self.lengthscales, dtype=np.float64).reshape(-1))  # set
+                              and hp[1] == float(self.kernel_variance) and hp[2] == float(self.noise)  # the attributes
+                              and hp[3] == self.kernel_name):                                           # directly)
             return False
         if int(self._info_dev.reshape(-1)[0].item()) != 0:
             return False

@@ -480,3 +480,18 @@ def test_large_input_dimension(d):
         with pytest.raises(BobeNativeError):
             ops.kernel_matrix("rbf", T(rng.uniform(0, 1, (8, 145))), T(rng.uniform(0, 1, (8, 145))), T(np.ones(145)), 1.0,
                               0.0, False)
+
+
+def test_incremental_update_refuses_a_stale_factor():
+    """Hyper-parameters assigned directly (not through update_hyperparams) invalidate the rank-b shortcut: update() must
+    then re-factorise with the current values, as the reference does at BOBE/gp.py:541."""
+    from bobe_b200 import GP
+    rng = np.random.default_rng(3)
+    X = rng.uniform(0, 1, (90, 2))
+    y = np.sin(4 * X[:, :1]) + X[:, 1:]
+    gp = GP(X[:80], y[:80], kernel="rbf", noise=1e-6, lengthscales=np.array([0.5, 0.5]))
+    _ = gp.cholesky
+    gp.lengthscales = np.array([0.3, 0.8])
+    gp.update(X[80:], y[80:])
+    ref = O.OracleGP(X, y, kernel="rbf", noise=1e-6, lengthscales=np.array([0.3, 0.8]))
+    assert mixed_err(gp.cholesky, ref.cholesky, float(np.abs(ref.cholesky).max())) < 1e-9
