@@ -203,4 +203,36 @@ __device__ __forceinline__ void kernel_from_q_n(const double (&q)[N], double kv,
     }
 }
 
+// kernel value K0 AND the factor G of its lengthscale / input derivatives (dK/dlog l_j = G s_j), N values in lock step:
+//   RBF: G = K0;   Matern-5/2: G = kv 5/3 (1 + sqrt5 r) exp(-sqrt5 r), 0 where the 1e-30 clamp is active
+template <int KIND, int N>
+__device__ __forceinline__ void kernel_and_g_from_q_n(const double (&q)[N], double kv, double (&k0)[N], double (&G)[N]) {
+    if (KIND == BOBE_KERNEL_RBF) {
+        double x[N], e[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) x[j] = -0.5 * q[j];
+        exp_nonpos_n<N>(x, e);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            k0[j] = kv * e[j];
+            G[j] = k0[j];
+        }
+    } else {
+        double r[N], x[N], e[N];
+        bool clamped[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            clamped[j] = __double_as_longlong(q[j]) < __double_as_longlong(1e-30);
+            r[j] = sqrt_pos(clamped[j] ? 1e-30 : q[j]);
+            x[j] = -SQRT5 * r[j];
+        }
+        exp_nonpos_n<N>(x, e);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            k0[j] = kv * (1.0 + r[j] * (SQRT5 + r[j] * (5.0 / 3.0))) * e[j];
+            G[j] = clamped[j] ? 0.0 : kv * (5.0 / 3.0) * (1.0 + SQRT5 * r[j]) * e[j];
+        }
+    }
+}
+
 }  // namespace bobe

@@ -28,9 +28,13 @@ __global__ void exp_params_kernel(const double* __restrict__ lp, int64_t R, int6
 
 constexpr int GT = 64, GLD = 66;
 
+// One CTA (256 threads as 16 x 16) per lower-triangular 64 x 64 tile pair: thread (ty, tx) owns rows 4 ty .. 4 ty + 3 and
+// the columns {2 tx, 2 tx + 1, 32 + 2 tx, 33 + 2 tx} (conflict-free LDS.128 of the column operand, as in kmat_kernel).
+// Both operands come from the pre-scaled, transposed inputs xs[k][j] = X_jk / l_k of this restart (plain copies, no
+// divisions), the 16 kernel values of a thread are evaluated in lock step (kernel_and_g_from_q_n), and the weights
+// W = alpha alpha^T - K^-1 are read as 16-byte vectors.
 template <int KIND>
-__global__ void __launch_bounds__(256) mll_grad_tile_kernel(const double* __restrict__ X, int64_t n, int d,
-                                                            const double* __restrict__ ls_all,
+__global__ void __launch_bounds__(256, 2) mll_grad_tile_kernel(const double* __restrict__ xs_all, int64_t n, int d,
                                                             const double* __restrict__ kv_all,
                                                             const double* __restrict__ Kinv, int npad,
                                                             const double* __restrict__ alpha_all, int has_kv,
@@ -50,15 +54,15 @@ __global__ void __launch_bounds__(256) mll_grad_tile_kernel(const double* __rest
     while (ti * (ti + 1) / 2 > x) --ti;
     const int tj = x - ti * (ti + 1) / 2;
     const int64_t i0 = (int64_t)ti * GT, k0 = (int64_t)tj * GT;
-    const double* ls = ls_all + z * d;
+    const double* xs = xs_all + z * (int64_t)d * npad;
     const double kv = kv_all[z];
     const double* alpha = alpha_all + z * npad;
     const double* Ki = Kinv + z * (int64_t)npad * npad;
 
-    for (int idx = tid; idx < GT * d; idx += 256) {
-        int r = idx / d, k = idx - r * d;
-        sa[k * GLD + r] = (i0 + r < n) ? X[(i0 + r) * d + k] / ls[k] : 0.0;
-        sb[k * GLD + r] = (k0 + r < n) ? X[(k0 + r) * d + k] / ls[k] : 0.0;
+    for (int idx = tid; idx < d * (GT / 2); idx += 256) {  // 16-byte copies; columns >= n of xs are zero
+        const int k = idx >> 5, c = (idx & 31) * 2;
+        *reinterpret_cast<double2*>(sa + k * GLD + c) = *reinterpret_cast<const double2*>(xs + (int64_t)k * npad + i0 + c);
+        *reinterpret_cast<double2*>(sb + k * GLD + c) = *reinterpret_cast<const double2*>(xs + (int64_t)k * npad + k0 + c);
     }
     if (tid < GT) {
         sai[tid] = (i0 + tid < n) ? alpha[i0 + tid] : 0.0;
@@ -66,69 +70,78 @@ __global__ void __launch_bounds__(256) mll_grad_tile_kernel(const double* __rest
     }
     __syncthreads();
 
-    double q[4][4];
+    const double* ap = sa + ty * 4;
+    const double* bp = sb + 2 * tx;
+    double q[16];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) q[i][j] = 0.0;
-#pragma unroll 4
+    for (int e = 0; e < 16; ++e) q[e] = 0.0;
+#pragma unroll 2
     for (int k = 0; k < d; ++k) {
-        double2 a01 = *reinterpret_cast<const double2*>(sa + k * GLD + ty * 4);
-        double2 a23 = *reinterpret_cast<const double2*>(sa + k * GLD + ty * 4 + 2);
-        double2 b01 = *reinterpret_cast<const double2*>(sb + k * GLD + tx * 4);
-        double2 b23 = *reinterpret_cast<const double2*>(sb + k * GLD + tx * 4 + 2);
-        double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
+        const double2 a01 = *reinterpret_cast<const double2*>(ap + k * GLD);
+        const double2 a23 = *reinterpret_cast<const double2*>(ap + k * GLD + 2);
+        const double2 b01 = *reinterpret_cast<const double2*>(bp + k * GLD);
+        const double2 b23 = *reinterpret_cast<const double2*>(bp + k * GLD + 32);
+        const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                double df = a[i] - b[j];
-                q[i][j] = fma(df, df, q[i][j]);
+                const double df = a[i] - b[j];
+                q[4 * i + j] = fma(df, df, q[4 * i + j]);
             }
     }
+    double kval[16], G[16];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // two lock-step groups of 8: keeps the register footprint at two CTAs per SM
+        double qq[8], kk8[8], gg8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) qq[e] = q[8 * h + e];
+        kernel_and_g_from_q_n<KIND, 8>(qq, kv, kk8, gg8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            kval[8 * h + e] = kk8[e];
+            G[8 * h + e] = gg8[e];
+        }
+    }
+
     const double wsym = (ti == tj) ? 1.0 : 2.0;  // off-diagonal tiles stand for both (i,k) and (k,i)
-    double wg[4][4];
+    const int64_t c0 = k0 + 2 * tx, c1 = c0 + 32;
+    const double ak[4] = {sak[2 * tx], sak[2 * tx + 1], sak[32 + 2 * tx], sak[33 + 2 * tx]};
     double gkv = 0.0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        int64_t row = i0 + ty * 4 + i;
+        const int64_t row = i0 + ty * 4 + i;
+        const double ai = sai[ty * 4 + i];
+        // K^-1 row segment: rows < npad always exist; columns c0, c0+1, c1, c1+1 < npad
+        const double2 k01 = *reinterpret_cast<const double2*>(Ki + row * npad + c0);
+        const double2 k23 = *reinterpret_cast<const double2*>(Ki + row * npad + c1);
+        const double kin[4] = {k01.x, k01.y, k23.x, k23.y};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            int64_t col = k0 + tx * 4 + j;
-            double w = 0.0, k0v = 0.0, g = 0.0;
-            if (row < n && col < n) {
-                w = wsym * (sai[ty * 4 + i] * sak[tx * 4 + j] - Ki[row * npad + col]);
-                if (KIND == BOBE_KERNEL_RBF) {
-                    k0v = kv * exp_nonpos(-0.5 * q[i][j]);
-                    g = k0v;
-                } else {
-                    bool clamped = q[i][j] < 1e-30;
-                    double r = sqrt_pos(clamped ? 1e-30 : q[i][j]);
-                    double e = exp_nonpos(-SQRT5 * r);
-                    k0v = kv * (1.0 + r * (SQRT5 + r * (5.0 / 3.0))) * e;
-                    g = clamped ? 0.0 : kv * (5.0 / 3.0) * (1.0 + SQRT5 * r) * e;
-                }
-            }
-            gkv = fma(w, k0v, gkv);
-            wg[i][j] = w * g;
+            const int64_t col = (j < 2 ? c0 : c1 - 2) + j;
+            const bool ok = row < n && col < n;
+            const double w = ok ? wsym * (ai * ak[j] - kin[j]) : 0.0;
+            gkv = fma(w, kval[4 * i + j], gkv);
+            G[4 * i + j] = w * G[4 * i + j];  // wg
         }
     }
     const int np1 = d + 1;
     for (int k = 0; k < d; ++k) {
-        double2 a01 = *reinterpret_cast<const double2*>(sa + k * GLD + ty * 4);
-        double2 a23 = *reinterpret_cast<const double2*>(sa + k * GLD + ty * 4 + 2);
-        double2 b01 = *reinterpret_cast<const double2*>(sb + k * GLD + tx * 4);
-        double2 b23 = *reinterpret_cast<const double2*>(sb + k * GLD + tx * 4 + 2);
-        double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
-        double s = 0.0;
+        const double2 a01 = *reinterpret_cast<const double2*>(ap + k * GLD);
+        const double2 a23 = *reinterpret_cast<const double2*>(ap + k * GLD + 2);
+        const double2 b01 = *reinterpret_cast<const double2*>(bp + k * GLD);
+        const double2 b23 = *reinterpret_cast<const double2*>(bp + k * GLD + 32);
+        const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
+        double s0 = 0.0, s1 = 0.0;  // two chains: the 16 terms of one dimension do not serialise on one accumulator
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                double df = a[i] - b[j];
-                s = fma(wg[i][j], df * df, s);
+            for (int j = 0; j < 4; j += 2) {
+                const double d0 = a[i] - b[j], d1 = a[i] - b[j + 1];
+                s0 = fma(G[4 * i + j], d0 * d0, s0);
+                s1 = fma(G[4 * i + j + 1], d1 * d1, s1);
             }
-        s = warp_sum(s);
+        const double s = warp_sum(s0 + s1);
         if (lane == 0) wred[warp * np1 + k] = s;
     }
     gkv = warp_sum(gkv);
@@ -322,11 +335,11 @@ extern "C" int32_t bobe_mll_grad_batched(void* stream_, int32_t kind, const doub
             if (kind == BOBE_KERNEL_RBF) {
                 if (int32_t rc = ensure_smem<mll_grad_tile_kernel<BOBE_KERNEL_RBF>>(smem)) return rc;
                 mll_grad_tile_kernel<BOBE_KERNEL_RBF><<<grid, 256, smem, st>>>(
-                    X, n, (int)d, ls_s, kv_s, fb.KB, npad, alpha, has_kv, (int)P, partial, (int)l.ntile_pairs);
+                    xs, n, (int)d, kv_s, fb.KB, npad, alpha, has_kv, (int)P, partial, (int)l.ntile_pairs);
             } else {
                 if (int32_t rc = ensure_smem<mll_grad_tile_kernel<BOBE_KERNEL_MATERN52>>(smem)) return rc;
                 mll_grad_tile_kernel<BOBE_KERNEL_MATERN52><<<grid, 256, smem, st>>>(
-                    X, n, (int)d, ls_s, kv_s, fb.KB, npad, alpha, has_kv, (int)P, partial, (int)l.ntile_pairs);
+                    xs, n, (int)d, kv_s, fb.KB, npad, alpha, has_kv, (int)P, partial, (int)l.ntile_pairs);
             }
             if (int32_t rc = check_launch("mll_grad_tile_kernel")) return rc;
             mll_finish_kernel<<<(unsigned)Rs, 256, 0, st>>>(partial, (int)l.ntile_pairs, (int)d, (int)P, has_kv, n, logdet,
