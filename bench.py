@@ -174,6 +174,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout must carry exactly ONE line (the JSON): native libraries (e.g. NCCL's version banner) write to fd 1, so
+    # fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     _ensure_native()
     import torch
     import torch.distributed as tdist
@@ -186,6 +191,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL_DEBUG=VERSION (set in this image) makes NCCL print its version banner on STDOUT, in front of the one
+        # JSON line the driver parses; keep warnings, drop the banner (an explicit INFO / TRACE request is respected)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         tdist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -309,7 +318,8 @@ def main():
                 "clocks": clocks, "roofline": roofline, "secondary": secondary}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         tdist.destroy_process_group()
 
