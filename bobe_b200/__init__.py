@@ -8,7 +8,7 @@ from . import ops  # noqa: F401
 from .gp import GP, rbf_kernel, matern_kernel, kernel_diag, fast_update_cholesky  # noqa: F401
 from .acquisition import (AcquisitionFunction, EI, LogEI, WIPV, WIPStd, get_mc_samples, get_mc_points,  # noqa: F401
                           ACQUISITIONS)
-from .optim import optimize_scipy, optimize_optax, optimize_optax_vmap  # noqa: F401
+from .optim import optimize_scipy, optimize_optax, optimize_optax_vmap, scale_to_unit, scale_from_unit  # noqa: F401
 from .batching import SurrogatePool, lax_map  # noqa: F401
 from .clf_gp import GPwithClassifier  # noqa: F401
 
