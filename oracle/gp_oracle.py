@@ -11,7 +11,9 @@ oracle is therefore pinned by mathematics instead (tests/test_oracle.py): closed
 interpolation/noise-level identities, gradient three ways (analytic, torch autograd through
 ``torch.linalg.cholesky`` = the same reverse-mode construction JAX uses, central differences),
 ``fantasy_var`` == ``predict_var`` of an actually-updated GP, and an mpmath 60-digit re-evaluation
-(``oracle/truth_mp.py``).
+(``oracle/truth_mp.py``); and EXTERNALLY, against third-party code that shares nothing with it: scikit-learn's
+``GaussianProcessRegressor`` (posterior mean / variance, log marginal likelihood and its gradient, both kernels) and
+``SVC.decision_function`` (the classifier mask), both in tests/test_oracle.py.
 
 Every function cites the reference lines it follows (paths relative to /root/reference).
 """

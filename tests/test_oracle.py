@@ -290,3 +290,36 @@ def test_oracle_svm_decision_matches_sklearn():
     ref = clf.decision_function(xq)
     assert np.allclose(dec, ref, rtol=1e-9, atol=1e-6 * np.abs(ref).max())
     assert np.array_equal(dec >= 0, clf.predict(xq) == 1)
+
+
+@pytest.mark.parametrize("kernel", ["rbf", "matern"])
+def test_oracle_against_sklearn_gpr(kernel):
+    """External pin: scikit-learn's GaussianProcessRegressor (an independent, widely used float64 implementation of the
+    same model: ARD RBF / Matern-5/2 x constant + fixed diagonal noise) must give the oracle's posterior mean, variance,
+    log marginal likelihood and its gradient with respect to the log hyper-parameters.  It is not the reference, but
+    it shares no code with the oracle (sklearn: cho_solve on its own kernel classes; gradient via its own einsum)."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Matern
+    rng = np.random.default_rng(7)
+    n, d = 120, 4
+    X = rng.uniform(0, 1, (n, d))
+    y = np.sin(3 * X.sum(1, keepdims=True)) + X[:, :1] ** 2
+    ls, kv, noise = np.array([0.35, 0.6, 0.8, 0.5]), 1.7, 1e-6
+    gp = O.OracleGP(X, y, kernel=kernel, noise=noise, lengthscales=ls, kernel_variance=kv)
+    base = RBF(length_scale=ls) if kernel == "rbf" else Matern(length_scale=ls, nu=2.5)
+    sk = GaussianProcessRegressor(kernel=ConstantKernel(kv) * base, alpha=noise, optimizer=None, normalize_y=False)
+    sk.fit(X, gp.train_y.ravel())  # the standardised targets the GP works on (BOBE/gp.py:296-306)
+    Xq = rng.uniform(0, 1, (200, d))
+    m_sk, s_sk = sk.predict(Xq, return_std=True)
+    m_or, v_or = gp.predict_batched(Xq)
+    assert np.allclose(m_or, m_sk, rtol=1e-8, atol=1e-8)
+    # sklearn's predictive variance has no noise term in k(x*, x*): add it (BOBE/gp.py:463 uses kv + noise)
+    assert np.allclose(v_or.ravel(), s_sk ** 2 + noise, rtol=1e-6, atol=1e-9)
+    theta = np.concatenate([[np.log(kv)], np.log(ls)])  # sklearn order: constant first, then the lengthscales
+    lml, g_sk = sk.log_marginal_likelihood(theta, eval_gradient=True)
+    val, grad = gp.neg_mll_and_grad(np.concatenate([np.log(ls), [np.log(kv)]]))
+    lp, glp = gp.log_prior_and_grad(np.concatenate([np.log(ls), [np.log(kv)]]))
+    assert abs((-val - lp) - lml) < 1e-8 * max(abs(lml), n)
+    g_or = -grad - glp  # d log p(y) / d (log l_1..d, log kv)
+    assert np.allclose(g_or[:d], g_sk[1:], rtol=1e-6, atol=1e-6 * np.abs(g_sk).max())
+    assert np.allclose(g_or[d], g_sk[0], rtol=1e-6, atol=1e-6 * np.abs(g_sk).max())
