@@ -375,12 +375,12 @@ extern "C" int32_t bobe_predict(void* stream_, int32_t kind, const double* X, in
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool want_mean = mode & BOBE_PREDICT_MEAN, want_var = mode & BOBE_PREDICT_VAR;
     const int standardised = (mode & BOBE_PREDICT_STANDARDISED) ? 1 : 0;
+    if (M == 0) return BOBE_OK;  // empty query set: nothing to do (the output pointers may be null then)
     if (!X || !ls || !Xq || n <= 0 || d <= 0 || M < 0 || (want_mean && (!alpha || !mean_out)) ||
         (want_var && (!Linv || !var_out)) || !(want_mean || want_var)) {
         set_error("predict: bad arguments");
         return BOBE_E_ARG;
     }
-    if (M == 0) return BOBE_OK;
     const int64_t npad = npad_of(n);
     if (!ws || ws_bytes < bobe_predict_workspace_bytes(n, d, M, mode)) {
         set_error("predict: workspace too small (%lld < %lld)", (long long)ws_bytes,

@@ -151,6 +151,7 @@ extern "C" int32_t bobe_predict_grad(void* stream_, int32_t kind, const double* 
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool want_mean = mode & BOBE_PREDICT_MEAN, want_var = mode & BOBE_PREDICT_VAR;
     const int standardised = (mode & BOBE_PREDICT_STANDARDISED) ? 1 : 0;
+    if (M == 0) return BOBE_OK;  // empty query set
     if (!X || !ls || !Xq || n <= 0 || d <= 0 || d > BOBE_MAX_DIM || M < 0 || !(want_mean || want_var) ||
         (want_mean && (!alpha || !mean_out || !dmean_out)) || (want_var && (!Linv || !LinvT || !var_out || !dvar_out))) {
         set_error("predict_grad: bad arguments");

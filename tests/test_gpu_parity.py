@@ -495,3 +495,27 @@ def test_incremental_update_refuses_a_stale_factor():
     gp.update(X[80:], y[80:])
     ref = O.OracleGP(X, y, kernel="rbf", noise=1e-6, lengthscales=np.array([0.3, 0.8]))
     assert mixed_err(gp.cholesky, ref.cholesky, float(np.abs(ref.cholesky).max())) < 1e-9
+
+
+def test_empty_and_ragged_inputs():
+    """Edge cases of the reference's tests (tests/test_gp.py:30-55,92-141): empty query sets, shape errors, a GP without
+    training points, query counts around every internal boundary (16 = matrix-vector path, 128 = tile, 74 tiles = row
+    split, 148 tiles = chunk)."""
+    from bobe_b200 import GP
+    ref, X, y, Xq, _, _, _ = make_case("M_matern_n300_d3")
+    gp = make_gp(ref)
+    m, v = gp.predict_mean_var_batched(np.zeros((0, 3)))
+    assert m.shape == (0,) and v.shape == (0,)
+    with pytest.raises(ValueError):
+        gp.predict_mean_batched(np.zeros((4, 2)))  # wrong number of columns
+    with pytest.raises(ValueError):
+        GP(X[:10], y[:9])  # BOBE/gp.py:286-291
+    rng = np.random.default_rng(4)
+    for M in (15, 16, 17, 128 * 73, 128 * 74 + 1, 148 * 128 + 3):
+        xq = rng.uniform(0, 1, (M, 3))
+        mean, var = gp.predict_mean_var_batched(xq)
+        sub = rng.choice(M, min(M, 300), replace=False)
+        assert mixed_err(mean[sub], ref.predict_mean_batched(xq[sub]), ref.y_std) < TOL_MEAN
+        assert mixed_err(var[sub], ref.predict_var_batched(xq[sub]), ref.y_std ** 2) < TOL_VAR
+        vo = gp.predict_var_batched(xq)  # variance-only call takes the same paths
+        assert np.array_equal(vo, var)
