@@ -99,7 +99,10 @@ class GP:
                  kernel_variance_bounds=[1e-4, 1e8], lengthscale_bounds=[0.01, 5], lengthscales=None,
                  kernel_variance=None, kernel_variance_prior=None, lengthscale_prior=None, tausq=None,
                  tausq_bounds=[1e-4, 1e4], param_names: List[str] = None, device=None):
-        self._device_arg = device
+        # The device is fixed at construction: torch's current device is THREAD-local (new threads start on device 0),
+        # and the lock-step optimisers / SurrogatePool call back into this object from worker threads.
+        self._device_arg = device if device is not None else (
+            torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None)
         self._setup_training_data(train_x, train_y)
         self.param_names = param_names if param_names is not None else ['x_' + str(i) for i in range(self.ndim)]
 
