@@ -8,6 +8,7 @@ its host-side bookkeeping exercised without a GPU, but any arithmetic raises unl
 """
 from __future__ import annotations
 
+import functools
 import logging
 from typing import List
 
@@ -42,9 +43,9 @@ def _to_dev(x, device) -> torch.Tensor:
 
 
 # ---- module-level kernel functions (BOBE/gp.py:80-168) -----------------------------------------------------
-def _kernel_call(kind, xa, xb, lengthscales, kernel_variance, noise, include_noise):
+def _kernel_call(kind, xa, xb, lengthscales, kernel_variance, noise, include_noise=True, device=None):
     as_t = _is_t(xa) or _is_t(xb)
-    dev = xa.device if _is_t(xa) and xa.is_cuda else (xb.device if _is_t(xb) and xb.is_cuda else _dev())
+    dev = xa.device if _is_t(xa) and xa.is_cuda else (xb.device if _is_t(xb) and xb.is_cuda else _dev(device))
     xa_d, xb_d = _to_dev(xa, dev), _to_dev(xb, dev)
     if xa_d.dim() != 2 or xb_d.dim() != 2:
         raise ValueError("kernel inputs must be 2D (n, d)")
@@ -107,7 +108,9 @@ class GP:
         self.param_names = param_names if param_names is not None else ['x_' + str(i) for i in range(self.ndim)]
 
         self.kernel_name = kernel if kernel == "rbf" else "matern"  # BOBE/gp.py:251-252
-        self.kernel = rbf_kernel if kernel == "rbf" else matern_kernel
+        # same call signature as the module-level kernels, but bound to this GP's device (worker threads of the
+        # lock-step optimisers would otherwise land on torch's thread-local default device)
+        self.kernel = functools.partial(_kernel_call, self.kernel_name, device=self._device_arg)
         self.lengthscales = (np.asarray(lengthscales, dtype=np.float64).reshape(-1) if lengthscales is not None
                              else np.ones(self.ndim))
         self.kernel_variance = float(kernel_variance) if kernel_variance is not None else 1.0
