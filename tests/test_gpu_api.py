@@ -194,3 +194,74 @@ def test_wipv_next_point(cls):  # the reference imports WIPV in its tests but ne
     xb, vb = acq.get_next_point(big, {"mc_samples": mc, "mc_points_size": 32}, rng=np.random.default_rng(3))
     pts_b = get_mc_points(mc, 32, rng=np.random.default_rng(3))
     assert any(np.array_equal(xb, p) for p in pts_b) and isinstance(vb, float)
+
+
+# ---- GPwithClassifier (SVM): transcribed from the reference's tests/test_clf_gp.py ---------------------------------------
+def generate_test_data_with_outliers(n_good=30, n_bad=20, d=2, seed=42):  # tests/test_clf_gp.py:20-38
+    rng = np.random.RandomState(seed)
+    X_good = rng.uniform(0.3, 0.7, size=(n_good, d))
+    y_good = -np.sum((X_good - 0.5) ** 2, axis=1, keepdims=True)
+    X_bad = rng.uniform(0, 1, size=(n_bad, d))
+    X_bad = np.where(X_bad < 0.5, X_bad * 0.4, 0.6 + X_bad * 0.4)
+    y_bad = -10 - np.sum((X_bad - 0.5) ** 2, axis=1, keepdims=True)
+    X, y = np.vstack([X_good, X_bad]), np.vstack([y_good, y_bad])
+    perm = rng.permutation(len(y))
+    return X[perm], y[perm]
+
+
+def test_clf_gp_initialization_svm():  # tests/test_clf_gp.py:41-70
+    from bobe_b200 import GPwithClassifier
+    X, y = generate_test_data_with_outliers(n_good=40, n_bad=30, d=3)
+    gp_clf = GPwithClassifier(train_x=X, train_y=y, clf_type='svm', clf_settings={'gamma': 'scale', 'C': 1e5},
+                              clf_use_size=50, clf_threshold=5.0, gp_threshold=10.0, noise=1e-6)
+    assert gp_clf.clf_type == 'svm' and gp_clf.clf_data_size == len(X) and gp_clf.npoints <= len(X)
+    assert gp_clf.use_clf and gp_clf.clf_metrics['n_support_vectors'] > 0
+    for other in ('nn', 'ellipsoid'):  # tests/test_clf_gp.py:73-130 -- flax classifiers are outside the hot path
+        with pytest.raises(NotImplementedError):
+            GPwithClassifier(train_x=X, train_y=y, clf_type=other)
+
+
+def test_clf_gp_predictions():  # tests/test_clf_gp.py:133-188
+    from bobe_b200 import GPwithClassifier
+    X, y = generate_test_data_with_outliers(n_good=40, n_bad=30, d=2)
+    gp_clf = GPwithClassifier(train_x=X, train_y=y, clf_type='svm', clf_use_size=50, clf_threshold=5.0, gp_threshold=10.0,
+                              probability_threshold=0.5, minus_inf=-1e5, noise=1e-6)
+    mean_good, var_good = gp_clf.predict_mean_single(np.array([0.5, 0.5])), gp_clf.predict_var_single(np.array([0.5, 0.5]))
+    mean_bad, var_bad = gp_clf.predict_mean_single(np.array([0.05, 0.05])), gp_clf.predict_var_single(np.array([0.05, 0.05]))
+    assert gp_clf.use_clf and mean_bad < mean_good and mean_bad == -1e5 and var_bad == 1e-12 and var_good > 0
+    pts = np.array([[0.5, 0.5], [0.05, 0.05], [0.6, 0.4]])
+    means, vars_ = gp_clf.predict_mean_batched(pts), gp_clf.predict_var_batched(pts)
+    assert means.shape == (3,) and vars_.shape == (3,) and means[1] == -1e5 and means[0] == mean_good
+
+
+def test_clf_gp_update_training_random_point_state_copy():  # tests/test_clf_gp.py:191-372
+    from bobe_b200 import GPwithClassifier
+    X, y = generate_test_data_with_outliers(n_good=25, n_bad=15, d=2)
+    gp_clf = GPwithClassifier(train_x=X, train_y=y, clf_type='svm', clf_use_size=30, clf_threshold=5.0, gp_threshold=10.0,
+                              noise=1e-6)
+    n_clf, n_gp = gp_clf.clf_data_size, gp_clf.npoints
+    new_X = np.array([[0.55, 0.45], [0.48, 0.52]])
+    gp_clf.update(new_X, -np.sum((new_X - 0.5) ** 2, axis=1, keepdims=True))
+    assert gp_clf.clf_data_size == n_clf + 2 and gp_clf.npoints >= n_gp
+    # classifier switches on once enough data has arrived (:229-263)
+    Xs, ys = generate_test_data_with_outliers(n_good=15, n_bad=10, d=2)
+    g2 = GPwithClassifier(train_x=Xs, train_y=ys, clf_type='svm', clf_use_size=50, clf_threshold=5.0, noise=1e-6)
+    assert not g2.use_clf
+    Xa, ya = generate_test_data_with_outliers(n_good=25, n_bad=15, d=2, seed=7)
+    g2.update(Xa, ya)
+    g2.train_classifier()
+    assert g2.clf_data_size >= g2.clf_use_size and g2.use_clf and g2.clf_params is not None
+    # random points come from the good training points (:266-296)
+    rng = np.random.default_rng(42)
+    pts = np.array([gp_clf.get_random_point(rng=rng) for _ in range(5)])
+    assert pts.shape == (5, 2) and np.all(pts >= 0) and np.all(pts <= 1)
+    assert all(np.any(np.all(np.isclose(gp_clf.train_x_clf, p), axis=1)) for p in pts)
+    # state round trip and independent copy (:299-372)
+    g3 = GPwithClassifier.from_state_dict(gp_clf.state_dict())
+    assert g3.clf_type == gp_clf.clf_type and g3.clf_data_size == gp_clf.clf_data_size and g3.use_clf == gp_clf.use_clf
+    assert np.allclose(g3.train_x_clf, gp_clf.train_x_clf)
+    p = np.array([0.5, 0.5])
+    assert np.isclose(g3.predict_mean_single(p), gp_clf.predict_mean_single(p), rtol=1e-5)
+    g4 = gp_clf.copy()
+    g4.update(np.array([[0.6, 0.4]]), np.array([[-0.02]]))
+    assert g4.clf_data_size == gp_clf.clf_data_size + 1
