@@ -265,3 +265,32 @@ def test_clf_gp_update_training_random_point_state_copy():  # tests/test_clf_gp.
     g4 = gp_clf.copy()
     g4.update(np.array([[0.6, 0.4]]), np.array([[-0.02]]))
     assert g4.clf_data_size == gp_clf.clf_data_size + 1
+
+
+@pytest.mark.parametrize("acq_name", ["ei", "wipv"])
+def test_mini_bo_loop_2d(acq_name):
+    """The pieces under bo.py working together (cf. the reference's tests/test_bo_2d.py, whose orchestrator is out of
+    scope): multi-restart fit -> update_hyperparams -> acquisition -> update, a few iterations on a 2-D Gaussian
+    log-likelihood.  EI must move the best value up; WIPV must shrink the integrated posterior variance."""
+    from bobe_b200 import GP, ACQUISITIONS
+    rng = np.random.default_rng(0)
+    f = lambda X: -0.5 * np.sum(((X - np.array([0.6, 0.4])) / 0.15) ** 2, axis=1, keepdims=True)
+    X = rng.uniform(0, 1, (12, 2))
+    gp = GP(X, f(X), kernel="rbf", noise=1e-6, lengthscales=np.array([0.3, 0.3]))
+    acq = ACQUISITIONS[acq_name]()
+    mc = {'x': rng.uniform(0, 1, (512, 2))}
+    best0 = float((gp.train_y * gp.y_std + gp.y_mean).max())
+    var0 = float(np.mean(gp.predict_var_batched(mc['x'])))
+    for it in range(6):
+        x0 = np.vstack([np.log(gp.get_hyperparams()), rng.uniform(gp.hyperparam_bounds[0], gp.hyperparam_bounds[1], (3, 3))])
+        res = gp.fit(x0, maxiter=30)
+        gp.update_hyperparams(res['params'])
+        kw = {'zeta': 0.01} if acq_name == "ei" else {'mc_samples': mc, 'mc_points_size': 128}
+        x_next, _ = acq.get_next_point(gp, kw, maxiter=50, n_restarts=4, verbose=False, rng=rng)
+        x_next = np.atleast_2d(x_next)
+        gp.update(x_next, f(x_next))
+    assert gp.npoints >= 12 + 4 and np.all(np.isfinite(gp.cholesky))
+    if acq_name == "ei":
+        assert float((gp.train_y * gp.y_std + gp.y_mean).max()) > best0
+    else:
+        assert float(np.mean(gp.predict_var_batched(mc['x']))) < var0
