@@ -41,6 +41,9 @@ SIGNATURES = {
     "bobe_fantasy_var_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64]),
     "bobe_fantasy_var": (_i32, [_vp, _i32, _vp, _i64, _i64, _vp, _f64, _f64, _vp, _f64, _vp, _i64, _vp, _i64, _i32,
                                 _vp, _vp, _i64]),
+    "bobe_fantasy_var_grad_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64]),
+    "bobe_fantasy_var_grad": (_i32, [_vp, _i32, _vp, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _f64, _vp, _i64, _vp, _i64,
+                                     _i32, _vp, _vp, _vp, _i64]),
     "bobe_chol_append": (_i32, [_vp, _vp, _i64, _i64, _vp, _f64, _vp, _i64]),
     "bobe_acq_ei": (_i32, [_vp, _i32, _vp, _vp, _i64, _f64, _f64, _vp]),
     "bobe_svm_mask_workspace_bytes": (_i64, [_i64, _i64]),

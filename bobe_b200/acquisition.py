@@ -2,8 +2,9 @@
 
 Same class names, ``fun`` / ``get_next_point`` / ``get_next_batch`` signatures and return conventions as the
 reference (BOBE/acquisition.py:79-489).  Differences, all forced by the absence of JAX autodiff here:
-  * gradients for the polish step are central finite differences evaluated in ONE batched device call per
-    optimiser step (all restarts x (2d+1) points), instead of ``jax.value_and_grad``;
+  * gradients for the polish step are ANALYTIC (``bobe_predict_grad`` for EI / LogEI, ``bobe_fantasy_var_grad`` for
+    WIPV / WIPStd), evaluated in ONE batched device call per optimiser step for all restarts, instead of
+    ``jax.value_and_grad``; batched central differences remain the default for user-defined acquisitions;
   * the candidate sweep of WIPV/WIPStd (``lax.map`` over MC points, :390-394) is one fused device call that
     shares V = L^-1 K(X, MC) between all candidates.
 """
@@ -215,6 +216,10 @@ class WeightedIntegratedPosteriorBase(AcquisitionFunction):
     def fun(self, x, gp, mc_points=None, k_train_mc=None):
         return self.fun_batched(np.atleast_2d(np.asarray(x, dtype=np.float64)), gp, mc_points=mc_points)[0]
 
+    def value_and_grad_batched(self, x, gp, mc_points=None, k_train_mc=None):
+        """``jax.value_and_grad(self.fun)`` of BOBE/optim.py:118,309 at (R, d) points, analytically on the device."""
+        return gp.fantasy_acquisition_value_and_grad(mc_points, np.atleast_2d(np.asarray(x, dtype=np.float64)), self._std)
+
     def get_next_point(self, gp, acq_kwargs, maxiter: int = 100, n_restarts: int = 1, verbose: bool = True,
                        early_stop_patience: int = 25, rng=None):
         mc_samples = acq_kwargs.get('mc_samples')
@@ -228,7 +233,8 @@ class WeightedIntegratedPosteriorBase(AcquisitionFunction):
         if gp.train_x.shape[0] > 500:  # BOBE/acquisition.py:400-401
             return x0_acq, acq_val_min
         return self._optimize(lambda xs: self.fun_batched(xs, gp, mc_points=mc_points), x0_acq, gp, maxiter,
-                              n_restarts, verbose)
+                              n_restarts, verbose,
+                              vg_batched=lambda xs: self.value_and_grad_batched(xs, gp, mc_points=mc_points))
 
 
 class WIPV(WeightedIntegratedPosteriorBase):

@@ -231,3 +231,312 @@ extern "C" int32_t bobe_predict_grad(void* stream_, int32_t kind, const double* 
     }
     return BOBE_OK;
 }
+
+// ---- gradient of the fantasy-variance acquisitions with respect to the candidate point ---------------------------
+// WIPV / WIPStd (BOBE/acquisition.py:438-440,463-465) are mean_j phi(s_j(x)) with
+//   v = Linv k(X,x), delta2 = k** - v.v, V_j = Linv k(X,mc_j), t_j = k(x,mc_j) - v.V_j, s_j = k** - |V_j|^2 - t_j^2/delta2.
+// jax.value_and_grad of that in x (the n <= 500 polish, BOBE/acquisition.py:400-412 through BOBE/optim.py:118,309):
+//   ds_j/dx = -2 t_j t_j'/delta2 + t_j^2 delta2'/delta2^2,
+//   t_j' = dk(x,mc_j)/dx - sum_i dk(x,X_i)/dx (K^-1 k(X,mc_j))_i,    delta2' = -2 sum_i (K^-1 k(X,x))_i dk(x,X_i)/dx.
+// With c_j = phi'(s_j) (0 where the NaN / 1e-12 floor of BOBE/gp.py:574-575 is active), a_j = -2 c_j t_j/delta2,
+// b = sum_j c_j t_j^2/delta2^2, z = sum_j a_j V_j:
+//   n_mc * d out/dx = sum_j a_j dk(x,mc_j)/dx + sum_i e_i dk(x,X_i)/dx,    e = -Linv^T (z + 2 b v),
+// i.e. per MC chunk one extra skinny GEMM (Z += A V^T) beside the products bobe_fantasy_var already does, then ONE
+// triangular product for all candidates and the two "coefficient x G" reductions of bobe_predict_grad.
+namespace bobe {
+namespace {
+
+constexpr int64_t FG_MCCHUNK = 16384;
+
+// one warp per row: out[r] = c0 - sum_k M[r][k]^2
+__global__ void __launch_bounds__(256) fg_row_sumsq_kernel(const double* __restrict__ Mtx, int64_t ld, int64_t rows,
+                                                           int64_t cols, double c0, double* __restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const double* m = Mtx + r * ld;
+    double s = 0.0;
+    for (int64_t k = lane; k < cols; k += 32) s = fma(m[k], m[k], s);
+    s = warp_sum(s);
+    if (lane == 0) out[r] = c0 - s;
+}
+
+__device__ __forceinline__ double block_sum_256(double v, double* red) {  // fixed order; result valid in thread 0
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < 8; ++w) t += red[w];
+    return t;
+}
+
+// One CTA per candidate c, over the MC points of one chunk:
+//   value accumulation (as fantasy_combine_kernel), A[c][j] = a_j, Cmc[c][j] = a_j G(x_c, mc_j), bacc[c] += b.
+template <int KIND>
+__global__ void __launch_bounds__(256) fantasy_grad_coef_kernel(
+    const double* __restrict__ base, const double* __restrict__ kc, const double* __restrict__ G, int64_t ldg,
+    const double* __restrict__ delta2, int64_t nj, int64_t nj_pad, double scale, int reduce,
+    const double* __restrict__ Xcand, const double* __restrict__ xms, int64_t ldx, int d, const double* __restrict__ ls,
+    double kv, double* __restrict__ A, double* __restrict__ Cmc, double* __restrict__ acc, double* __restrict__ bacc) {
+    __shared__ double red[8];
+    __shared__ double xc[BOBE_MAX_DIM];
+    const int64_t c = blockIdx.x;
+    for (int k = threadIdx.x; k < d; k += 256) xc[k] = Xcand[c * d + k] / ls[k];
+    __syncthreads();
+    double d2 = delta2[c];
+    if (d2 < 0.0) d2 = nan("");  // sqrt of a negative pivot in fast_update_cholesky (BOBE/gp.py:187)
+    double s_val = 0.0, s_b = 0.0;
+    for (int64_t j = threadIdx.x; j < nj_pad; j += 256) {
+        double a = 0.0, cm = 0.0;
+        if (j < nj) {
+            const double kcj = kc[c * ldg + j];
+            const double t = kcj - G[c * ldg + j];
+            double s = base[j] - t * t / d2;
+            const bool floored = !(s >= SAFE_FLOOR);  // NaN or below the floor (BOBE/gp.py:574-575): zero gradient
+            if (floored) s = SAFE_FLOOR;
+            const double val = s * scale;
+            double cj;
+            if (reduce == BOBE_REDUCE_MEAN_SQRT) {
+                const double sq = sqrt(val);
+                s_val += sq;
+                cj = scale / (2.0 * sq);
+            } else {
+                s_val += val;
+                cj = scale;
+            }
+            if (!floored) {
+                a = -2.0 * cj * t / d2;
+                s_b += cj * t * t / (d2 * d2);
+                double Gk;
+                if (KIND == BOBE_KERNEL_RBF) {
+                    Gk = kcj;
+                } else {
+                    double qq = 0.0;
+                    for (int k = 0; k < d; ++k) {
+                        const double df = xc[k] - xms[(int64_t)k * ldx + j];
+                        qq = fma(df, df, qq);
+                    }
+                    const bool clamped = qq < 1e-30;
+                    const double r = sqrt_pos(clamped ? 1e-30 : qq);
+                    Gk = clamped ? 0.0 : kv * (5.0 / 3.0) * (1.0 + SQRT5 * r) * exp_nonpos(-SQRT5 * r);
+                }
+                cm = a * Gk;
+            }
+        }
+        A[c * ldg + j] = a;
+        Cmc[c * ldg + j] = cm;
+    }
+    const double tv = block_sum_256(s_val, red);
+    const double tb = block_sum_256(s_b, red);
+    if (threadIdx.x == 0) {  // chunks arrive in stream order: deterministic
+        acc[c] += tv;
+        bacc[c] += tb;
+    }
+}
+
+// Y[c][k] = Z[c][k] + 2 b_c VcT[c][k]
+__global__ void __launch_bounds__(256) fantasy_grad_y_kernel(const double* __restrict__ Z, const double* __restrict__ VcT,
+                                                             const double* __restrict__ bacc, int64_t npad,
+                                                             double* __restrict__ Y) {
+    const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x, c = blockIdx.y;
+    if (k < npad) Y[c * npad + k] = fma(2.0 * bacc[c], VcT[c * npad + k], Z[c * npad + k]);
+}
+
+__global__ void __launch_bounds__(256) fantasy_grad_combine_kernel(const double* __restrict__ Xcand, int64_t C, int d,
+                                                                   const double* __restrict__ ls,
+                                                                   const double* __restrict__ Pmc,
+                                                                   const double* __restrict__ Pe, int64_t ldp,
+                                                                   const double* __restrict__ acc, double inv_nmc,
+                                                                   double* __restrict__ out, double* __restrict__ dout) {
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= C * d) return;
+    const int64_t c = idx / d;
+    const int k = (int)(idx - c * d);
+    const double l = ls[k], xk = Xcand[c * d + k] / l;
+    const double gm = xk * Pmc[c * ldp + d] - Pmc[c * ldp + k];
+    const double ge = xk * Pe[c * ldp + d] - Pe[c * ldp + k];
+    dout[idx] = -(gm + ge) / l * inv_nmc;
+    if (k == 0) out[c] = acc[c] * inv_nmc;
+}
+
+struct FGradLayout {
+    double *xs, *xms, *Kmc, *VT, *V, *base, *Kc, *VcT, *delta2, *G, *kc, *A, *Cmc, *acc, *bacc, *Z, *Y, *E, *Ce, *Pmc, *Pe;
+    int64_t chunk, cpad, dpad, bytes;
+};
+FGradLayout fgrad_layout(void* ws, int64_t n, int64_t d, int64_t n_mc, int64_t C) {
+    const int64_t npad = npad_of(n);
+    FGradLayout l{};
+    l.chunk = round_up(n_mc < FG_MCCHUNK ? n_mc : FG_MCCHUNK, 64);
+    l.cpad = round_up(C, 64);
+    l.dpad = round_up(d + 1, 2);
+    double* b = ws ? align256(ws) : nullptr;
+    int64_t off = 0;
+    auto take = [&](int64_t doubles) {
+        double* p = b ? b + off : nullptr;
+        off += round_up(doubles, 32);
+        return p;
+    };
+    l.xs = take(l.dpad * npad);
+    l.xms = take(l.dpad * l.chunk);
+    l.Kmc = take(l.chunk * npad);
+    l.VT = take(l.chunk * npad);
+    l.V = take(npad * l.chunk);
+    l.base = take(l.chunk);
+    l.Kc = take(l.cpad * npad);
+    l.VcT = take(l.cpad * npad);
+    l.delta2 = take(l.cpad);
+    l.G = take(l.cpad * l.chunk);
+    l.kc = take(l.cpad * l.chunk);
+    // zero-initialised block (one memset): A, Cmc, acc, bacc, Z, Pmc
+    l.A = take(l.cpad * l.chunk);
+    l.Cmc = take(l.cpad * l.chunk);
+    l.acc = take(l.cpad);
+    l.bacc = take(l.cpad);
+    l.Z = take(l.cpad * npad);
+    l.Pmc = take(l.cpad * l.dpad);
+    l.Y = take(l.cpad * npad);
+    l.E = take(l.cpad * npad);
+    l.Ce = take(l.cpad * npad);
+    l.Pe = take(l.cpad * l.dpad);
+    l.bytes = off * 8 + 256;
+    return l;
+}
+
+}  // namespace
+}  // namespace bobe
+
+extern "C" int64_t bobe_fantasy_var_grad_workspace_bytes(int64_t n, int64_t d, int64_t n_mc, int64_t C) {
+    if (n <= 0 || d <= 0 || n_mc <= 0 || C <= 0) return 256;
+    return fgrad_layout(nullptr, n, d, n_mc, C).bytes;
+}
+
+extern "C" int32_t bobe_fantasy_var_grad(void* stream_, int32_t kind, const double* X, int64_t n, int64_t d,
+                                         const double* ls, double kv, double noise, const double* Linv,
+                                         const double* LinvT, double y_std, const double* Xmc, int64_t n_mc,
+                                         const double* Xcand, int64_t C, int32_t reduce, double* out, double* dout,
+                                         void* ws, int64_t ws_bytes) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (C == 0) return BOBE_OK;  // no candidates
+    if (!X || !ls || !Linv || !LinvT || !Xmc || !Xcand || !out || !dout || n <= 0 || d <= 0 || d > BOBE_MAX_DIM ||
+        n_mc <= 0 || C < 0 || (reduce != BOBE_REDUCE_MEAN && reduce != BOBE_REDUCE_MEAN_SQRT) ||
+        (kind != BOBE_KERNEL_RBF && kind != BOBE_KERNEL_MATERN52)) {
+        set_error("fantasy_var_grad: bad arguments");
+        return BOBE_E_ARG;
+    }
+    if (!ws || ws_bytes < bobe_fantasy_var_grad_workspace_bytes(n, d, n_mc, C)) {
+        set_error("fantasy_var_grad: workspace too small (%lld < %lld)", (long long)ws_bytes,
+                  (long long)bobe_fantasy_var_grad_workspace_bytes(n, d, n_mc, C));
+        return BOBE_E_WORKSPACE;
+    }
+    if ((((uintptr_t)Linv) | ((uintptr_t)LinvT)) & 15) {
+        set_error("fantasy_var_grad: Linv / LinvT must be 16-byte aligned");
+        return BOBE_E_ARG;
+    }
+    const int64_t npad = npad_of(n);
+    const double kk = kv + noise;  // kernel_diag(..., include_noise=True), BOBE/gp.py:561,570
+    FGradLayout l = fgrad_layout(ws, n, d, n_mc, C);
+    if (int32_t rc = launch_prescale(stream, X, n, d, ls, 0, l.xs, npad, 0, 1)) return rc;
+    ones_row_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, stream>>>(l.xs, n, npad, d, l.dpad);
+    if (int32_t rc = check_launch("ones_row_kernel")) return rc;
+    // A .. Pmc are contiguous in the layout: the accumulators start from zero, pad rows / columns stay zero
+    if (cudaMemsetAsync(l.A, 0, (size_t)((l.Pmc + round_up(l.cpad * l.dpad, 32)) - l.A) * 8, stream) != cudaSuccess) {
+        set_error("fantasy_var_grad: memset failed");
+        return BOBE_E_CUDA;
+    }
+    auto kstar_panel = [&](const double* pts, int64_t rows, int64_t rows_pad, double* Kout) {
+        KmatArgs a{};
+        a.xa = pts; a.xb = X; a.ls = ls; a.kv = kv; a.noise = noise; a.out = Kout;
+        a.xbs = l.xs; a.xbs_ld = npad;
+        a.n1 = rows; a.n2 = n; a.d = d; a.ldo = npad; a.rows_pad = rows_pad; a.cols_pad = npad;
+        a.store_rows = rows_pad; a.store_cols = npad; a.vec_ok = 1;
+        return launch_kmat(stream, kind, a, 1);
+    };
+    auto apply_linv = [&](const double* Kin, int64_t rows_pad, double* VTout, double* Vout, int64_t ldv) {
+        GemmArgs g{};  // V = Linv Kin^T; VTout[j][i] (transposed store) and optionally Vout[i][j]
+        g.A = Linv; g.Bt = Kin; g.C = Vout; g.Ct = VTout; g.lda = g.ldb = g.ldct = npad; g.ldc = ldv;
+        g.M = (int)npad; g.N = (int)rows_pad; g.K = (int)npad; g.alpha = 1.0; g.flags = GEMM_A_LOWER;
+        return launch_gemm_nt(stream, g, 1);
+    };
+    auto rows_sumsq = [&](const double* Vin, int64_t rows, double* o) {
+        fg_row_sumsq_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(Vin, npad, rows, npad, kk, o);
+        return check_launch("fg_row_sumsq_kernel");
+    };
+    if (int32_t rc = kstar_panel(Xcand, C, l.cpad, l.Kc)) return rc;
+    if (int32_t rc = apply_linv(l.Kc, l.cpad, l.VcT, nullptr, 0)) return rc;
+    if (int32_t rc = rows_sumsq(l.VcT, C, l.delta2)) return rc;
+    for (int64_t j0 = 0; j0 < n_mc; j0 += l.chunk) {
+        const int64_t nj = (n_mc - j0 < l.chunk) ? n_mc - j0 : l.chunk;
+        const int64_t nj_pad = round_up(nj, 64);
+        const double* xmc = Xmc + j0 * d;
+        if (int32_t rc = kstar_panel(xmc, nj, nj_pad, l.Kmc)) return rc;
+        if (int32_t rc = apply_linv(l.Kmc, nj_pad, l.VT, l.V, l.chunk)) return rc;
+        if (int32_t rc = rows_sumsq(l.VT, nj, l.base)) return rc;
+        {  // G[c][j] = sum_i VcT[c][i] VT[j][i]
+            GemmArgs g{};
+            g.A = l.VcT; g.Bt = l.VT; g.C = l.G; g.lda = g.ldb = npad; g.ldc = l.chunk;
+            g.M = (int)l.cpad; g.N = (int)nj_pad; g.K = (int)npad; g.alpha = 1.0;
+            if (int32_t rc = launch_gemm_nt(stream, g, 1)) return rc;
+        }
+        {  // kc[c][j] = k(x_c, mc_j)   (BOBE/gp.py:565-568)
+            KmatArgs a{};
+            a.xa = Xcand; a.xb = xmc; a.ls = ls; a.kv = kv; a.noise = noise; a.out = l.kc;
+            a.n1 = C; a.n2 = nj; a.d = d; a.ldo = l.chunk; a.rows_pad = l.cpad; a.cols_pad = nj_pad;
+            a.store_rows = l.cpad; a.store_cols = nj_pad; a.vec_ok = 1;
+            if (int32_t rc = launch_kmat(stream, kind, a, 1)) return rc;
+        }
+        if (int32_t rc = launch_prescale(stream, xmc, nj, d, ls, 0, l.xms, l.chunk, 0, 1)) return rc;
+        ones_row_kernel<<<(unsigned)((l.chunk + 255) / 256), 256, 0, stream>>>(l.xms, nj, l.chunk, d, l.dpad);
+        if (int32_t rc = check_launch("ones_row_kernel")) return rc;
+        if (kind == BOBE_KERNEL_RBF)
+            fantasy_grad_coef_kernel<BOBE_KERNEL_RBF><<<(unsigned)C, 256, 0, stream>>>(
+                l.base, l.kc, l.G, l.chunk, l.delta2, nj, nj_pad, y_std * y_std, reduce, Xcand, l.xms, l.chunk, (int)d, ls, kv,
+                l.A, l.Cmc, l.acc, l.bacc);
+        else
+            fantasy_grad_coef_kernel<BOBE_KERNEL_MATERN52><<<(unsigned)C, 256, 0, stream>>>(
+                l.base, l.kc, l.G, l.chunk, l.delta2, nj, nj_pad, y_std * y_std, reduce, Xcand, l.xms, l.chunk, (int)d, ls, kv,
+                l.A, l.Cmc, l.acc, l.bacc);
+        if (int32_t rc = check_launch("fantasy_grad_coef_kernel")) return rc;
+        {  // Z[c][i] += sum_j A[c][j] V[i][j]
+            GemmArgs g{};
+            g.A = l.A; g.Bt = l.V; g.C = l.Z; g.D = l.Z; g.lda = g.ldb = l.chunk; g.ldc = g.ldd = npad;
+            g.M = (int)l.cpad; g.N = (int)npad; g.K = (int)nj_pad; g.alpha = 1.0;
+            if (int32_t rc = launch_gemm_nt(stream, g, 1)) return rc;
+        }
+        {  // Pmc[c][k] += sum_j Cmc[c][j] xms_ext[k][j]
+            GemmArgs g{};
+            g.A = l.Cmc; g.Bt = l.xms; g.C = l.Pmc; g.D = l.Pmc; g.lda = g.ldb = l.chunk; g.ldc = g.ldd = l.dpad;
+            g.M = (int)l.cpad; g.N = (int)l.dpad; g.K = (int)nj_pad; g.alpha = 1.0;
+            if (int32_t rc = launch_gemm_nt(stream, g, 1)) return rc;
+        }
+    }
+    fantasy_grad_y_kernel<<<dim3((unsigned)((npad + 255) / 256), (unsigned)l.cpad), 256, 0, stream>>>(l.Z, l.VcT, l.bacc, npad,
+                                                                                                    l.Y);
+    if (int32_t rc = check_launch("fantasy_grad_y_kernel")) return rc;
+    {  // E[c][i] = -sum_k LinvT[i][k] Y[c][k]
+        GemmArgs g{};
+        g.A = LinvT; g.Bt = l.Y; g.C = nullptr; g.Ct = l.E; g.lda = g.ldb = g.ldct = npad;
+        g.M = (int)npad; g.N = (int)l.cpad; g.K = (int)npad; g.alpha = -1.0; g.flags = GEMM_A_UPPER;
+        if (int32_t rc = launch_gemm_nt(stream, g, 1)) return rc;
+    }
+    {  // Ce[c][i] = E[c][i] G(x_c, X_i)
+        dim3 grid((unsigned)((npad + 255) / 256), (unsigned)l.cpad);
+        if (kind == BOBE_KERNEL_RBF)
+            grad_coef_kernel<BOBE_KERNEL_RBF><<<grid, 256, 0, stream>>>(Xcand, C, l.cpad, l.xs, n, npad, (int)d, ls, kv, nullptr,
+                                                                       l.E, nullptr, l.Ce);
+        else
+            grad_coef_kernel<BOBE_KERNEL_MATERN52><<<grid, 256, 0, stream>>>(Xcand, C, l.cpad, l.xs, n, npad, (int)d, ls, kv,
+                                                                            nullptr, l.E, nullptr, l.Ce);
+        if (int32_t rc = check_launch("grad_coef_kernel")) return rc;
+    }
+    {  // Pe[c][k] = sum_i Ce[c][i] xs_ext[k][i]
+        GemmArgs g{};
+        g.A = l.Ce; g.Bt = l.xs; g.C = l.Pe; g.lda = g.ldb = npad; g.ldc = l.dpad;
+        g.M = (int)l.cpad; g.N = (int)l.dpad; g.K = (int)npad; g.alpha = 1.0;
+        if (int32_t rc = launch_gemm_nt(stream, g, 1)) return rc;
+    }
+    fantasy_grad_combine_kernel<<<(unsigned)((C * d + 255) / 256), 256, 0, stream>>>(Xcand, C, (int)d, ls, l.Pmc, l.Pe, l.dpad,
+                                                                                   l.acc, 1.0 / (double)n_mc, out, dout);
+    return check_launch("fantasy_grad_combine_kernel");
+}

@@ -601,6 +601,23 @@ class GP:
                               "mean_sqrt" if std else "mean")
         return out if as_t else out.cpu().numpy()
 
+    def fantasy_acquisition_value_and_grad(self, mc_points, candidates, std=False):
+        """WIPV / WIPStd at the (C, d) candidates and their (C, d) gradients with respect to the candidate point:
+        ``jax.value_and_grad(acq.fun)`` as the n <= 500 polish takes it (BOBE/acquisition.py:400-412 through
+        BOBE/optim.py:118,309), analytically in one ``bobe_fantasy_var_grad`` call."""
+        as_t = _is_t(mc_points) or _is_t(candidates)
+        dev = self.device
+        cand = _to_dev(candidates, dev)
+        if cand.dim() == 1:
+            cand = cand[None, :]
+        if cand.shape[1] != self.ndim:
+            raise ValueError(f"candidates must have {self.ndim} columns")
+        linvT = self._ensure_linvT()
+        val, grad = ops.fantasy_var_grad(self.kernel_name, self._X_dev, self._ls_dev, float(self.kernel_variance),
+                                         float(self.noise), self._Linv_dev, linvT, float(self.y_std),
+                                         _to_dev(mc_points, dev), cand, "mean_sqrt" if std else "mean")
+        return (val, grad) if as_t else (val.cpu().numpy(), grad.cpu().numpy())
+
     def get_random_point(self, rng=None, nstd=None):
         """BOBE/gp.py:578-585."""
         rng = rng if rng is not None else np.random.default_rng()

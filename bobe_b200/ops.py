@@ -223,6 +223,27 @@ def fantasy_var(kind: str, X, ls, kv: float, noise: float, Linv, y_std: float, X
     return out
 
 
+def fantasy_var_grad(kind: str, X, ls, kv: float, noise: float, Linv, LinvT, y_std: float, Xmc, Xcand,
+                     reduce: str = "mean"):
+    """WIPV ("mean") / WIPStd ("mean_sqrt") at the candidates and their gradients w.r.t. the candidate point --
+    value_and_grad of BOBE/acquisition.py:438-440,463-465 as taken at BOBE/acquisition.py:400-412.  -> ((C,), (C, d))."""
+    X, ls, Xmc, Xcand = _chk(X, "X"), _chk(ls, "ls"), _chk(Xmc, "Xmc"), _chk(Xcand, "Xcand")
+    Linv, LinvT = _chk(Linv, "Linv"), _chk(LinvT, "LinvT")
+    n, d = X.shape
+    n_mc, C = Xmc.shape[0], Xcand.shape[0]
+    red = {"mean": _lib.REDUCE_MEAN, "mean_sqrt": _lib.REDUCE_MEAN_SQRT}[reduce]
+    dev = X.device
+    out = torch.empty(C, dtype=torch.float64, device=dev)
+    dout = torch.empty((C, d), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.bobe_fantasy_var_grad_workspace_bytes(n, d, n_mc, C), dev)
+        check(lib.bobe_fantasy_var_grad(_stream(), KIND[kind], X.data_ptr(), n, d, ls.data_ptr(), float(kv), float(noise),
+                                        Linv.data_ptr(), LinvT.data_ptr(), float(y_std), Xmc.data_ptr(), n_mc,
+                                        Xcand.data_ptr(), C, red, out.data_ptr(), dout.data_ptr(), ws.data_ptr(),
+                                        ws.numel()), "bobe_fantasy_var_grad")
+    return out, dout
+
+
 def chol_append(L, k, k_self: float) -> torch.Tensor:
     """fast_update_cholesky -- BOBE/gp.py:181-197."""
     L, k = _chk(L, "L"), _chk(k, "k").reshape(-1)

@@ -127,6 +127,18 @@ int32_t bobe_fantasy_var(void* stream, int32_t kind, const double* X, int64_t n,
                          int64_t n_mc, const double* Xcand, int64_t C, int32_t reduce, double* out, void* ws,
                          int64_t ws_bytes);
 
+/* WIPV / WIPStd values AND their gradients with respect to each candidate point
+ * -- jax.value_and_grad of WIPV.fun / WIPStd.fun (BOBE/acquisition.py:438-440,463-465, i.e. of GP.fantasy_var
+ *    BOBE/gp.py:552-576 in new_x) as the n <= 500 polish step takes it: BOBE/acquisition.py:400-412 through
+ *    BOBE/optim.py:118,309.  reduce must be BOBE_REDUCE_MEAN or BOBE_REDUCE_MEAN_SQRT; out is (C), dout is (C, d).
+ *    The gradient of an MC term is zero where the NaN / 1e-12 floor of BOBE/gp.py:574-575 is active.
+ *    LinvT from bobe_linv_transpose. */
+int64_t bobe_fantasy_var_grad_workspace_bytes(int64_t n, int64_t d, int64_t n_mc, int64_t C);
+int32_t bobe_fantasy_var_grad(void* stream, int32_t kind, const double* X, int64_t n, int64_t d, const double* ls,
+                              double kv, double noise, const double* Linv, const double* LinvT, double y_std,
+                              const double* Xmc, int64_t n_mc, const double* Xcand, int64_t C, int32_t reduce,
+                              double* out, double* dout, void* ws, int64_t ws_bytes);
+
 /* rank-1 append to a lower Cholesky factor -- fast_update_cholesky BOBE/gp.py:181-197.
  * L (n, ldl) lower; k (n); L_out (n+1, ldo) fully written (zero upper). */
 int32_t bobe_chol_append(void* stream, const double* L, int64_t n, int64_t ldl, const double* k, double k_self,

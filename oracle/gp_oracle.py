@@ -571,6 +571,67 @@ def wipv_values(gp: OracleGP, cand_x, mc_points, std=False):
     return np.mean(np.sqrt(var) if std else var, axis=1)
 
 
+def _kernel_and_gradcoef(gp: OracleGP, xa, xb):
+    """k(xa, xb) and G with dk(x, p)/dx = -G (x - p) / l^2 (G = k for RBF; Matern-5/2: kv 5/3 (1 + sqrt5 r) exp(-sqrt5 r),
+    0 where the 1e-30 clamp of BOBE/gp.py:162 is active)."""
+    ls, kv = gp.lengthscales, gp.kernel_variance
+    q = dist_sq(xa / ls, xb / ls)
+    if gp.kernel_name == "rbf":
+        k = kv * np.exp(-0.5 * q)
+        return k, k
+    clamped = q < 1e-30
+    r = np.sqrt(np.where(clamped, 1e-30, q))
+    e = np.exp(-SQRT5 * r)
+    return kv * (1.0 + r * (SQRT5 + r * 5.0 / 3.0)) * e, np.where(clamped, 0.0, kv * (5.0 / 3.0) * (1.0 + SQRT5 * r) * e)
+
+
+def wipv_values_and_grad(gp: OracleGP, cand_x, mc_points, std=False):
+    """WIPV / WIPStd (BOBE/acquisition.py:438-440,463-465) and their gradient with respect to the candidate point:
+    what ``jax.value_and_grad(self.fun)`` yields in the n <= 500 polish of BOBE/acquisition.py:400-412 (through
+    BOBE/optim.py:118,309), i.e. the reverse-mode derivative of GP.fantasy_var (BOBE/gp.py:552-576) in ``new_x``.
+
+    With v = L^-1 k(X,x), delta2 = k** - v.v, V_j = L^-1 k(X,mc_j), t_j = k(x,mc_j) - v.V_j (the posterior covariance
+    of x and mc_j) and s_j = k** - |V_j|^2 - t_j^2 / delta2:
+        ds_j/dx = -2 t_j t_j'/delta2 + t_j^2 delta2'/delta2^2,
+        t_j'    = dk(x,mc_j)/dx - sum_i dk(x,X_i)/dx (K^-1 k(X,mc_j))_i,     delta2' = -2 sum_i (K^-1 k(X,x))_i dk(x,X_i)/dx,
+    zero where the NaN / 1e-12 floor of gp.py:574-575 is active.  Pinned by central differences in tests/test_oracle.py.
+    Returns (values (C,), gradients (C, d))."""
+    cand_x = np.atleast_2d(np.asarray(cand_x, dtype=np.float64))
+    mc_points = np.atleast_2d(np.asarray(mc_points, dtype=np.float64))
+    L, kk, scale = gp.cholesky, gp.kernel_variance + gp.noise, gp.y_std**2
+    ls2 = gp.lengthscales**2
+    V = sla.solve_triangular(L, gp._k12(mc_points), lower=True, check_finite=False)  # (n, n_mc)
+    base = kk - np.sum(V * V, axis=0)
+    Wmc = sla.solve_triangular(L.T, V, lower=False, check_finite=False)  # K^-1 k(X, MC)
+    vals, grads = [], []
+    for x in cand_x:
+        x = x[None, :]
+        kx, Gx = _kernel_and_gradcoef(gp, x, gp.train_x)  # (1, n)
+        kc, Gc = _kernel_and_gradcoef(gp, x, mc_points)  # (1, n_mc)
+        v = sla.solve_triangular(L, kx.T, lower=True, check_finite=False)  # (n, 1)
+        w = sla.solve_triangular(L.T, v, lower=False, check_finite=False).ravel()
+        with np.errstate(all="ignore"):
+            delta2 = kk - float(np.sum(v * v))
+            if delta2 < 0:
+                delta2 = np.nan  # sqrt of a negative pivot, gp.py:187
+            t = (kc - v.T @ V).ravel()
+            s = base - t * t / delta2
+        floored = ~(s >= SAFE_NOISE_FLOOR)  # NaN or below the floor
+        s = np.where(floored, SAFE_NOISE_FLOOR, s)
+        val = scale * s
+        c = np.full_like(s, scale) if not std else scale / (2.0 * np.sqrt(val))
+        c = np.where(floored, 0.0, c)
+        with np.errstate(all="ignore"):
+            a = np.where(floored, 0.0, -2.0 * c * t / delta2)
+            b = float(np.sum(np.where(floored, 0.0, c * t * t / delta2**2)))
+        dk_mc = -(Gc.ravel()[:, None]) * (x - mc_points) / ls2  # (n_mc, d) = dk(x, mc_j)/dx
+        dk_tr = -(Gx.ravel()[:, None]) * (x - gp.train_x) / ls2  # (n, d)   = dk(x, X_i)/dx
+        e = -(Wmc @ a) - 2.0 * b * w  # coefficient of dk(x, X_i)/dx
+        grads.append((a @ dk_mc + e @ dk_tr) / mc_points.shape[0])
+        vals.append(np.mean(np.sqrt(val) if std else val))
+    return np.array(vals), np.array(grads)
+
+
 # ----------------------------------------------------------------------------------------------
 # synthetic workloads (SURVEY.md 8d) -- shared by tests and bench so that both sides see the same inputs
 # ----------------------------------------------------------------------------------------------

@@ -374,6 +374,54 @@ def test_acquisition_analytic_gradient(cls_name):
             assert np.max(np.abs(grad[:, k] - fd) / scale) < (2e-5 if cls_name == "EI" else 3e-4)
 
 
+@pytest.mark.parametrize("name", ["A_banana_rbf_n100_d2", "M_matern_n300_d3", "B_rbf_n500_d6"])
+def test_fantasy_acquisition_gradient_matches_oracle(name, monkeypatch):
+    """d WIPV / dx_new and d WIPStd / dx_new (bobe_fantasy_var_grad) against the oracle's analytic
+    gradient (pinned by central differences in tests/test_oracle.py); values against the value-only call; several MC
+    chunks must give the single-chunk result; the floor has zero gradient."""
+    ref, X, y, Xq, _, _, _ = make_case(name)
+    gp = make_gp(ref)
+    rng = np.random.default_rng(11)
+    d = X.shape[1]
+    mc = rng.uniform(0, 1, (333, d))
+    cand = np.vstack([rng.uniform(0, 1, (70, d)), mc[:2], X[:1]])  # MC points and a training point as candidates too
+    for std in (False, True):
+        val, grad = gp.fantasy_acquisition_value_and_grad(mc, cand, std=std)
+        rval, rgrad = O.wipv_values_and_grad(ref, cand, mc, std=std)
+        scale = ref.y_std if std else ref.y_std ** 2
+        assert val.shape == (73,) and grad.shape == (73, d)
+        assert mixed_err(val, rval, scale) < TOL_VAR
+        assert mixed_err(val, gp.fantasy_acquisition(mc, cand, std=std), scale) < 1e-13
+        assert mixed_err(grad, rgrad, max(float(np.abs(rgrad).max()), scale)) < TOL_GRAD, (name, std)
+        assert np.all(np.isfinite(grad))
+    # a candidate on a training point: delta2 ~ noise, the rank-1 term is floored or ill-defined but never NaN
+    v1, g1 = gp.fantasy_acquisition_value_and_grad(mc, X[:4], std=False)
+    assert np.all(np.isfinite(v1)) and np.all(np.isfinite(g1))
+    # single candidate as a 1-D vector
+    v0, g0 = gp.fantasy_acquisition_value_and_grad(mc, cand[0], std=False)
+    assert v0.shape == (1,) and g0.shape == (1, d)
+
+
+def test_wipv_polish_uses_analytic_gradient_and_improves():
+    """The n <= 500 branch of WeightedIntegratedPosteriorBase.get_next_point (BOBE/acquisition.py:400-412): polishing from
+    the best MC candidate with the analytic gradient never returns a worse point than its start."""
+    import bobe_b200
+    ref, X, y, Xq, _, _, _ = make_case("A_banana_rbf_n100_d2")
+    gp = make_gp(ref)
+    rng = np.random.default_rng(3)
+    mc_samples = {"x": rng.uniform(0, 1, (512, 2))}
+    for cls in (bobe_b200.WIPV, bobe_b200.WIPStd):
+        acq = cls(optimizer="scipy")
+        x, v = acq.get_next_point(gp, {"mc_samples": mc_samples, "mc_points_size": 128}, maxiter=50, n_restarts=1,
+                                  verbose=False, rng=np.random.default_rng(4))
+        mc_points = bobe_b200.acquisition.get_mc_points(mc_samples, 128, rng=np.random.default_rng(4))
+        start = gp.fantasy_acquisition(mc_points, None, std=acq._std).min()
+        x = np.asarray(x).reshape(-1)
+        assert x.shape == (2,) and np.all((x >= 0) & (x <= 1))
+        assert float(v) <= float(start) * (1 + 1e-12)
+        assert abs(float(acq.fun(x, gp, mc_points=mc_points)) - float(v)) <= 1e-10 * abs(float(v))
+
+
 @pytest.mark.parametrize("kernel,n0,b", [("rbf", 120, 1), ("matern", 126, 5), ("matern", 300, 8), ("rbf", 63, 3)])
 def test_incremental_update_matches_full_refactorisation(kernel, n0, b):
     """GP.update extends the factor by rank-b appends (O(b n^2)); factor, alpha and predictions

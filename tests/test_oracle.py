@@ -178,6 +178,38 @@ def test_fantasy_var_equals_predict_var_of_updated_gp():
         assert mixed_err(shared[1], gp.fantasy_var(mc[0], mc, ktm), y_std0 ** 2) < 1e-9
 
 
+@pytest.mark.parametrize("kernel", ["rbf", "matern"])
+@pytest.mark.parametrize("std", [False, True])
+def test_wipv_gradient_matches_central_differences(kernel, std):
+    """d WIPV / dx_new and d WIPStd / dx_new (wipv_values_and_grad: the derivative jax.value_and_grad takes of
+    BOBE/acquisition.py:438-440,463-465 in the n <= 500 polish) against central differences of the literal
+    fantasy-variance path (BOBE/gp.py:552-576), which shares no code with the analytic gradient."""
+    X, y = toy(60, 3, seed=0)
+    gp = O.OracleGP(X, y, kernel=kernel, noise=1e-6, lengthscales=np.array([0.15, 0.2, 0.25]), kernel_variance=1.3)
+    rng = np.random.default_rng(5)
+    mc, cand = rng.uniform(0, 1, (40, 3)), rng.uniform(0, 1, (4, 3))
+    ktm = gp.kernel(gp.train_x, mc, gp.lengthscales, gp.kernel_variance, gp.noise, False)
+
+    def literal(c):  # mean_j of the reference's fantasy_var, one candidate at a time
+        out = []
+        for x in c:
+            fv = gp.fantasy_var(x, mc, ktm)
+            out.append(np.mean(np.sqrt(fv) if std else fv))
+        return np.array(out)
+
+    val, g = O.wipv_values_and_grad(gp, cand, mc, std)
+    assert mixed_err(val, literal(cand), 1.0) < 1e-12
+    h = 1e-6
+    for k in range(3):
+        e = np.zeros(3); e[k] = h
+        fd = (literal(cand + e) - literal(cand - e)) / (2 * h)
+        assert np.max(np.abs(g[:, k] - fd)) < 1e-8 * np.max(np.abs(g))
+    # floored terms carry no gradient: a candidate on a training point with (almost) no noise
+    gp0 = O.OracleGP(X, y, kernel=kernel, noise=1e-14, lengthscales=np.array([0.15, 0.2, 0.25]))
+    v0, g0 = O.wipv_values_and_grad(gp0, X[:2], mc, std)
+    assert np.all(np.isfinite(v0)) and np.all(np.isfinite(g0))
+
+
 def test_fast_update_cholesky_matches_full_factor():
     X, y = toy(20, 2)
     gp = O.OracleGP(X, y, noise=1e-6)
