@@ -85,6 +85,21 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(BobeFantasyVar, FantasyImpl,
                                   .Attr<double>("y_std").Attr<int64_t>("reduce").Ret<F64>()
                                   .Ret<ffi::Buffer<ffi::U8>>());
 
+// WIPV / WIPStd value + gradient in the candidate: the custom_vjp rule of the n <= 500 polish (BOBE/acquisition.py:400-412)
+static ffi::Error FantasyGradImpl(cudaStream_t s, F64 X, F64 ls, F64 Linv, F64 LinvT, F64 Xmc, F64 Xcand, int64_t kind,
+                                  double kv, double noise, double y_std, int64_t reduce, RF64 out, RF64 dout, RU8 ws) {
+  int64_t n = X.dimensions()[0], d = X.dimensions()[1], n_mc = Xmc.dimensions()[0], C = Xcand.dimensions()[0];
+  return status(bobe_fantasy_var_grad(s, (int32_t)kind, X.typed_data(), n, d, ls.typed_data(), kv, noise,
+                                      Linv.typed_data(), LinvT.typed_data(), y_std, Xmc.typed_data(), n_mc,
+                                      Xcand.typed_data(), C, (int32_t)reduce, out->typed_data(), dout->typed_data(),
+                                      ws->untyped_data(), (int64_t)ws->size_bytes()));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(BobeFantasyVarGrad, FantasyGradImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<F64>().Arg<F64>().Arg<F64>()
+                                  .Arg<F64>().Arg<F64>().Arg<F64>().Attr<int64_t>("kind").Attr<double>("kv")
+                                  .Attr<double>("noise").Attr<double>("y_std").Attr<int64_t>("reduce").Ret<F64>()
+                                  .Ret<F64>().Ret<ffi::Buffer<ffi::U8>>());
+
 // value + input gradients: the backward rule of the custom_vjp around bobe_predict (BOBE/samplers.py:268-285,
 // BOBE/optim.py:118,309 differentiate predict_*_single with respect to x)
 static ffi::Error PredictGradImpl(cudaStream_t s, F64 X, F64 ls, F64 Linv, F64 LinvT, F64 alpha, F64 Xq, int64_t kind,

@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SHIM_PATH = os.path.join(_HERE, "lib", "libbobe_xla_ffi.so")
 TARGETS = {"bobe_kernel_matrix": "BobeKernelMatrix", "bobe_factorize": "BobeFactorize",
            "bobe_mll_grad": "BobeMllGrad", "bobe_predict": "BobePredict", "bobe_fantasy_var": "BobeFantasyVar",
+           "bobe_fantasy_var_grad": "BobeFantasyVarGrad",
            "bobe_predict_grad": "BobePredictGrad", "bobe_linv_transpose": "BobeLinvTranspose",
            "bobe_factor_append": "BobeFactorAppend", "bobe_svm_mask": "BobeSvmMask"}
 
