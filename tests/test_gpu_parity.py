@@ -402,6 +402,20 @@ def test_fantasy_acquisition_gradient_matches_oracle(name, monkeypatch):
     assert v0.shape == (1,) and g0.shape == (1, d)
 
 
+def test_fantasy_acquisition_gradient_over_several_mc_chunks():
+    """n_mc beyond one internal MC chunk (16,384): accumulation over chunks against the oracle."""
+    ref, X, y, Xq, _, _, _ = make_case("A_banana_rbf_n100_d2")
+    gp = make_gp(ref)
+    rng = np.random.default_rng(12)
+    mc, cand = rng.uniform(0, 1, (40001, 2)), rng.uniform(0, 1, (5, 2))
+    for std in (False, True):
+        val, grad = gp.fantasy_acquisition_value_and_grad(mc, cand, std=std)
+        rval, rgrad = O.wipv_values_and_grad(ref, cand, mc, std=std)
+        scale = ref.y_std if std else ref.y_std ** 2
+        assert mixed_err(val, rval, scale) < TOL_VAR
+        assert mixed_err(grad, rgrad, max(float(np.abs(rgrad).max()), scale)) < TOL_GRAD
+
+
 def test_wipv_polish_uses_analytic_gradient_and_improves():
     """The n <= 500 branch of WeightedIntegratedPosteriorBase.get_next_point (BOBE/acquisition.py:400-412): polishing from
     the best MC candidate with the analytic gradient never returns a worse point than its start."""
