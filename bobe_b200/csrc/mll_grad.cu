@@ -184,6 +184,7 @@ constexpr int MLL_MAX_STREAMS = 8;
 struct StreamPool {
     cudaStream_t streams[MLL_MAX_STREAMS];
     cudaEvent_t fork, join[MLL_MAX_STREAMS];
+    std::mutex enqueue_mu;  // the fork / join events are shared: one host thread enqueues on the pool at a time
 };
 static StreamPool* stream_pool() {
     static std::mutex mu;
@@ -290,11 +291,16 @@ extern "C" int32_t bobe_mll_grad_batched(void* stream_, int32_t kind, const doub
     // joined to the caller's stream with events): one sub-batch's latency-bound leaves and small products overlap
     // with another's large tensor-core products.
     static const int64_t max_streams = std::min<int64_t>(MLL_MAX_STREAMS, env_int("BOBE_MLL_STREAMS", 4));
-    const int S = (int)std::min<int64_t>(max_streams, std::max<int64_t>(1, R / 4));
+    static const int64_t min_per_stream = std::max<int64_t>(1, env_int("BOBE_MLL_MIN_PER_STREAM", 4));
+    const int S = (int)std::min<int64_t>(max_streams, std::max<int64_t>(1, R / min_per_stream));
     StreamPool* pool = nullptr;
+    // XLA may call handlers from several host threads: the record / wait pairs below must not interleave with those
+    // of another caller of the same device (stream order then keeps the shared side streams correct)
+    std::unique_lock<std::mutex> pool_lock;
     if (S > 1) {
         pool = stream_pool();
         if (!pool) return BOBE_E_CUDA;
+        pool_lock = std::unique_lock<std::mutex>(pool->enqueue_mu);
         if (cudaEventRecord(pool->fork, stream) != cudaSuccess) {
             set_error("mll_grad: event record failed");
             return BOBE_E_CUDA;

@@ -5,6 +5,7 @@ No function here has a CPU path; a CPU tensor raises.
 """
 from __future__ import annotations
 
+from collections import OrderedDict
 from typing import Optional, Tuple
 
 import torch
@@ -14,7 +15,8 @@ from ._lib import lib, check
 
 KIND = {"rbf": _lib.KERNEL_RBF, "matern": _lib.KERNEL_MATERN52}
 
-_ws_cache = {}
+_ws_cache = OrderedDict()
+_WS_MAX_ARENAS = 4  # most recently used (device, stream) arenas kept alive
 
 
 def _stream() -> int:
@@ -22,13 +24,20 @@ def _stream() -> int:
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
-    """Grow-only scratch arena per device (the C-ABI never allocates)."""
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    """Grow-only scratch arena per (device, stream) (the C-ABI never allocates).
+
+    Calls on one stream are stream-ordered, so they can share an arena; calls on different streams (or from different
+    host threads with their own current stream) must not."""
+    dev = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
-        _ws_cache[key] = None
-        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=f"cuda:{key}")
+        _ws_cache[key] = None  # drop the old arena first (the caching allocator keeps it valid for queued kernels)
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=f"cuda:{dev}")
         _ws_cache[key] = buf
+    _ws_cache.move_to_end(key)
+    while len(_ws_cache) > _WS_MAX_ARENAS:  # arenas of streams no longer in use (stream-ordered free: safe)
+        _ws_cache.popitem(last=False)
     return buf
 
 
