@@ -1,4 +1,5 @@
 // extern "C" entry points declared in include/bobe_b200.h (except bobe_mll_grad_batched, see mll_grad.cu).
+#include <algorithm>
 #include <cmath>
 
 #include "gemm_nt.cuh"
@@ -398,7 +399,12 @@ extern "C" int32_t bobe_predict(void* stream_, int32_t kind, const double* X, in
     // mean only: no K* panel to bound, so the rows go out in launches as large as the grid allows (more CTAs per SM
     // for the kernel-matrix kernel); with the variance, the K* panel of KCHUNKS chunks is built by one launch and
     // consumed by one trmm_sumsq launch per 148 x 128-query chunk
-    const int64_t step = want_var ? KCHUNKS * QCHUNK : (int64_t)64 * 32768;
+    // BOBE_TRMM_SPLIT = S > 1 (experiment knob, see launch_trmm_sumsq): chunks of 148 / S query tiles, one chunk per
+    // kernel-matrix launch, so that the K* panels written by one launch are still in L2 when the next one reads them
+    static const int64_t tsplit = std::max<int64_t>(1, std::min<int64_t>(TRMM_MAX_SPLIT, env_int("BOBE_TRMM_SPLIT", 1)));
+    static const int64_t kchunks = std::max<int64_t>(1, std::min<int64_t>(KCHUNKS, env_int("BOBE_KCHUNKS", tsplit > 1 ? 1 : KCHUNKS)));
+    const int64_t qchunk = (148 / tsplit) * 128;
+    const int64_t step = want_var ? kchunks * qchunk : (int64_t)64 * 32768;
     for (int64_t q0 = 0; q0 < M; q0 += step) {
         int64_t rows = (M - q0 < step) ? M - q0 : step;
         int64_t rows_pad = round_up(rows, 128);
@@ -420,8 +426,8 @@ extern "C" int32_t bobe_predict(void* stream_, int32_t kind, const double* X, in
                                                             var_out);
             if (int32_t rc = check_launch("small-M variance")) return rc;
         } else if (want_var) {
-            for (int64_t c0 = 0; c0 < rows_pad; c0 += QCHUNK) {
-                const int64_t crows = (rows_pad - c0 < QCHUNK) ? rows_pad - c0 : QCHUNK;
+            for (int64_t c0 = 0; c0 < rows_pad; c0 += qchunk) {
+                const int64_t crows = (rows_pad - c0 < qchunk) ? rows_pad - c0 : qchunk;
                 if (int32_t rc = launch_trmm_sumsq(stream, Linv, (int)n, (int)npad, kstar + c0 * npad, npad, crows, q0 + c0, M,
                                                    kv + noise, y_std * y_std, standardised, var_out, partial))
                     return rc;

@@ -115,6 +115,10 @@ int32_t launch_trmm_sumsq(cudaStream_t stream, const double* Linv, int n, int np
         split = split > nblk ? nblk : split;
         split = split > TRMM_MAX_SPLIT ? TRMM_MAX_SPLIT : split;
     }
+    // L2-resident schedule (bobe_predict with BOBE_TRMM_SPLIT = S > 1 sends chunks of 148 / S query tiles): S CTAs share
+    // one K* panel, so the panels in flight (148 / S x 128 x npad x 8 bytes) stay in L2 between the row-block sweeps
+    static const int64_t forced = env_int("BOBE_TRMM_SPLIT", 1);
+    if (partial && forced > 1 && nblk >= forced && qtiles * forced <= 148 && split < forced) split = (int)forced;
     dim3 grid(qtiles, split);
     if (split > 1)
         trmm_sumsq_kernel<Cfg, true><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(Linv, n, npad, Kstar, ldk, q_begin, M, kk,

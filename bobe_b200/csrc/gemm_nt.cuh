@@ -419,7 +419,14 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
     const int r_first = n8 % Cfg::BM;
     const int first = r_first ? r_first : Cfg::BM;       // rows of block 0
     const int nblk = (n8 + Cfg::BM - 1) / Cfg::BM;
-    for (int b = SPLIT ? blockIdx.y : 0; b < nblk; b += SPLIT ? gridDim.y : 1) {
+    for (int b = 0; b < nblk; ++b) {
+        if (SPLIT) {
+            // Row block b costs ~(b + 1) k-blocks.  Dealing the blocks out boustrophedon-wise (0 1 2 3 3 2 1 0 0 1 ...)
+            // gives every CTA of a query tile the same triangular work (a plain stride would leave the last CTA with
+            // up to 40 % more than the first).
+            const int S = gridDim.y, r = b % (2 * S);
+            if ((r < S ? r : 2 * S - 1 - r) != (int)blockIdx.y) continue;
+        }
         const int i0 = b == 0 ? 0 : first + (b - 1) * Cfg::BM;
         double acc[Cfg::MF][Cfg::NF][2];
 #pragma unroll
