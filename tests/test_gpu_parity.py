@@ -581,3 +581,84 @@ def test_empty_and_ragged_inputs():
         assert mixed_err(var[sub], ref.predict_var_batched(xq[sub]), ref.y_std ** 2) < TOL_VAR
         vo = gp.predict_var_batched(xq)  # variance-only call takes the same paths
         assert np.array_equal(vo, var)
+
+
+# ---- the remaining BASELINE configurations at their FULL sizes (size-independent properties + oracle sub-samples) --------
+def test_config_c_64_restarts_full_size():
+    """Config C: n = 2000, d = 16 Matern-5/2, 64 restarts drawn as BOBE/pool.py:277-286 does (some are not PD).
+    Batch independence (a restart's value / gradient does not depend on which other restarts share the launch), NaN
+    pattern == info flags, and the oracle on the restarts it can afford."""
+    from bobe_b200 import ops
+    ref, X, y, _, _, _, _ = make_case("H_matern_n2000_d16")
+    gp = make_gp(ref)
+    gp._ensure_factor()
+    lp = O.synthetic_restarts(ref, 64)
+    val, grad, info = ops.mll_grad_batched("matern", gp._X_dev, gp._y_dev, T(lp), True, 1.0, float(ref.noise))
+    val, grad, info = val.cpu().numpy(), grad.cpu().numpy(), info.cpu().numpy()
+    assert val.shape == (64,) and grad.shape == (64, 17)
+    bad = info != 0
+    assert np.array_equal(np.isnan(val), bad) and np.array_equal(np.isnan(grad).any(axis=1), bad)
+    assert np.isfinite(val[0]) and (~bad).sum() >= 32
+    # the same rows in other company: sub-batches of 5 and 59 (different stream split, different grid.z)
+    va, ga, _ = ops.mll_grad_batched("matern", gp._X_dev, gp._y_dev, T(lp[:5]), True, 1.0, float(ref.noise))
+    vb, gb, _ = ops.mll_grad_batched("matern", gp._X_dev, gp._y_dev, T(lp[5:]), True, 1.0, float(ref.noise))
+    v2 = np.concatenate([va.cpu().numpy(), vb.cpu().numpy()])
+    g2 = np.concatenate([ga.cpu().numpy(), gb.cpu().numpy()])
+    assert np.array_equal(np.isnan(v2), bad)
+    assert np.array_equal(v2[~bad], val[~bad]) and np.array_equal(g2[~bad], grad[~bad])
+    # oracle on row 0 (the current hyper-parameters) and the first two PD random rows
+    rows = [0] + [int(r) for r in np.where(~bad)[0][1:3]]
+    for r in rows:
+        rv, rg = ref.neg_mll_and_grad(lp[r])  # uniform priors: neg_mll = -(log p + const), gradient = -d log p
+        const = rv + val[r]
+        assert abs(const - (ref.neg_mll_and_grad(lp[0])[0] + val[0])) <= TOL_MLL * 2000  # same prior constant everywhere
+        check_grad(-grad[r], rg, f"restart {r}")
+
+
+def test_config_d_full_sweep():
+    """Config D: n = 1500, d = 27 RBF surrogate, nested-sampling sweep of M = 1e6 points (mean + variance)."""
+    ref, X, y, _, _, _, _ = make_case("D_rbf_n1500_d27")
+    gp = make_gp(ref)
+    M = 1_000_000
+    Xq = torch.rand(M, 27, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    mean, var = gp.predict_mean_var_batched(Xq)
+    assert mean.shape == (M,) and torch.isfinite(mean).all() and (var > 0).all()
+    assert float(var.max()) <= (1 + 1e-8) * ref.y_std ** 2 * 1.0000001
+    mean_only = gp.predict_mean_batched(Xq)  # the mean-only launch path (no K* panel) gives the same numbers
+    assert float((mean_only - mean).abs().max()) <= 1e-12 * max(1.0, float(mean.abs().max()))
+    k = 5 * 148 * 128  # whole chunks: bitwise the same as inside the big call
+    m_a, v_a = gp.predict_mean_var_batched(Xq[:k])
+    assert torch.equal(m_a, mean[:k]) and torch.equal(v_a, var[:k])
+    idx = np.random.default_rng(1).choice(M, 256, replace=False)
+    xs = Xq[idx].cpu().numpy()
+    assert mixed_err(mean[idx].cpu().numpy(), ref.predict_mean_batched(xs), ref.y_std) < TOL_MEAN
+    assert mixed_err(var[idx].cpu().numpy(), ref.predict_var_batched(xs), ref.y_std ** 2) < TOL_VAR
+
+
+def test_config_e_wipv_full_size():
+    """Config E: WIPV over n_mc = 1e5 MC points x 8 candidates at n = 4000, d = 12 (RBF)."""
+    from bobe_b200 import GP
+    n, d, n_mc, C = 4000, 12, 100_000, 8
+    X, y = O.synthetic_training_set(n, d)
+    ls = np.ones(d)
+    gp = GP(X, y, kernel="rbf", lengthscales=ls)
+    mc = O.synthetic_queries(n_mc, d, seed=1)
+    cand = O.synthetic_queries(C, d, seed=6)
+    wipv = gp.fantasy_acquisition(mc, cand, std=False)
+    wipstd = gp.fantasy_acquisition(mc, cand, std=True)
+    full = gp.fantasy_var(cand, mc)  # (C, n_mc), reduce = none
+    assert full.shape == (C, n_mc) and np.all(full > 0)
+    assert np.allclose(full.mean(axis=1), wipv, rtol=1e-12, atol=0) and np.allclose(np.sqrt(full).mean(axis=1), wipstd, rtol=1e-12)
+    # conditioning on one more point never increases a variance (up to rounding at the floor)
+    pv = gp.predict_var_batched(mc)
+    assert np.all(full <= pv[None, :] * (1 + 1e-9) + 1e-12 * gp.y_std ** 2)
+    # the MC columns shard (multi-GPU split of SURVEY.md 8e): the mean is the weighted mean of the shard means
+    h = 37_123
+    w2 = (h * gp.fantasy_acquisition(mc[:h], cand) + (n_mc - h) * gp.fantasy_acquisition(mc[h:], cand)) / n_mc
+    assert np.allclose(w2, wipv, rtol=1e-11, atol=0)
+    # oracle on a sub-sample of the MC columns
+    ref = O.OracleGP(X, y, kernel="rbf", lengthscales=ls)
+    idx = np.random.default_rng(2).choice(n_mc, 300, replace=False)
+    err = mixed_err(full[:, idx], ref.fantasy_var_shared(cand, mc[idx]), ref.y_std ** 2)
+    print(f"config E fantasy variance vs oracle: {err:.2e}")
+    assert err < TOL_VAR
