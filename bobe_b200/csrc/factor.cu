@@ -50,10 +50,10 @@ struct Rec {
             LeafIO io{fb.KB, fb.L, fb.Lt, fb.Linv, fb.U, fb.diag, fb.dstat, fb.gate, npad, b0 * NB};
             if (nb == 1) {
                 if ((rc = ensure_smem<leaf64_kernel>(LEAF64_SMEM)) != BOBE_OK) return;
-                leaf64_kernel<<<dim3(1, 1, batch), LEAF_THREADS, LEAF64_SMEM, stream>>>(io);
+                launch_pdl(leaf64_kernel, dim3(1, 1, batch), dim3(LEAF_THREADS), LEAF64_SMEM, stream, io);
             } else {
                 if ((rc = ensure_smem<leaf128_kernel>(LEAF128_SMEM)) != BOBE_OK) return;
-                leaf128_kernel<<<dim3(1, 1, batch), LEAF_THREADS, LEAF128_SMEM, stream>>>(io);
+                launch_pdl(leaf128_kernel, dim3(1, 1, batch), dim3(LEAF_THREADS), LEAF128_SMEM, stream, io);
             }
             rc = check_launch("leaf kernel");
             return;

@@ -33,6 +33,12 @@ int64_t env_int(const char* name, int64_t dflt) {
     return (v && *v) ? atoll(v) : dflt;
 }
 
+bool pdl_enabled(int64_t ctas) {
+    static const bool on = env_int("BOBE_PDL", 1) != 0;
+    static const int64_t max_ctas = env_int("BOBE_PDL_MAX_CTAS", 592);
+    return on && ctas <= max_ctas;
+}
+
 int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& a, int batch) {
     if (a.M <= 0 || a.N <= 0 || batch <= 0) return BOBE_OK;
     if ((a.K % 32) || (a.N % 2) || (a.lda % 2) || (a.ldb % 2) || (a.ldc % 2)) {
@@ -58,7 +64,10 @@ int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& a, int batch) {
         constexpr int MODE = decltype(mode_c)::value;
         if (int32_t rc = ensure_smem<gemm_nt_kernel<Cfg, MODE>>(Cfg::SMEM_BYTES)) return rc;
         dim3 grid((a.N + Cfg::BN - 1) / Cfg::BN, (a.M + Cfg::BM - 1) / Cfg::BM, batch);
-        gemm_nt_kernel<Cfg, MODE><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a);
+        if (launch_pdl(gemm_nt_kernel<Cfg, MODE>, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, a) != cudaSuccess) {
+            set_error("gemm_nt: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return BOBE_E_CUDA;
+        }
         return BOBE_OK;
     };
     using M0 = std::integral_constant<int, TRI_NONE>;

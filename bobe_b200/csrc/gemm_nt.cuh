@@ -340,6 +340,8 @@ struct GemmArgs {
 template <class Cfg, int MODE>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_kernel(GemmArgs p) {
     extern __shared__ __align__(16) double smem[];
+    pdl_wait();     // launched with the PDL attribute: everything below reads what the previous launch wrote
+    pdl_trigger();  // the next launch of the chain may become resident as soon as all CTAs of this one have started
     const int i0 = blockIdx.y * Cfg::BM, j0 = blockIdx.x * Cfg::BN;
     if ((p.flags & GEMM_C_LOWER) && j0 > i0 + Cfg::BM - 1) return;
     const int64_t z = blockIdx.z;

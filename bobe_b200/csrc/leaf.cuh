@@ -211,6 +211,8 @@ __device__ __forceinline__ bool leaf_update_stats(const LeafIO& io, const double
 
 __global__ void __launch_bounds__(LEAF_THREADS) leaf64_kernel(LeafIO io) {
     extern __shared__ __align__(16) double sm[];
+    pdl_wait();
+    pdl_trigger();
     double* A = sm;
     double* W = A + 64 * SLD;
     double* colb = W + 64 * SLD;  // [2][64]
@@ -236,6 +238,8 @@ constexpr int LEAF64_SMEM = (2 * 64 * SLD + 2 * 128 + 2 * 64 + 64 * TLD) * 8;
 //   (L22, X22) = chol_inv(A22);  X21 = -(X22 L21) X11
 __global__ void __launch_bounds__(LEAF_THREADS) leaf128_kernel(LeafIO io) {
     extern __shared__ __align__(16) double sm[];
+    pdl_wait();
+    pdl_trigger();
     double* B0 = sm;              // A11 -> L11
     double* B1 = B0 + 64 * SLD;   // X11
     double* B2 = B1 + 64 * SLD;   // A21 -> residual -> T
