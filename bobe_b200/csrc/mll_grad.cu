@@ -126,23 +126,39 @@ __global__ void __launch_bounds__(256, 2) mll_grad_tile_kernel(const double* __r
         }
     }
     const int np1 = d + 1;
-    for (int k = 0; k < d; ++k) {
-        const double2 a01 = *reinterpret_cast<const double2*>(ap + k * GLD);
-        const double2 a23 = *reinterpret_cast<const double2*>(ap + k * GLD + 2);
-        const double2 b01 = *reinterpret_cast<const double2*>(bp + k * GLD);
-        const double2 b23 = *reinterpret_cast<const double2*>(bp + k * GLD + 32);
-        const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
-        double s0 = 0.0, s1 = 0.0;  // two chains: the 16 terms of one dimension do not serialise on one accumulator
+    // Eight dimensions per trip: their eight warp reductions run interleaved (eight independent shuffle / add chains instead
+    // of one 5-deep dependent chain per dimension inside the loop); the order of every sum is that of warp_sum().
+    for (int kb = 0; kb < d; kb += 8) {
+        double s[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int u = 0; u < 8; ++u) {
+            const int k = kb + u;
+            double s0 = 0.0, s1 = 0.0;  // two chains: the 16 terms of one dimension do not serialise on one accumulator
+            if (k < d) {
+                const double2 a01 = *reinterpret_cast<const double2*>(ap + k * GLD);
+                const double2 a23 = *reinterpret_cast<const double2*>(ap + k * GLD + 2);
+                const double2 b01 = *reinterpret_cast<const double2*>(bp + k * GLD);
+                const double2 b23 = *reinterpret_cast<const double2*>(bp + k * GLD + 32);
+                const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
-            for (int j = 0; j < 4; j += 2) {
-                const double d0 = a[i] - b[j], d1 = a[i] - b[j + 1];
-                s0 = fma(G[4 * i + j], d0 * d0, s0);
-                s1 = fma(G[4 * i + j + 1], d1 * d1, s1);
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; j += 2) {
+                        const double d0 = a[i] - b[j], d1 = a[i] - b[j + 1];
+                        s0 = fma(G[4 * i + j], d0 * d0, s0);
+                        s1 = fma(G[4 * i + j + 1], d1 * d1, s1);
+                    }
             }
-        const double s = warp_sum(s0 + s1);
-        if (lane == 0) wred[warp * np1 + k] = s;
+            s[u] = s0 + s1;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+        if (lane == 0)
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (kb + u < d) wred[warp * np1 + kb + u] = s[u];
     }
     gkv = warp_sum(gkv);
     if (lane == 0) wred[warp * np1 + d] = gkv;
