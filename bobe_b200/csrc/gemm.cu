@@ -5,8 +5,11 @@
 #include <mutex>
 #include <type_traits>
 
+#include <cudaTypedefs.h>
+
 #include "gemm_nt.cuh"
 #include "kernels.cuh"
+#include "trmm_tma.cuh"
 
 namespace bobe {
 
@@ -104,6 +107,30 @@ __global__ void __launch_bounds__(256) trmm_finish_kernel(const double* __restri
     var_out[q] = var;
 }
 
+// ---- TMA tensor maps (driver entry point fetched through the runtime: no link dependency on libcuda) ----------------
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = []() -> PFN_cuTensorMapEncodeTiled_v12000 {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return (PFN_cuTensorMapEncodeTiled_v12000)p;
+    }();
+    return fn;
+}
+// row-major (rows, cols) float64 matrix with leading dimension ld; box = one k8 panel of `box_rows` rows
+static bool make_panel_map(CUtensorMap* map, const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    auto enc = tensor_map_encoder();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+    cuuint32_t box[2] = {8, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int32_t launch_trmm_sumsq(cudaStream_t stream, const double* Linv, int n, int npad, const double* Kstar, int64_t ldk,
                           int64_t rows_pad, int64_t q_begin, int64_t M, double kk, double scale, int standardised,
                           double* var_out, double* partial) {
@@ -129,6 +156,17 @@ int32_t launch_trmm_sumsq(cudaStream_t stream, const double* Linv, int n, int np
     static const int64_t forced = env_int("BOBE_TRMM_SPLIT", 1);
     if (partial && forced > 1 && nblk >= forced && qtiles * forced <= 148 && split < forced) split = (int)forced;
     dim3 grid(qtiles, split);
+    static const int64_t use_tma = env_int("BOBE_TRMM_TMA", 1);  // 0: the cp.async kernel (also the fallback below)
+    if (split == 1 && use_tma && (((uintptr_t)Kstar | (uintptr_t)Linv) & 15) == 0 && (ldk % 2) == 0) {
+        CUtensorMap mapA, mapB;
+        if (make_panel_map(&mapA, Linv, npad, npad, npad, Cfg::BM) && make_panel_map(&mapB, Kstar, rows_pad, npad, ldk, Cfg::BN)) {
+            constexpr int TMA_SMEM = Cfg::SMEM_BYTES + 128;  // room to align the stages to 128 bytes
+            if (int32_t rc = ensure_smem<trmm_sumsq_tma_kernel<Cfg>>(TMA_SMEM)) return rc;
+            trmm_sumsq_tma_kernel<Cfg><<<grid, Cfg::THREADS, TMA_SMEM, stream>>>(mapA, mapB, n, npad, q_begin, M, kk, scale,
+                                                                                   standardised, var_out);
+            return check_launch("trmm_sumsq_tma_kernel");
+        }
+    }
     if (split > 1)
         trmm_sumsq_kernel<Cfg, true><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(Linv, n, npad, Kstar, ldk, q_begin, M, kk,
                                                                                    scale, standardised, var_out, partial,

@@ -1,0 +1,232 @@
+// TMA-fed variant of trmm_sumsq_kernel (gemm_nt.cuh): same tiles, same fragment ownership, same order of every sum (the
+// results are bitwise those of the cp.async kernel), but
+//   * the k-tiles of Linv and K* are brought in by cp.async.bulk.tensor (TMA) issued by ONE lane and land on a
+//     transaction mbarrier per pipeline stage, instead of 8 LDGSTS per thread and k-tile;
+//   * there is no block-wide barrier in the k loop: a warp waits on the "full" mbarrier of its stage, computes, and counts
+//     itself out of the stage; the LAST warp to leave a stage issues its refill.  Warps drift apart by up to two k-tiles
+//     instead of meeting at every k-tile;
+//   * the (row block, k-tile) items of the whole triangular sweep form ONE pipeline: the first k-tiles of the next row
+//     block are in flight while the current one finishes (the cp.async kernel drains and refills at each of the 16 row
+//     blocks).
+// Shared-memory layout per stage and operand is the one of gemm_nt.cuh (BK/8 "k8 panels" of rows x 64 bytes): one 2-D
+// TMA box {8 doubles, 128 rows} is exactly one panel, so no swizzle is involved.
+#pragma once
+#include <cuda.h>
+
+#include "gemm_nt.cuh"
+
+namespace bobe {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// one 2-D box (c0 = first element along the contiguous dimension, c1 = first row) -> dense shared memory
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
+    trmm_sumsq_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int n, int npad,
+                          int64_t q_begin, int64_t M, double kk, double scale, int standardised,
+                          double* __restrict__ var_out) {
+    using ML = Mainloop<Cfg>;
+    constexpr int STAGES = Cfg::STAGES, NWARPS = Cfg::THREADS / 32;
+    constexpr uint32_t STAGE_BYTES = Cfg::STAGE_DOUBLES * 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // TMA destinations must be 128-byte aligned; the dynamic window starts behind the static arrays below
+    double* smem = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    __shared__ __align__(8) uint64_t full[STAGES];
+    __shared__ int left[STAGES];  // warps that have not yet left the stage
+    __shared__ double red[Cfg::WM][Cfg::BN];
+    const int j0 = blockIdx.x * Cfg::BN;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp / Cfg::WN, wn = warp % Cfg::WN;
+
+    // the sweep: row blocks aligned to the END of the matrix (see trmm_sumsq_kernel), k range of block b = [0, ke_b)
+    const int kmax = ((n + Cfg::BK - 1) / Cfg::BK) * Cfg::BK;
+    const int n8 = (n + 7) & ~7;
+    const int r_first = n8 % Cfg::BM;
+    const int first = r_first ? r_first : Cfg::BM;
+    const int nblk = (n8 + Cfg::BM - 1) / Cfg::BM;
+    auto row0 = [&](int b) { return b == 0 ? 0 : first + (b - 1) * Cfg::BM; };
+    auto ktiles_of = [&](int b) {
+        const int live = b == 0 ? first : Cfg::BM;
+        const int ke = min(kmax, ((row0(b) + live + Cfg::BK - 1) / Cfg::BK) * Cfg::BK);
+        return ke / Cfg::BK;
+    };
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            left[s] = NWARPS;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // issue the TMA loads of item (b, kt) into `stage` (one lane)
+    auto issue = [&](int b, int kt, int stage) {
+        double* sA = smem + stage * Cfg::STAGE_DOUBLES;
+        double* sB = sA + Cfg::BM * Cfg::BK;
+        mbar_expect_tx(&full[stage], STAGE_BYTES);
+        const int i0 = row0(b), k0 = kt * Cfg::BK;
+#pragma unroll
+        for (int p = 0; p < Cfg::PANELS; ++p) {
+            tma_load_2d(sA + p * Cfg::BM * 8, &mapA, &full[stage], k0 + 8 * p, i0);
+            tma_load_2d(sB + p * Cfg::BN * 8, &mapB, &full[stage], k0 + 8 * p, j0);
+        }
+    };
+
+    // look-ahead iterator (item + STAGES), kept by every warp's lane 0
+    int lb = 0, lkt = 0;
+    auto advance = [&](int& b, int& kt) {
+        if (b >= nblk) return;
+        if (++kt == ktiles_of(b)) {
+            kt = 0;
+            ++b;
+        }
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            if (lb < nblk) issue(lb, lkt, s);
+            advance(lb, lkt);
+        }
+    } else {
+        for (int s = 0; s < STAGES; ++s) advance(lb, lkt);
+    }
+
+    double colsum[Cfg::NF][2];
+#pragma unroll
+    for (int nf = 0; nf < Cfg::NF; ++nf) colsum[nf][0] = colsum[nf][1] = 0.0;
+
+    constexpr int FSTEP = Cfg::ILV ? 8 * Cfg::WM : 8;
+    constexpr int FLAST = Cfg::frag_row(Cfg::WM - 1, 0);
+    const int fbase = Cfg::frag_row(wm, 0);
+    int stage = 0;
+    uint32_t parity = 0;
+    for (int b = 0; b < nblk; ++b) {
+        const int i0 = row0(b);
+        const int rows_live = b == 0 ? first : Cfg::BM;
+        const int ktiles = ktiles_of(b);
+        int hi = (rows_live - fbase + FSTEP - 1) / FSTEP;
+        hi = hi < 0 ? 0 : (hi > Cfg::MF ? Cfg::MF : hi);
+        // k-tiles without a dead fragment (Mainloop::run, TRI_LOWER)
+        const int num = i0 + FLAST + 7 - 8 * (Cfg::PANELS - 1);
+        int kt_full = rows_live >= Cfg::BM ? (num < 0 ? 0 : num / Cfg::BK + 1) : 0;
+        kt_full = kt_full > ktiles ? ktiles : kt_full;
+
+        double acc[Cfg::MF][Cfg::NF][2];
+#pragma unroll
+        for (int mf = 0; mf < Cfg::MF; ++mf)
+#pragma unroll
+            for (int nf = 0; nf < Cfg::NF; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
+
+        for (int kt = 0; kt < ktiles; ++kt) {
+            mbar_wait(&full[stage], parity);
+            const double* sA = smem + stage * Cfg::STAGE_DOUBLES;
+            const double* sB = sA + Cfg::BM * Cfg::BK;
+            if (kt < kt_full) {
+#pragma unroll
+                for (int p = 0; p < Cfg::PANELS; ++p) ML::mma_panel(acc, sA, sB, p, wm, wn, g, t);
+            } else {
+                const int kp0 = kt * Cfg::BK;
+#pragma unroll
+                for (int p = 0; p < Cfg::PANELS; ++p) {
+                    const int kp = kp0 + 8 * p;
+                    if (rows_live >= Cfg::BM) {
+                        const int rel = kp - i0 - FLAST - 7;
+                        const int lo = rel <= 0 ? 0 : (rel + FSTEP - 1) / FSTEP;
+                        if (lo == 0)
+                            ML::mma_panel(acc, sA, sB, p, wm, wn, g, t);
+                        else
+                            ML::template mma_panel_jump<false>(acc, sA, sB, p, wm, wn, g, t, lo);
+                    } else {
+                        const int rel = kp - i0 - fbase - 7;
+                        const int lo = rel <= 0 ? 0 : (rel + FSTEP - 1) / FSTEP;
+                        if (lo < hi) ML::mma_panel_range(acc, sA, sB, p, wm, wn, g, t, lo, hi);
+                    }
+                }
+            }
+            // leave the stage; the last warp out refills it with item + STAGES
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                const int before = atomicSub(&left[stage], 1);
+                if (before == 1) {
+                    left[stage] = NWARPS;  // nobody touches it again before the refill has landed
+                    __threadfence_block();
+                    if (lb < nblk) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        issue(lb, lkt, stage);
+                    }
+                }
+                advance(lb, lkt);
+            }
+            if (++stage == STAGES) {
+                stage = 0;
+                parity ^= 1u;
+            }
+        }
+#pragma unroll
+        for (int mf = 0; mf < Cfg::MF; ++mf)
+#pragma unroll
+            for (int nf = 0; nf < Cfg::NF; ++nf) {
+                colsum[nf][0] = fma(acc[mf][nf][0], acc[mf][nf][0], colsum[nf][0]);
+                colsum[nf][1] = fma(acc[mf][nf][1], acc[mf][nf][1], colsum[nf][1]);
+            }
+    }
+#pragma unroll
+    for (int nf = 0; nf < Cfg::NF; ++nf)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            double v = colsum[nf][c];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (g == 0) red[wm][wn * Cfg::WTN + nf * 8 + 2 * t + c] = v;
+        }
+    __syncthreads();
+    for (int c = threadIdx.x; c < Cfg::BN; c += Cfg::THREADS) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < Cfg::WM; ++w) s += red[w][c];
+        const int64_t q = q_begin + j0 + c;
+        if (q < M) {
+            double var = kk - s;
+            if (standardised) {
+                if (isnan(var)) var = SAFE_FLOOR;
+                if (var < SAFE_FLOOR) var = SAFE_FLOOR;
+            } else {
+                if (var < SAFE_FLOOR) var = SAFE_FLOOR;
+                var *= scale;
+            }
+            var_out[q] = var;
+        }
+    }
+}
+
+}  // namespace bobe
