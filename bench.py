@@ -268,7 +268,7 @@ def main():
         traffic = float(j["dram_bytes_read"]) + float(j["dram_bytes_write"])
     except Exception:
         pass
-    roofline = {"bound": "tensor", "kernel": "trmm_sumsq_kernel (FP64 DMMA.8x8x4; no tcgen05 f64 kind exists)",
+    roofline = {"bound": "tensor", "kernel": "trmm_sumsq_tma_kernel (FP64 DMMA.8x8x4 fed by TMA on mbarriers; no tcgen05 f64 kind exists)",
                 "achieved": achieved, "peak": peaks["fp64_dgemm_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["fp64_dgemm_tflops"], "traffic": traffic,
                 "peak_source": peaks["src"], "flops_per_launch": flops_per_launch, "ms_per_launch": ms_k,
