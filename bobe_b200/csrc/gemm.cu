@@ -1,5 +1,6 @@
 // Launchers for the DMMA NT-GEMM and the fused "triangular multiply + column sum of squares" kernel that
 // produces the predictive variance term ||L^-1 k*||^2 without ever writing V = L^-1 K* to memory.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdlib>
 #include <mutex>
@@ -36,6 +37,53 @@ int64_t env_int(const char* name, int64_t dflt) {
     return (v && *v) ? atoll(v) : dflt;
 }
 
+// ---- TMA tensor maps (driver entry point fetched through the runtime: no link dependency on libcuda) ----------------
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = []() -> PFN_cuTensorMapEncodeTiled_v12000 {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return (PFN_cuTensorMapEncodeTiled_v12000)p;
+    }();
+    return fn;
+}
+// row-major (rows, cols) float64 matrix with leading dimension ld; box = one k8 panel of `box_rows` rows
+static bool make_panel_map(CUtensorMap* map, const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    auto enc = tensor_map_encoder();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+    cuuint32_t box[2] = {8, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// batched variant: (batch, rows, cols) with row stride ld and matrix stride `stride` (in doubles); box = one k8 panel
+static bool make_panel_map3(CUtensorMap* map, const double* base, int64_t batch, int64_t rows, int64_t cols, int64_t ld,
+                            int64_t stride, int box_rows) {
+    auto enc = tensor_map_encoder();
+    if (!enc) return false;
+    if (batch <= 1 || stride <= 0) stride = rows * ld;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(batch < 1 ? 1 : batch)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 8, (cuuint64_t)stride * 8};
+    cuuint32_t box[3] = {8, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int sm_count() {
+    static const int n = []() {
+        int dev = 0, v = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v > 0 ? v : 148;
+    }();
+    return n;
+}
+
 bool pdl_enabled(int64_t ctas) {
     static const bool on = env_int("BOBE_PDL", 1) != 0;
     static const int64_t max_ctas = env_int("BOBE_PDL_MAX_CTAS", 592);
@@ -62,6 +110,32 @@ int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& a, int batch) {
         return BOBE_E_ARG;
     }
     const int mode = (a.flags & GEMM_A_LOWER) ? TRI_LOWER : ((a.flags & GEMM_A_UPPER) ? TRI_UPPER : TRI_NONE);
+    // Products whose 128 x 128 tiles can fill the machine: the persistent TMA kernel (trmm_tma.cuh)
+    static const int64_t tma_gemm = env_int("BOBE_GEMM_TMA", 0);
+    static const int64_t tma_min_tiles = env_int("BOBE_GEMM_TMA_MIN_TILES", 2);  // live tiles per SM
+    if (tma_gemm && !forced && a.M >= 256 && a.N >= 256 && a.K >= 128 && ((((uintptr_t)a.A) | ((uintptr_t)a.Bt)) & 15) == 0 &&
+        (a.strideA % 2) == 0 && (a.strideB % 2) == 0) {
+        using Cfg = CfgBig;
+        const int tiles_m = (a.M + Cfg::BM - 1) / Cfg::BM, tiles_n = (a.N + Cfg::BN - 1) / Cfg::BN;
+        const int64_t total = (int64_t)tiles_m * tiles_n * batch;
+        const int64_t live = (a.flags & GEMM_C_LOWER) ? total / 2 : total;
+        CUtensorMap mapA, mapB;
+        if (live >= tma_min_tiles * sm_count() && total < (int64_t)1 << 30 &&
+            make_panel_map3(&mapA, a.A, batch, a.M, a.K, a.lda, a.strideA, Cfg::BM) &&
+            make_panel_map3(&mapB, a.Bt, batch, a.N, a.K, a.ldb, a.strideB, Cfg::BN)) {
+            constexpr int TMA_SMEM = Cfg::SMEM_BYTES + 128;
+            const unsigned grid = (unsigned)std::min<int64_t>(total, sm_count());
+            auto go_tma = [&](auto mode_c) -> int32_t {
+                constexpr int MODE = decltype(mode_c)::value;
+                if (int32_t rc = ensure_smem<gemm_nt_tma_kernel<Cfg, MODE>>(TMA_SMEM)) return rc;
+                gemm_nt_tma_kernel<Cfg, MODE><<<grid, Cfg::THREADS, TMA_SMEM, stream>>>(mapA, mapB, a, tiles_m, tiles_n, (int)total);
+                return check_launch("gemm_nt_tma_kernel");
+            };
+            if (mode == TRI_LOWER) return go_tma(std::integral_constant<int, TRI_LOWER>{});
+            if (mode == TRI_UPPER) return go_tma(std::integral_constant<int, TRI_UPPER>{});
+            return go_tma(std::integral_constant<int, TRI_NONE>{});
+        }
+    }
     auto go = [&](auto cfg, auto mode_c) -> int32_t {
         using Cfg = decltype(cfg);
         constexpr int MODE = decltype(mode_c)::value;
@@ -105,30 +179,6 @@ __global__ void __launch_bounds__(256) trmm_finish_kernel(const double* __restri
         var *= scale;
     }
     var_out[q] = var;
-}
-
-// ---- TMA tensor maps (driver entry point fetched through the runtime: no link dependency on libcuda) ----------------
-static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
-    static PFN_cuTensorMapEncodeTiled_v12000 fn = []() -> PFN_cuTensorMapEncodeTiled_v12000 {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess)
-            return nullptr;
-        return (PFN_cuTensorMapEncodeTiled_v12000)p;
-    }();
-    return fn;
-}
-// row-major (rows, cols) float64 matrix with leading dimension ld; box = one k8 panel of `box_rows` rows
-static bool make_panel_map(CUtensorMap* map, const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
-    auto enc = tensor_map_encoder();
-    if (!enc) return false;
-    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
-    cuuint32_t box[2] = {8, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 int32_t launch_trmm_sumsq(cudaStream_t stream, const double* Linv, int n, int npad, const double* Kstar, int64_t ldk,

@@ -229,4 +229,204 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
     }
 }
 
+// ---- persistent TMA-fed NT GEMM ------------------------------------------------------------------------------------------
+// gemm_nt_kernel (gemm_nt.cuh) with the operand feed of trmm_sumsq_tma_kernel: 128 x 128 tiles, one CTA per SM that walks the
+// tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of the (batch, tile row, tile column) grid; the (tile, k-tile) items of
+// a CTA form ONE pipeline, so the first k-tiles of the next tile are in flight while the warps store the current one.  Same
+// arguments, flags, dual store and addend as gemm_nt_kernel; per element the same sum in the same order.  Used for the
+// products whose tile count can fill the machine (launch_gemm_nt); the 64 x 64 cp.async kernel keeps the small ones.
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+struct TileWalk {  // position in a CTA's tile sequence
+    int t;         // tile index in the (z, ti, tj) enumeration; >= total: finished
+    int z, i0, j0, kb, ktiles;
+};
+
+template <class Cfg>
+__device__ __forceinline__ void tile_seek(TileWalk& w, const GemmArgs& p, int total, int tiles_m, int tiles_n,
+                                          bool skip_empty) {
+    const int per = tiles_m * tiles_n;
+    while (w.t < total) {
+        const int z = w.t / per, r = w.t - z * per, tj = r % tiles_n;
+        int ti = r / tiles_n;
+        // longest k ranges first, so that the tail of the static round-robin consists of the cheapest tiles: a lower-
+        // triangular A has its longest rows at the bottom (an upper-triangular one at the top: natural order)
+        if (p.flags & GEMM_A_LOWER) ti = tiles_m - 1 - ti;
+        const int i0 = ti * Cfg::BM, j0 = tj * Cfg::BN;
+        const bool live = !((p.flags & GEMM_C_LOWER) && j0 > i0 + Cfg::BM - 1) && !(p.gate && p.gate[z] == 0);
+        if (live) {
+            int kb, ke;
+            tile_k_range(p.flags, i0, j0, Cfg::BM, Cfg::BN, Cfg::BK, p.K, kb, ke);
+            const int kts = (ke - kb) / Cfg::BK;
+            if (kts > 0 || !skip_empty) {
+                w.z = z; w.i0 = i0; w.j0 = j0; w.kb = kb; w.ktiles = kts;
+                return;
+            }
+        }
+        w.t += gridDim.x;
+    }
+}
+
+template <class Cfg, int MODE>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
+    gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, GemmArgs p,
+                       int tiles_m, int tiles_n, int total) {
+    using ML = Mainloop<Cfg>;
+    constexpr int STAGES = Cfg::STAGES, NWARPS = Cfg::THREADS / 32;
+    constexpr uint32_t STAGE_BYTES = Cfg::STAGE_DOUBLES * 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* smem = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    __shared__ __align__(8) uint64_t full[STAGES];
+    __shared__ int left[STAGES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp / Cfg::WN, wn = warp % Cfg::WN;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            left[s] = NWARPS;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // look-ahead walk over the items (tile, k-tile) that are STAGES ahead of the one being consumed
+    TileWalk la{(int)blockIdx.x, 0, 0, 0, 0, 0};
+    int lkt = 0;
+    tile_seek<Cfg>(la, p, total, tiles_m, tiles_n, true);
+    auto issue = [&](int stage) {  // item (la, lkt) -> stage
+        double* sA = smem + stage * Cfg::STAGE_DOUBLES;
+        double* sB = sA + Cfg::BM * Cfg::BK;
+        mbar_expect_tx(&full[stage], STAGE_BYTES);
+        const int k0 = la.kb + lkt * Cfg::BK;
+#pragma unroll
+        for (int pn = 0; pn < Cfg::PANELS; ++pn) {
+            tma_load_3d(sA + pn * Cfg::BM * 8, &mapA, &full[stage], k0 + 8 * pn, la.i0, la.z);
+            tma_load_3d(sB + pn * Cfg::BN * 8, &mapB, &full[stage], k0 + 8 * pn, la.j0, la.z);
+        }
+    };
+    auto la_advance = [&]() {
+        if (la.t >= total) return;
+        if (++lkt == la.ktiles) {
+            lkt = 0;
+            la.t += gridDim.x;
+            tile_seek<Cfg>(la, p, total, tiles_m, tiles_n, true);
+        }
+    };
+    for (int s = 0; s < STAGES; ++s) {
+        if (threadIdx.x == 0 && la.t < total) issue(s);
+        la_advance();
+    }
+
+    constexpr int FSTEP = Cfg::ILV ? 8 * Cfg::WM : 8;
+    constexpr int FLAST = Cfg::frag_row(Cfg::WM - 1, 0);
+    int stage = 0;
+    uint32_t parity = 0;
+    TileWalk cur{(int)blockIdx.x, 0, 0, 0, 0, 0};
+    for (tile_seek<Cfg>(cur, p, total, tiles_m, tiles_n, false); cur.t < total;
+         cur.t += gridDim.x, tile_seek<Cfg>(cur, p, total, tiles_m, tiles_n, false)) {
+        const int i0 = cur.i0, j0 = cur.j0, ktiles = cur.ktiles;
+        double acc[Cfg::MF][Cfg::NF][2];
+#pragma unroll
+        for (int mf = 0; mf < Cfg::MF; ++mf)
+#pragma unroll
+            for (int nf = 0; nf < Cfg::NF; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
+
+        // which k-tiles carry dead fragments (Mainloop::run): TRI_UPPER the first kt_tri, TRI_LOWER those from kt_full on
+        int kt_tri = 0, kt_full = ktiles;
+        if (MODE == TRI_UPPER) {
+            kt_tri = (i0 + (Cfg::MF - 1) * FSTEP - 7 - cur.kb + Cfg::BK - 1) / Cfg::BK;
+            kt_tri = kt_tri < 0 ? 0 : (kt_tri > ktiles ? ktiles : kt_tri);
+        }
+        if (MODE == TRI_LOWER) {
+            const int num = i0 + FLAST + 7 - 8 * (Cfg::PANELS - 1) - cur.kb;
+            kt_full = num < 0 ? 0 : num / Cfg::BK + 1;
+            kt_full = kt_full > ktiles ? ktiles : kt_full;
+        }
+        for (int kt = 0; kt < ktiles; ++kt) {
+            mbar_wait(&full[stage], parity);
+            const double* sA = smem + stage * Cfg::STAGE_DOUBLES;
+            const double* sB = sA + Cfg::BM * Cfg::BK;
+            const int kp0 = cur.kb + kt * Cfg::BK;
+            if (MODE == TRI_UPPER && kt < kt_tri) {
+#pragma unroll
+                for (int pn = 0; pn < Cfg::PANELS; ++pn) {
+                    const int rel = kp0 + 8 * pn + 7 - i0;  // fragment live iff mf * FSTEP <= rel (first warp row)
+                    const int up = rel < 0 ? 0 : rel / FSTEP + 1;
+                    if (up >= Cfg::MF)
+                        ML::mma_panel(acc, sA, sB, pn, wm, wn, g, t);
+                    else
+                        ML::template mma_panel_jump<true>(acc, sA, sB, pn, wm, wn, g, t, up);
+                }
+            } else if (MODE == TRI_LOWER && kt >= kt_full) {
+#pragma unroll
+                for (int pn = 0; pn < Cfg::PANELS; ++pn) {
+                    const int rel = kp0 + 8 * pn - i0 - FLAST - 7;
+                    const int lo = rel <= 0 ? 0 : (rel + FSTEP - 1) / FSTEP;
+                    if (lo == 0)
+                        ML::mma_panel(acc, sA, sB, pn, wm, wn, g, t);
+                    else
+                        ML::template mma_panel_jump<false>(acc, sA, sB, pn, wm, wn, g, t, lo);
+                }
+            } else {
+#pragma unroll
+                for (int pn = 0; pn < Cfg::PANELS; ++pn) ML::mma_panel(acc, sA, sB, pn, wm, wn, g, t);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                const int before = atomicSub(&left[stage], 1);
+                if (before == 1) {
+                    left[stage] = NWARPS;
+                    __threadfence_block();
+                    if (la.t < total) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        issue(stage);
+                    }
+                }
+            }
+            la_advance();
+            if (++stage == STAGES) {
+                stage = 0;
+                parity ^= 1u;
+            }
+        }
+
+        // epilogue of gemm_nt_kernel
+        const int64_t z = cur.z;
+        double* C = p.C ? p.C + z * p.strideC : nullptr;
+        double* Ct = p.Ct ? p.Ct + z * p.strideCt : nullptr;
+        const double* D = p.D ? p.D + z * p.strideD : nullptr;
+#pragma unroll
+        for (int mf = 0; mf < Cfg::MF; ++mf) {
+            const int row = i0 + Cfg::frag_row(wm, mf) + g;
+            if (row >= p.M) continue;
+#pragma unroll
+            for (int nf = 0; nf < Cfg::NF; ++nf) {
+                const int col = j0 + wn * Cfg::WTN + nf * 8 + 2 * t;
+                if (col >= p.N) continue;
+                double v0 = p.alpha * acc[mf][nf][0], v1 = p.alpha * acc[mf][nf][1];
+                if (D) {
+                    const double2 old = *reinterpret_cast<const double2*>(D + (int64_t)row * p.ldd + col);
+                    v0 += old.x;
+                    v1 += old.y;
+                }
+                if (C) *reinterpret_cast<double2*>(C + (int64_t)row * p.ldc + col) = make_double2(v0, v1);
+                if (Ct) {
+                    Ct[(int64_t)col * p.ldct + row] = v0;
+                    Ct[(int64_t)(col + 1) * p.ldct + row] = v1;
+                }
+            }
+        }
+    }
+}
+
 }  // namespace bobe
