@@ -662,3 +662,46 @@ def test_config_e_wipv_full_size():
     err = mixed_err(full[:, idx], ref.fantasy_var_shared(cand, mc[idx]), ref.y_std ** 2)
     print(f"config E fantasy variance vs oracle: {err:.2e}")
     assert err < TOL_VAR
+
+
+def _run_with_env(env, code):
+    """Run a snippet in a fresh interpreter (the native library reads its knobs once per process); returns stdout."""
+    import subprocess
+    import sys
+    e = dict(os.environ)
+    e.update(env)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r.stdout.strip().splitlines()[-1]
+
+
+_KERNEL_VARIANT_SNIPPET = """
+import hashlib, numpy as np, torch
+from bobe_b200 import GP, ops
+from oracle import gp_oracle as O
+X, y = O.synthetic_training_set(1000, 7)
+gp = GP(X, y, kernel="matern", lengthscales=np.full(7, 0.8))
+Xq = torch.as_tensor(O.synthetic_queries(148 * 128 + 4321, 7), device="cuda")
+m, v = gp.predict_mean_var_batched(Xq)
+ref = O.OracleGP(X, y, kernel="matern", lengthscales=np.full(7, 0.8))
+lp = torch.as_tensor(O.synthetic_restarts(ref, 16), device="cuda")
+val, grad, info = ops.mll_grad_batched("matern", gp._X_dev, gp._y_dev, lp, True, 1.0, 1e-8)
+mc = O.synthetic_queries(3000, 7, seed=3)
+w = gp.fantasy_acquisition(mc, O.synthetic_queries(70, 7, seed=4))
+h = hashlib.sha256()
+for a in (m, v, val, grad):
+    h.update(np.nan_to_num(a.cpu().numpy(), nan=-1.0).tobytes())
+h.update(np.asarray(w).tobytes())
+print(h.hexdigest())
+"""
+
+
+def test_kernel_variants_agree_bitwise():
+    """The TMA-fed kernels keep the tiles, fragment ownership and summation order of their cp.async predecessors: the
+    predictive variance (trmm_sumsq_tma_kernel vs trmm_sumsq_kernel), and log-ML / gradient / WIPV values with the
+    persistent TMA GEMM switched on (gemm_nt_tma_kernel vs gemm_nt_kernel), must be bitwise equal."""
+    default = _run_with_env({}, _KERNEL_VARIANT_SNIPPET)
+    assert _run_with_env({"BOBE_TRMM_TMA": "0"}, _KERNEL_VARIANT_SNIPPET) == default
+    assert _run_with_env({"BOBE_GEMM_TMA": "1", "BOBE_GEMM_TMA_MIN_TILES": "1"}, _KERNEL_VARIANT_SNIPPET) == default
+    assert _run_with_env({"BOBE_PDL": "0", "BOBE_MLL_STREAMS": "1"}, _KERNEL_VARIANT_SNIPPET) == default
