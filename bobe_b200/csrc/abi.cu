@@ -439,7 +439,7 @@ extern "C" int32_t bobe_predict(void* stream_, int32_t kind, const double* X, in
 
 // ---- fantasy variance ---------------------------------------------------------------------------------------
 namespace {
-constexpr int64_t MCCHUNK = 16384;
+constexpr int64_t MCCHUNK = 148 * 128;  // MC columns per chunk: one 128-column tile per SM for the TMA trmm route
 struct FantasyLayout {
     double *Kmc, *VT, *base, *Kc, *VcT, *delta2, *G, *kc, *acc, *xs;
     int64_t chunk, cpad, bytes;
@@ -500,6 +500,9 @@ extern "C" int32_t bobe_fantasy_var(void* stream_, int32_t kind, const double* X
         return launch_kmat(stream, kind, a, 1);
     };
     auto apply_linv = [&](const double* Kin, int64_t rows_pad, double* Vout) {  // Vout[j][i] = sum_k Kin[j][k] Linv[i][k]
+        // full chunks: the TMA trmm pipeline (one 128-column tile per SM, V stored instead of squared); bitwise the same V
+        const int32_t rt = launch_trmm_store(stream, Linv, (int)n, (int)npad, Kin, npad, rows_pad, Vout, npad);
+        if (rt <= 0) return rt;
         GemmArgs g{};  // computed as V = Linv * Kin^T with only the transposed store (triangular operand = row operand)
         g.A = Linv; g.Bt = Kin; g.C = nullptr; g.Ct = Vout; g.lda = g.ldb = g.ldct = npad;
         g.M = (int)npad; g.N = (int)rows_pad; g.K = (int)npad; g.alpha = 1.0; g.flags = GEMM_A_LOWER;

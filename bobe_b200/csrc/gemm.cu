@@ -161,6 +161,26 @@ int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& a, int batch) {
     return check_launch("gemm_nt_kernel");
 }
 
+// VT[q][i] = sum_k Linv[i][k] Kin[q][k] for rows_pad (multiple of 128) rows of Kin, through the TMA trmm pipeline (STORE).
+// Returns 1 if this route is not available (the caller then uses launch_gemm_nt), 0 on success, < 0 on error.
+int32_t launch_trmm_store(cudaStream_t stream, const double* Linv, int n, int npad, const double* Kin, int64_t ldk,
+                          int64_t rows_pad, double* VT, int64_t ldv) {
+    using Cfg = CfgTrmm;
+    static const int64_t use_tma = env_int("BOBE_TRMM_TMA", 1);
+    const int64_t qtiles = rows_pad / Cfg::BN;
+    // one 128-query tile per CTA sweeps the whole triangular product: only worth it when the tiles fill the machine
+    if (!use_tma || rows_pad % Cfg::BN || qtiles < (sm_count() * 3) / 4 || ((((uintptr_t)Kin) | ((uintptr_t)Linv)) & 15) || (ldk % 2))
+        return 1;
+    CUtensorMap mapA, mapB;
+    if (!make_panel_map(&mapA, Linv, npad, npad, npad, Cfg::BM) || !make_panel_map(&mapB, Kin, rows_pad, npad, ldk, Cfg::BN))
+        return 1;
+    constexpr int TMA_SMEM = Cfg::SMEM_BYTES + 128;
+    if (int32_t rc = ensure_smem<trmm_sumsq_tma_kernel<Cfg, true>>(TMA_SMEM)) return rc;
+    trmm_sumsq_tma_kernel<Cfg, true><<<(unsigned)qtiles, Cfg::THREADS, TMA_SMEM, stream>>>(mapA, mapB, n, npad, 0, rows_pad, 0.0, 1.0, 0,
+                                                                                         nullptr, VT, ldv);
+    return check_launch("trmm_sumsq_tma_kernel<STORE>");
+}
+
 // var = kk - sum over the row-split partial sums, with the floor / scale semantics of the fused path
 __global__ void __launch_bounds__(256) trmm_finish_kernel(const double* __restrict__ partial, int64_t ld, int split,
                                                           int64_t rows, int64_t q_begin, int64_t M, double kk, double scale,

@@ -42,6 +42,10 @@ int32_t launch_trmm_sumsq(cudaStream_t stream, const double* Linv, int n, int np
                           int64_t rows_pad, int64_t q_begin, int64_t M, double kk, double scale, int standardised,
                           double* var_out, double* partial = nullptr);
 
+// VT = (Linv Kin^T)^T through the TMA trmm pipeline; 1 = route not available (use launch_gemm_nt), 0 = done, < 0 = error
+int32_t launch_trmm_store(cudaStream_t stream, const double* Linv, int n, int npad, const double* Kin, int64_t ldk,
+                          int64_t rows_pad, double* VT, int64_t ldv);
+
 // factorisation (factor.cu) -----------------------------------------------------------------------------
 struct FactorBuffers {
     double* KB;    // (batch, npad, npad) in: K (lower used); out: scratch / K^-1 if requested

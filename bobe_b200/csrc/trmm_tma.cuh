@@ -46,11 +46,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 
-template <class Cfg>
+// STORE = true: the same sweep, but instead of squaring V = Linv K*^T into per-query sums the finished row blocks are written
+// out transposed, VT[q][i] (leading dimension ldv, rows i in [n8, npad) zeroed): the shared solve of the fantasy variance
+// (bobe_fantasy_var), whose K* panel is K(MC, X).  The values are bitwise those of gemm_nt_kernel for the same product.
+template <class Cfg, bool STORE = false>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
     trmm_sumsq_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int n, int npad,
                           int64_t q_begin, int64_t M, double kk, double scale, int standardised,
-                          double* __restrict__ var_out) {
+                          double* __restrict__ var_out, double* __restrict__ vt_out = nullptr, int64_t ldv = 0) {
     using ML = Mainloop<Cfg>;
     constexpr int STAGES = Cfg::STAGES, NWARPS = Cfg::THREADS / 32;
     constexpr uint32_t STAGE_BYTES = Cfg::STAGE_DOUBLES * 8;
@@ -191,13 +194,35 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
                 parity ^= 1u;
             }
         }
+        if (STORE) {  // VT[j0 + col][i0 + row] = acc (rows of a partial first block beyond rows_live belong to block 1)
 #pragma unroll
-        for (int mf = 0; mf < Cfg::MF; ++mf)
+            for (int mf = 0; mf < Cfg::MF; ++mf) {
+                const int r = Cfg::frag_row(wm, mf) + g;
+                if (r >= rows_live) continue;
 #pragma unroll
-            for (int nf = 0; nf < Cfg::NF; ++nf) {
-                colsum[nf][0] = fma(acc[mf][nf][0], acc[mf][nf][0], colsum[nf][0]);
-                colsum[nf][1] = fma(acc[mf][nf][1], acc[mf][nf][1], colsum[nf][1]);
+                for (int nf = 0; nf < Cfg::NF; ++nf) {
+                    const int64_t col = j0 + wn * Cfg::WTN + nf * 8 + 2 * t;
+                    vt_out[col * ldv + i0 + r] = acc[mf][nf][0];
+                    vt_out[(col + 1) * ldv + i0 + r] = acc[mf][nf][1];
+                }
             }
+        } else {
+#pragma unroll
+            for (int mf = 0; mf < Cfg::MF; ++mf)
+#pragma unroll
+                for (int nf = 0; nf < Cfg::NF; ++nf) {
+                    colsum[nf][0] = fma(acc[mf][nf][0], acc[mf][nf][0], colsum[nf][0]);
+                    colsum[nf][1] = fma(acc[mf][nf][1], acc[mf][nf][1], colsum[nf][1]);
+                }
+        }
+    }
+    if (STORE) {  // identity rows of the padded Linv meet zero columns of K*: V is zero there
+        const int tail = npad - n8;
+        for (int idx = threadIdx.x; idx < tail * Cfg::BN; idx += Cfg::THREADS) {
+            const int c = idx / tail, r = idx - c * tail;
+            vt_out[(int64_t)(j0 + c) * ldv + n8 + r] = 0.0;
+        }
+        return;
     }
 #pragma unroll
     for (int nf = 0; nf < Cfg::NF; ++nf)
