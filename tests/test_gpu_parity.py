@@ -705,3 +705,31 @@ def test_kernel_variants_agree_bitwise():
     assert _run_with_env({"BOBE_TRMM_TMA": "0"}, _KERNEL_VARIANT_SNIPPET) == default
     assert _run_with_env({"BOBE_GEMM_TMA": "1", "BOBE_GEMM_TMA_MIN_TILES": "1"}, _KERNEL_VARIANT_SNIPPET) == default
     assert _run_with_env({"BOBE_PDL": "0", "BOBE_MLL_STREAMS": "1"}, _KERNEL_VARIANT_SNIPPET) == default
+
+
+@pytest.mark.parametrize("kernel", ["rbf", "matern"])
+@pytest.mark.parametrize("n,d", [(5, 2), (50, 2), (127, 3), (130, 3), (300, 5), (517, 4)])
+def test_small_training_sets_with_many_queries(kernel, n, d):
+    """The machine-filling routes (TMA trmm pipeline: >= one full chunk of 148 x 128 queries / MC columns) at SMALL n, where the
+    sweep is a single partial row block or ends in one: against the oracle on a sub-sample, against the few-query routes
+    (row-split kernel, matrix-vector path) on the same points, and for the fantasy variance (STORE variant)."""
+    from bobe_b200 import GP
+    X, y = O.synthetic_training_set(n, d, seed=n)
+    ls = np.full(d, 0.35)
+    gp = GP(X, y, kernel=kernel, lengthscales=ls, noise=1e-6)
+    ref = O.OracleGP(X, y, kernel=kernel, lengthscales=ls, noise=1e-6)
+    M = 148 * 128 + 777
+    Xq = O.synthetic_queries(M, d, seed=7)
+    mean, var = gp.predict_mean_batched(Xq), gp.predict_var_batched(Xq)
+    idx = np.random.default_rng(0).choice(M, 300, replace=False)
+    assert mixed_err(mean[idx], ref.predict_mean_batched(Xq[idx]), ref.y_std) < TOL_MEAN
+    assert mixed_err(var[idx], ref.predict_var_batched(Xq[idx]), ref.y_std ** 2) < TOL_VAR
+    few = gp.predict_var_batched(Xq[idx])  # 300 queries: the row-split route
+    assert mixed_err(var[idx], few, ref.y_std ** 2) < 1e-12
+    one = np.array([gp.predict_var_single(x) for x in Xq[idx[:5]]])  # matrix-vector route
+    assert mixed_err(var[idx[:5]], one, ref.y_std ** 2) < 1e-12
+    # fantasy variance over a full chunk of MC columns
+    cand = O.synthetic_queries(6, d, seed=9)
+    fv = gp.fantasy_var(cand, Xq)
+    assert fv.shape == (6, M)
+    assert mixed_err(fv[:, idx], ref.fantasy_var_shared(cand, Xq[idx]), ref.y_std ** 2) < TOL_VAR
