@@ -222,34 +222,34 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
             const int c = idx / tail, r = idx - c * tail;
             vt_out[(int64_t)(j0 + c) * ldv + n8 + r] = 0.0;
         }
-        return;
-    }
+    } else {
 #pragma unroll
-    for (int nf = 0; nf < Cfg::NF; ++nf)
+        for (int nf = 0; nf < Cfg::NF; ++nf)
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            double v = colsum[nf][c];
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            v += __shfl_xor_sync(0xffffffffu, v, 16);
-            if (g == 0) red[wm][wn * Cfg::WTN + nf * 8 + 2 * t + c] = v;
-        }
-    __syncthreads();
-    for (int c = threadIdx.x; c < Cfg::BN; c += Cfg::THREADS) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < Cfg::WM; ++w) s += red[w][c];
-        const int64_t q = q_begin + j0 + c;
-        if (q < M) {
-            double var = kk - s;
-            if (standardised) {
-                if (isnan(var)) var = SAFE_FLOOR;
-                if (var < SAFE_FLOOR) var = SAFE_FLOOR;
-            } else {
-                if (var < SAFE_FLOOR) var = SAFE_FLOOR;
-                var *= scale;
+            for (int c = 0; c < 2; ++c) {
+                double v = colsum[nf][c];
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                if (g == 0) red[wm][wn * Cfg::WTN + nf * 8 + 2 * t + c] = v;
             }
-            var_out[q] = var;
+        __syncthreads();
+        for (int c = threadIdx.x; c < Cfg::BN; c += Cfg::THREADS) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < Cfg::WM; ++w) s += red[w][c];
+            const int64_t q = q_begin + j0 + c;
+            if (q < M) {
+                double var = kk - s;
+                if (standardised) {  // predict_single, BOBE/gp.py:487-488: NaN -> floor, then < floor -> floor
+                    if (isnan(var)) var = SAFE_FLOOR;
+                    if (var < SAFE_FLOOR) var = SAFE_FLOOR;
+                } else {  // predict_var_single, BOBE/gp.py:465-466: clip (NaN propagates), times y_std^2
+                    if (var < SAFE_FLOOR) var = SAFE_FLOOR;
+                    var *= scale;
+                }
+                var_out[q] = var;
+            }
         }
     }
 }
