@@ -12,6 +12,19 @@ constexpr int SLD = 72;  // smem row stride (doubles) of every 64x64 operand: 16
 constexpr int LEAF_THREADS = 256;
 constexpr double REFINE_RATIO = 1e3;
 
+// 1/x on the critical path of every elimination step: MUFU.RCP64H seed (~2^-20) and two Newton steps (4 dependent DFMAs,
+// ~1 ulp), instead of __drcp_rn's five DFMAs plus a denormal / overflow fix-up branch.  A zero, negative, huge or tiny pivot
+// (|x| outside ~[1e-300, 1e300]) gives inf / NaN / a less accurate value: such a matrix is not a valid K anyway and ends as
+// NaN with info = 1 downstream.
+__device__ __forceinline__ double rcp_newton(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
 // ---- 64x64 Cholesky + inverse, register-blocked ----------------------------------------------------------
 // Thread (ty, tx) of a 16x16 grid owns A[ty+16a][tx+16b] and W[ty+16a][tx+16b] (a, b < 4) in REGISTERS for the
 // whole sweep.  Step j: the owners publish column j of A and row j of W to a double-buffered smem line (one
@@ -61,7 +74,7 @@ __device__ __forceinline__ void chol_inv_64(double* A, double* W, double* colb, 
         // roots are taken for all 64 pivots at once after the loop.
         const double ajj = cb[j];
         if (tid == 0) dd[j] = ajj;  // pivot, turned into d_j below
-        const double w = __drcp_rn(ajj);
+        const double w = rcp_newton(ajj);
         double ai[4], ak[4], wj[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
