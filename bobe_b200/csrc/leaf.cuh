@@ -205,18 +205,27 @@ __device__ __forceinline__ void leaf_store(const double* S, double* T, double* G
 // max/min pivot is a lower bound on cond(L); beyond REFINE_RATIO the panel solves get a correction step.
 __device__ __forceinline__ bool leaf_update_stats(const LeafIO& io, const double* dd, int count, int64_t z) {
     __shared__ int s_gate;
-    if (threadIdx.x == 0) {
-        double lo = io.dstat[z * 2], hi = io.dstat[z * 2 + 1];
-        for (int i = 0; i < count; ++i) {
+    if (threadIdx.x < 32) {  // warp 0: min / max of the pivots by shuffles (fmin / fmax skip NaN pivots, as a serial scan would)
+        double lo = 1e300, hi = 0.0;
+        for (int i = threadIdx.x; i < count; i += 32) {
             lo = fmin(lo, dd[i]);
             hi = fmax(hi, dd[i]);
         }
-        io.dstat[z * 2] = lo;
-        io.dstat[z * 2 + 1] = hi;
-        int gte = io.gate[z];
-        if (hi > REFINE_RATIO * lo) gte = 1;
-        io.gate[z] = gte;
-        s_gate = gte;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (threadIdx.x == 0) {
+            lo = fmin(lo, io.dstat[z * 2]);
+            hi = fmax(hi, io.dstat[z * 2 + 1]);
+            io.dstat[z * 2] = lo;
+            io.dstat[z * 2 + 1] = hi;
+            int gte = io.gate[z];
+            if (hi > REFINE_RATIO * lo) gte = 1;
+            io.gate[z] = gte;
+            s_gate = gte;
+        }
     }
     __syncthreads();
     return s_gate != 0;
