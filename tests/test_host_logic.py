@@ -35,6 +35,30 @@ def test_abi_library_exports_every_declared_symbol():
     assert _lib.lib.bobe_predict_workspace_bytes(2000, 16, 10**6, 3) == (3 * 148 * 128 + 16) * 2048 * 8 + 32 * 148 * 128 * 8 + 512
 
 
+def test_ctypes_table_matches_the_header_argument_lists():
+    """Every prototype of include/bobe_b200.h against the ctypes signature in bobe_b200/_lib.py: same number of arguments,
+    same kinds (pointer / int32 / int64 / double) in the same order, same return type."""
+    import ctypes as C
+    from bobe_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "bobe_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = re.findall(r"\b(const char\*|int32_t|int64_t)\s+(bobe_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr)
+    assert len(protos) == len(_lib.SIGNATURES)
+
+    def kind(decl):
+        decl = decl.strip()
+        if "*" in decl:
+            return C.c_void_p
+        return {"int32_t": C.c_int32, "int64_t": C.c_int64, "double": C.c_double}[decl.split()[0]]
+
+    ret = {"const char*": C.c_char_p, "int32_t": C.c_int32, "int64_t": C.c_int64}
+    for rtype, name, args in protos:
+        res, argtypes = _lib.SIGNATURES[name]
+        assert res is ret[rtype], name
+        want = [] if args.strip() in ("", "void") else [kind(a) for a in args.split(",")]
+        assert want == list(argtypes), (name, want, argtypes)
+
+
 def test_abi_argument_errors_without_a_gpu():
     from bobe_b200._lib import lib
     rc = lib.bobe_kernel_matrix(None, 0, None, 4, None, 4, 2, None, 1.0, 0.0, 0, None, 4)
