@@ -47,7 +47,8 @@ struct Rec {
         if (rc != BOBE_OK) return;
         int nb = b1 - b0;
         if (nb <= 2) {  // leaf: one CTA per matrix does the whole 64- or 128-block in shared memory
-            LeafIO io{fb.KB, fb.L, fb.Lt, fb.Linv, fb.U, fb.diag, fb.dstat, fb.gate, npad, b0 * NB};
+            static const int panel4 = (int)env_int("BOBE_LEAF_PANEL4", 1);
+            LeafIO io{fb.KB, fb.L, fb.Lt, fb.Linv, fb.U, fb.diag, fb.dstat, fb.gate, npad, b0 * NB, panel4};
             if (nb == 1) {
                 if ((rc = ensure_smem<leaf64_kernel>(LEAF64_SMEM)) != BOBE_OK) return;
                 launch_pdl(leaf64_kernel, dim3(1, 1, batch), dim3(LEAF_THREADS), LEAF64_SMEM, stream, io);

@@ -113,6 +113,129 @@ __device__ __forceinline__ void chol_inv_64(double* A, double* W, double* colb, 
     __syncthreads();
 }
 
+// ---- the same elimination, FOUR columns per barrier ----------------------------------------------------------------------
+// chol_inv_64 pays a publish -> barrier -> reciprocal -> update chain of ~850 cycles for every column.  Here the owners
+// publish the four columns j0 .. j0+3 of A (and the four rows of W) as they are BEFORE the panel, and every thread replays
+// the three intra-panel eliminations on the few published entries it needs (the 4 x 4 diagonal block, the panel entries of
+// its four rows and of its four columns, the panel rows of W at its four columns) before applying the four rank-1 updates
+// to its own 4 x 4 blocks.  Every element sees exactly the operations of chol_inv_64 in the same order, so the results are
+// bitwise identical; the number of block-wide barriers drops from 64 to 16 and the reciprocals of a panel no longer wait
+// for a round trip through shared memory.
+__device__ __forceinline__ void chol_inv_64_panel4(double* A, double* W, double* colb, double* rowb, double* invd,
+                                                   double* dd) {
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    double ra[4][4], rw[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            int i = ty + 16 * a, k = tx + 16 * b;
+            ra[a][b] = A[i * SLD + k];
+            rw[a][b] = (i == k) ? 1.0 : 0.0;
+        }
+    // colb / rowb: [2][4][64] (double-buffered by panel parity)
+    for (int j0 = 0; j0 < 64; j0 += 4) {
+        const int ja = j0 >> 4, jx0 = j0 & 15;
+        double* cb = colb + ((j0 >> 2) & 1) * 256;
+        double* rb = rowb + ((j0 >> 2) & 1) * 256;
+        if (tx >= jx0 && tx < jx0 + 4) {  // my column tx + 16 ja is panel column tx - jx0
+            double* dst = cb + (tx - jx0) * 64;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                double v = ra[a][0];
+                v = (ja == 1) ? ra[a][1] : v;
+                v = (ja == 2) ? ra[a][2] : v;
+                v = (ja == 3) ? ra[a][3] : v;
+                dst[ty + 16 * a] = v;
+            }
+        }
+        if (ty >= jx0 && ty < jx0 + 4) {  // my row ty + 16 ja is panel row ty - jx0
+            double* dst = rb + (ty - jx0) * 64;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                double v = rw[0][b];
+                v = (ja == 1) ? rw[1][b] : v;
+                v = (ja == 2) ? rw[2][b] : v;
+                v = (ja == 3) ? rw[3][b] : v;
+                dst[tx + 16 * b] = v;
+            }
+        }
+        __syncthreads();
+        double D[4][4], Ri[4][4], Ck[4][4], Wp[4][4];  // [.][jj]: panel column jj;  Wp[jj][b]: panel row jj at my column b
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                D[m][jj] = cb[jj * 64 + j0 + m];
+                Ri[m][jj] = cb[jj * 64 + ty + 16 * m];
+                Ck[m][jj] = cb[jj * 64 + tx + 16 * m];
+                Wp[jj][m] = rb[jj * 64 + tx + 16 * m];
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = j0 + jj;
+            const double ajj = D[jj][jj];
+            if (tid == 0) dd[j] = ajj;
+            const double w = rcp_newton(ajj);
+            double ai[4], ak[4], wj[4], dm[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                ai[m] = (ty + 16 * m > j) ? Ri[m][jj] * w : 0.0;
+                ak[m] = (tx + 16 * m > j) ? Ck[m][jj] : 0.0;
+                wj[m] = Wp[jj][m];
+                dm[m] = (m > jj) ? D[m][jj] * w : 0.0;  // multiplier of panel row j0 + m
+            }
+            // replay column j on the rest of the panel (the entries other threads will publish as columns j+1 ..)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                if (kk <= jj) continue;
+                const double dk = D[kk][jj];  // A[j0 + kk][j], k > j
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    Ri[m][kk] = fma(-ai[m], dk, Ri[m][kk]);
+                    const double ci = (tx + 16 * m > j) ? Ck[m][jj] * w : 0.0;  // as a ROW entry of the element (k_b, j0+kk)
+                    Ck[m][kk] = fma(-ci, dk, Ck[m][kk]);
+                    if (m > jj) D[m][kk] = fma(-dm[m], dk, D[m][kk]);
+                }
+            }
+#pragma unroll
+            for (int mm = 0; mm < 4; ++mm) {
+                if (mm <= jj) continue;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) Wp[mm][b] = fma(-dm[mm], wj[b], Wp[mm][b]);
+            }
+            // my own blocks
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    ra[a][b] = fma(-ai[a], ak[b], ra[a][b]);
+                    rw[a][b] = fma(-ai[a], wj[b], rw[a][b]);
+                }
+        }
+    }
+    __syncthreads();
+    if (tid < 64) {
+        const double piv = dd[tid];
+        double r0 = rsqrt(piv);
+        double d0 = piv * r0;
+        double d = fma(fma(-d0, d0, piv), 0.5 * r0, d0);
+        invd[tid] = fma(fma(-d, r0, 1.0), r0, r0);
+        dd[tid] = d;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            int i = ty + 16 * a, k = tx + 16 * b;
+            A[i * SLD + k] = (k < i) ? ra[a][b] * invd[k] : (k == i ? dd[i] : 0.0);
+            W[i * SLD + k] = (k <= i) ? rw[a][b] * invd[i] : 0.0;
+        }
+    __syncthreads();
+}
+
 // ---- 64x64x64 product on smem operands with DMMA: C = alpha * A * op(B) + D -------------------------------
 // op(B)[k][j] = B[j][k] (BT, "NT") or B[k][j] (NN).  D may be null or alias C (each element is read and
 // written by the same thread).  8 warps: warp w owns rows 16*(w&3).., columns 32*(w>>2)...
@@ -169,7 +292,15 @@ struct LeafIO {
     double *L, *Lt, *Linv, *U, *diag, *dstat;
     int* gate;
     int npad, o;  // o = first row/column of the block
+    int panel4;   // 1: chol_inv_64_panel4 (four columns per barrier), 0: chol_inv_64
 };
+__device__ __forceinline__ void chol_inv_64_any(int panel4, double* A, double* W, double* colb, double* rowb, double* invd,
+                                                double* dd) {
+    if (panel4)
+        chol_inv_64_panel4(A, W, colb, rowb, invd, dd);
+    else
+        chol_inv_64(A, W, colb, rowb, invd, dd);
+}
 
 // global -> smem: 64x64 block at (row r0, col c0) of KB, as 16-byte cp.async copies (all blocks of a leaf are issued
 // back to back and waited for once, so the leaf pays ONE global-load latency instead of one per element batch).
@@ -237,9 +368,9 @@ __global__ void __launch_bounds__(LEAF_THREADS) leaf64_kernel(LeafIO io) {
     pdl_trigger();
     double* A = sm;
     double* W = A + 64 * SLD;
-    double* colb = W + 64 * SLD;  // [2][64]
-    double* rowb = colb + 128;    // [2][64]
-    double* invd = rowb + 128;    // [64]
+    double* colb = W + 64 * SLD;  // [2][4][64]
+    double* rowb = colb + 512;    // [2][4][64]
+    double* invd = rowb + 512;    // [64]
     double* dd = invd + 64;       // [64]
     const int64_t z = blockIdx.z, zoff = z * (int64_t)io.npad * io.npad;
     double* T = dd + 64;          // [64][TLD] transpose staging
@@ -247,13 +378,13 @@ __global__ void __launch_bounds__(LEAF_THREADS) leaf64_kernel(LeafIO io) {
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    chol_inv_64(A, W, colb, rowb, invd, dd);
+    chol_inv_64_any(io.panel4, A, W, colb, rowb, invd, dd);
     leaf_store(A, T, io.L + zoff, io.Lt + zoff, io.npad, io.o, io.o);
     leaf_store(W, T, io.Linv + zoff, io.U + zoff, io.npad, io.o, io.o);
     if (threadIdx.x < 64) io.diag[z * io.npad + io.o + threadIdx.x] = dd[threadIdx.x];
     leaf_update_stats(io, dd, 64, z);
 }
-constexpr int LEAF64_SMEM = (2 * 64 * SLD + 2 * 128 + 2 * 64 + 64 * TLD) * 8;
+constexpr int LEAF64_SMEM = (2 * 64 * SLD + 2 * 512 + 2 * 64 + 64 * TLD) * 8;
 
 // 128x128 block = [A11 .; A21 A22]:
 //   (L11, X11) = chol_inv(A11);  L21 = A21 X11^T [+ gated correction];  A22 -= L21 L21^T;
@@ -268,9 +399,9 @@ __global__ void __launch_bounds__(LEAF_THREADS) leaf128_kernel(LeafIO io) {
     double* B3 = B2 + 64 * SLD;   // A22 -> L22
     double* B4 = B3 + 64 * SLD;   // X22
     double* B5 = B4 + 64 * SLD;   // L21 -> X21
-    double* colb = B5 + 64 * SLD;
-    double* rowb = colb + 128;
-    double* invd = rowb + 128;    // [128]
+    double* colb = B5 + 64 * SLD;  // [2][4][64]
+    double* rowb = colb + 512;     // [2][4][64]
+    double* invd = rowb + 512;     // [128]
     double* dd = invd + 128;      // [128]
     const int64_t z = blockIdx.z, zoff = z * (int64_t)io.npad * io.npad;
     const int o = io.o, npad = io.npad;
@@ -281,7 +412,7 @@ __global__ void __launch_bounds__(LEAF_THREADS) leaf128_kernel(LeafIO io) {
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    chol_inv_64(B0, B1, colb, rowb, invd, dd);
+    chol_inv_64_any(io.panel4, B0, B1, colb, rowb, invd, dd);
     const bool refine = leaf_update_stats(io, dd, 64, z);
     mma64<true>(B2, B1, 1.0, B5, nullptr);  // L21 = A21 X11^T
     __syncthreads();
@@ -294,7 +425,7 @@ __global__ void __launch_bounds__(LEAF_THREADS) leaf128_kernel(LeafIO io) {
     mma64<true>(B5, B5, -1.0, B3, B3);  // A22 -= L21 L21^T
     __syncthreads();
     leaf_store(B5, B2, io.L + zoff, io.Lt + zoff, npad, o + 64, o);  // L21 (B2 = A21 / residual is dead: staging)
-    chol_inv_64(B3, B4, colb, rowb, invd + 64, dd + 64);
+    chol_inv_64_any(io.panel4, B3, B4, colb, rowb, invd + 64, dd + 64);
     leaf_update_stats(io, dd + 64, 64, z);
     mma64<false>(B4, B5, 1.0, B2, nullptr);  // T = X22 L21
     __syncthreads();
@@ -308,6 +439,6 @@ __global__ void __launch_bounds__(LEAF_THREADS) leaf128_kernel(LeafIO io) {
     leaf_store(B5, B2, io.Linv + zoff, io.U + zoff, npad, o + 64, o);
     if (threadIdx.x < 128) io.diag[z * npad + o + threadIdx.x] = dd[threadIdx.x];
 }
-constexpr int LEAF128_SMEM = (6 * 64 * SLD + 2 * 128 + 2 * 128) * 8;
+constexpr int LEAF128_SMEM = (6 * 64 * SLD + 2 * 512 + 2 * 128) * 8;
 
 }  // namespace bobe
