@@ -143,8 +143,11 @@ class EI(AcquisitionFunction):
         xq = _to_dev(x, gp.device)
         if xq.dim() == 1:
             xq = xq[None, :]
-        mean, var = ops.predict(gp.kernel_name, gp._X_dev, gp._ls_dev, float(gp.kernel_variance), float(gp.noise),
-                                gp._Linv_dev, gp._alpha_dev, xq, float(gp.y_mean), float(gp.y_std), True, True, True)
+        if xq.shape[1] != gp.ndim:
+            raise ValueError(f"query points must have {gp.ndim} columns")
+        # gp.predict_single semantics (BOBE/acquisition.py:246,323), through the GP's own device path so that a
+        # GPwithClassifier applies its feasibility mask (BOBE/clf_gp.py:197-205)
+        mean, var = gp._predict_dev(xq, True, True, True)
         out = ops.acq_ei(self._which, mean, var, float(best_y), float(zeta))
         return out if as_t else out.cpu().numpy()
 

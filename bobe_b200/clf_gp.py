@@ -128,6 +128,27 @@ class GPwithClassifier(GP):
                          self.minus_inf, SAFE_NOISE_FLOOR)
         return mean, var
 
+    def predict_grad_batched(self, x, standardised=False, want_mean=True, want_var=True):
+        """``jax.value_and_grad`` of the MASKED ``predict_*_single`` (BOBE/clf_gp.py:173-205): where the classifier
+        excludes the point the value is the fill (``minus_inf`` / ``safe_noise_floor``) and -- ``jnp.where`` passing no
+        gradient through a constant branch -- its input gradient is zero."""
+        out = super().predict_grad_batched(x, standardised, want_mean, want_var)
+        if not self._clf_active():
+            return out
+        if not (0.0 < self.probability_threshold <= 1.0):
+            raise ValueError("probability_threshold must be in (0, 1] for the 0/1 SVM probabilities")
+        as_np = not _is_t(x)
+        dec = self.clf_decision(x if _is_t(x) else np.atleast_2d(np.asarray(x, dtype=np.float64)))
+        bad = (dec < 0.0) if as_np else (dec.to(out[0].device if out[0] is not None else out[1].device) < 0.0)
+        mean, var, dmean, dvar = out
+        fix = (lambda a, fill: np.where(bad.reshape((-1,) + (1,) * (a.ndim - 1)), fill, a)) if as_np else \
+              (lambda a, fill: torch.where(bad.reshape((-1,) + (1,) * (a.dim() - 1)), torch.as_tensor(fill, dtype=a.dtype, device=a.device), a))
+        if mean is not None:
+            mean, dmean = fix(mean, self.minus_inf), fix(dmean, 0.0)
+        if var is not None:
+            var, dvar = fix(var, SAFE_NOISE_FLOOR), fix(dvar, 0.0)
+        return mean, var, dmean, dvar
+
     # ---- data ------------------------------------------------------------------------------------------------------
     def update(self, new_x, new_y):
         """BOBE/clf_gp.py:214-246 -- append to the classifier set, re-select the GP set, re-factorise."""

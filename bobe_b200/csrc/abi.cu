@@ -268,7 +268,12 @@ extern "C" int32_t bobe_factorize(void* stream_, int32_t kind, const double* X, 
     ka.ls_stride = d; ka.out_stride = (int64_t)npad * npad; ka.noise = noise; ka.add_noise = 1; ka.pad_identity = 1;
     ka.lower_only = 1;  // the factorisation reads the lower triangle only
     if (int32_t rc = launch_kmat(stream, kind, ka, (int)batch)) return rc;
-    if (int32_t rc = factor_recursive(stream, fb, npad, (int)batch)) return rc;
+    {
+        StreamPool* pool = stream_pool();
+        if (!pool) return BOBE_E_CUDA;
+        std::lock_guard<std::mutex> pool_lock(pool->enqueue_mu);
+        if (int32_t rc = factor_any(stream, pool, 0, fb, npad, (int)batch)) return rc;
+    }
     SolveArgs sa{kind, X, ls, kv, d, noise, l.xs};
     return launch_solve_vectors(stream, fb, sa, y, n, npad, (int)batch, l.z, alpha ? alpha : l.alpha, logdet, quad,
                                 info);

@@ -40,6 +40,36 @@ inline int32_t ensure_smem(int bytes) {
     return BOBE_OK;
 }
 
+// same, for a kernel given as a function-pointer VALUE (one static slot per distinct kernel type + first pointer seen;
+// used where the kernel is picked at run time between a few instantiations of one signature)
+template <class... KArgs>
+inline int32_t ensure_smem_fn(void (*kernel)(KArgs...), int bytes) {
+    struct Slot { void* fn; std::atomic<int> have[64]; };
+    static Slot slots[8];
+    static std::atomic<int> nslots{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    const int n = nslots.load(std::memory_order_acquire);
+    for (int i = 0; i < n; ++i)
+        if (slots[i].fn == (void*)kernel && slots[i].have[dev].load(std::memory_order_relaxed) >= bytes) return BOBE_OK;
+    cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(smem=%d): %s", bytes, cudaGetErrorString(e));
+        return BOBE_E_CUDA;
+    }
+    for (int i = 0; i < n; ++i)
+        if (slots[i].fn == (void*)kernel) {
+            slots[i].have[dev].store(bytes, std::memory_order_relaxed);
+            return BOBE_OK;
+        }
+    const int idx = nslots.fetch_add(1);
+    if (idx < 8) {  // a racing duplicate entry is harmless (the attribute call is idempotent)
+        slots[idx].fn = (void*)kernel;
+        slots[idx].have[dev].store(bytes, std::memory_order_relaxed);
+    }
+    return BOBE_OK;
+}
+
 // ---- programmatic dependent launch (PDL) --------------------------------------------------------------------
 // The factorisation is a chain of ~230 dependent launches; with the launch attribute below the next kernel of the chain
 // is made resident while the previous one drains and parks at pdl_wait() until that one has completed and flushed.
@@ -198,7 +228,10 @@ __device__ __forceinline__ void exp_nonpos_n(const double (&x)[N], double (&res)
         // x < -707.7 decided on the high word (x <= 0, so a larger unsigned high word is a larger magnitude);
         // 0xC0861D99 is the high word of -707.7 and the low word's 2^-20 relative slack is immaterial (both sides of
         // the threshold give a normal, correctly scaled result down to x = -708.3)
-        const bool under = (unsigned)__double2hiint(x[j]) > 0xC0861D99u;
+        // (a NaN argument has a high word >= 0xFFF00000 or, positive, < 0x80000000: it must NOT read as "under" -- it falls
+        // through to the polynomial, whose result is NaN, as exp_nonpos and the reference's jnp.exp give)
+        const unsigned hx = (unsigned)__double2hiint(x[j]);
+        const bool under = hx > 0xC0861D99u && hx <= 0xFFF00000u && !(hx == 0xFFF00000u && __double2loint(x[j]) != 0);
         const int hi = __double2hiint(p[j]) + (n[j] << 20);
         res[j] = __hiloint2double(under ? 0 : hi, under ? 0 : __double2loint(p[j]));
     }

@@ -24,9 +24,9 @@ __global__ void init_stat_kernel(double* dstat, int* gate, int batch, int force)
     }
 }
 
-int64_t factor_q_elems(int64_t npad) {
+int64_t factor_q_elems(int64_t npad) {  // >= npad^2 / 4 (inverse tree, phase 2) and >= 128 npad (panel correction)
     int64_t m = ((npad / NB + 1) / 2) * NB;
-    return m * m;
+    return m * m > 128 * npad ? m * m : 128 * npad;
 }
 
 namespace {
@@ -131,14 +131,18 @@ __global__ void zero_other_triangle_kernel(double* L, double* Lt, double* Linv, 
     }
     if (rb == cb) return;
     double* lo0 = (cb > rb) ? L : Lt;     // L, Linv: zero where col block > row block
-    double* lo1 = (cb > rb) ? Linv : U;   // Lt, U: zero where col block < row block
+    double* lo1 = (cb > rb) ? Linv : U;   // Lt, U: zero where col block < row block   (null: buffer not kept)
     for (int idx = threadIdx.x; idx < NB * NB; idx += blockDim.x) {
         int r = idx >> 6, c = idx & 63;
         int64_t off = zoff + (int64_t)(rb * NB + r) * npad + cb * NB + c;
-        lo0[off] = 0.0;
-        lo1[off] = 0.0;
+        if (lo0) lo0[off] = 0.0;
+        if (lo1) lo1[off] = 0.0;
     }
 }
+
+}  // namespace bobe
+#include "factor_tiled.cuh"
+namespace bobe {
 
 int32_t factor_recursive(cudaStream_t stream, const FactorBuffers& fb, int npad, int batch) {
     if (npad % NB) {
@@ -157,6 +161,25 @@ int32_t factor_recursive(cudaStream_t stream, const FactorBuffers& fb, int npad,
     Rec r{stream, fb, npad, batch, (int64_t)npad * npad, factor_q_elems(npad)};
     r.run(0, nbk);
     return r.rc;
+}
+
+// Which scheme factorises: BOBE_FACTOR = 1 (default) the tile-column scheme of factor_tiled.cuh, 0 the recursive one above
+// (kept for A/B measurements; needs fb.Lt).  Look-ahead on a second stream is used for sub-batches of at most
+// BOBE_LOOKAHEAD_MAX matrices: a larger sub-batch fills the machine by itself and the sub-batches overlap each other.
+int32_t factor_any(cudaStream_t stream, StreamPool* pool, int lane, const FactorBuffers& fb, int npad, int batch) {
+    static const int64_t scheme = env_int("BOBE_FACTOR", 1);
+    if (scheme == 0) {
+        if (!fb.Lt) {
+            set_error("factor: the recursive scheme needs the Lt buffer");
+            return BOBE_E_ARG;
+        }
+        return factor_recursive(stream, fb, npad, batch);
+    }
+    static const int64_t la_max = env_int("BOBE_LOOKAHEAD_MAX", 16);
+    static const int64_t pw = env_int("BOBE_FACTOR_PW", 4);  // tile columns per outer panel (the same for every batch size)
+    const bool la = pool && batch <= la_max && lane >= 0 && 2 * lane + 1 < POOL_STREAMS;
+    FactorExec ex{stream, la ? pool->streams[2 * lane + 1] : nullptr, pool, lane < 0 ? 0 : lane, (int)pw};
+    return factor_tiled(ex, fb, npad, batch);
 }
 
 int32_t launch_kinv(cudaStream_t stream, const FactorBuffers& fb, int npad, int batch) {

@@ -113,7 +113,7 @@ int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& a, int batch) {
     // Products whose 128 x 128 tiles can fill the machine: the persistent TMA kernel (trmm_tma.cuh)
     static const int64_t tma_gemm = env_int("BOBE_GEMM_TMA", 0);
     static const int64_t tma_min_tiles = env_int("BOBE_GEMM_TMA_MIN_TILES", 2);  // live tiles per SM
-    if (tma_gemm && !forced && a.M >= 256 && a.N >= 256 && a.K >= 128 && ((((uintptr_t)a.A) | ((uintptr_t)a.Bt)) & 15) == 0 &&
+    if (tma_gemm && !forced && a.node_count == 0 && a.M >= 256 && a.N >= 256 && a.K >= 128 && ((((uintptr_t)a.A) | ((uintptr_t)a.Bt)) & 15) == 0 &&
         (a.strideA % 2) == 0 && (a.strideB % 2) == 0) {
         using Cfg = CfgBig;
         const int tiles_m = (a.M + Cfg::BM - 1) / Cfg::BM, tiles_n = (a.N + Cfg::BN - 1) / Cfg::BN;
@@ -140,7 +140,7 @@ int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& a, int batch) {
         using Cfg = decltype(cfg);
         constexpr int MODE = decltype(mode_c)::value;
         if (int32_t rc = ensure_smem<gemm_nt_kernel<Cfg, MODE>>(Cfg::SMEM_BYTES)) return rc;
-        dim3 grid((a.N + Cfg::BN - 1) / Cfg::BN, (a.M + Cfg::BM - 1) / Cfg::BM, batch);
+        dim3 grid((a.N + Cfg::BN - 1) / Cfg::BN, (a.M + Cfg::BM - 1) / Cfg::BM, batch * (a.node_count > 0 ? a.node_count : 1));
         if (launch_pdl(gemm_nt_kernel<Cfg, MODE>, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, a) != cudaSuccess) {
             set_error("gemm_nt: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             return BOBE_E_CUDA;

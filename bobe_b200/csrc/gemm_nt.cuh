@@ -331,6 +331,13 @@ struct GemmArgs {
     int M, N, K;
     double alpha;
     int flags;
+    // "Node mode" (node_count > 0): one launch serves the same step of ALL nodes of one level of the triangular-inverse
+    // tree (factor.cu, phase 2).  grid.z = batch * node_count; node t covers rows/columns [2 m t, 2 m t + 2 m) of the
+    // npad x npad matrices, m = node_m, its second half clipped to m2 = min(m, node_total - 2 m t - m) rows (nodes
+    // with m2 <= 0 do nothing).  The operands are located from the matrix BASE pointers:
+    //   node_kind 1:  P^T = U11 L21^T      A = U (upper),  Bt = L,  C = scratch [t m^2 ..), row length m2
+    //   node_kind 2:  X21 = -X22 P         A = Linv (lower), Bt = scratch,  C = Linv,  Ct = U
+    int node_count, node_m, node_total, node_kind;
 };
 
 // Batched NT GEMM with optional dual (normal + transposed) store.  grid = (tiles_n, tiles_m, batch).
@@ -344,12 +351,42 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_kernel(GemmAr
     pdl_trigger();  // the next launch of the chain may become resident as soon as all CTAs of this one have started
     const int i0 = blockIdx.y * Cfg::BM, j0 = blockIdx.x * Cfg::BN;
     if ((p.flags & GEMM_C_LOWER) && j0 > i0 + Cfg::BM - 1) return;
-    const int64_t z = blockIdx.z;
+    int64_t z = blockIdx.z;
+    const double* A = p.A;
+    const double* Bt = p.Bt;
+    double* C = p.C;
+    double* Ct = p.Ct;
+    int M = p.M, N = p.N, K = p.K;
+    int64_t ldb = p.ldb, ldc = p.ldc;
+    if (p.node_count > 0) {
+        const int t = (int)(z % p.node_count);
+        z /= p.node_count;
+        const int m = p.node_m;
+        const int64_t o = 2 * (int64_t)m * t;
+        const int64_t rem = (int64_t)p.node_total - o - m;
+        const int m2 = rem < m ? (int)rem : m;
+        if (m2 <= 0) return;
+        if (p.node_kind == 1) {
+            A += o * p.lda + o;
+            Bt += (o + m) * p.ldb + o;
+            C += (int64_t)t * m * m;
+            ldc = m2;
+            M = m; N = m2; K = m;
+        } else {
+            A += (o + m) * (p.lda + 1);
+            Bt += (int64_t)t * m * m;
+            ldb = m2;
+            C += (o + m) * p.ldc + o;
+            Ct += o * p.ldct + (o + m);
+            M = m2; N = m; K = m2;
+        }
+        if (i0 >= M || j0 >= N) return;
+    }
     if (p.gate && p.gate[z] == 0) return;
-    const double* A = p.A + z * p.strideA + (int64_t)i0 * p.lda;
-    const double* Bt = p.Bt + z * p.strideB + (int64_t)j0 * p.ldb;
+    A += z * p.strideA + (int64_t)i0 * p.lda;
+    Bt += z * p.strideB + (int64_t)j0 * ldb;
     int kb, ke;
-    tile_k_range(p.flags, i0, j0, Cfg::BM, Cfg::BN, Cfg::BK, p.K, kb, ke);
+    tile_k_range(p.flags, i0, j0, Cfg::BM, Cfg::BN, Cfg::BK, K, kb, ke);
 
     double acc[Cfg::MF][Cfg::NF][2];
 #pragma unroll
@@ -357,30 +394,29 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_kernel(GemmAr
 #pragma unroll
         for (int nf = 0; nf < Cfg::NF; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
 
-    Mainloop<Cfg>::template run<MODE>(acc, A, p.lda, min(Cfg::BM, p.M - i0), Bt, p.ldb, min(Cfg::BN, p.N - j0), kb, ke, smem,
-                                      i0);
+    Mainloop<Cfg>::template run<MODE>(acc, A, p.lda, min(Cfg::BM, M - i0), Bt, ldb, min(Cfg::BN, N - j0), kb, ke, smem, i0);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp / Cfg::WN, wn = warp % Cfg::WN;
-    double* C = p.C ? p.C + z * p.strideC : nullptr;
-    double* Ct = p.Ct ? p.Ct + z * p.strideCt : nullptr;
+    C = C ? C + z * p.strideC : nullptr;
+    Ct = Ct ? Ct + z * p.strideCt : nullptr;
     const double* D = p.D ? p.D + z * p.strideD : nullptr;
 #pragma unroll
     for (int mf = 0; mf < Cfg::MF; ++mf) {
         int row = i0 + Cfg::frag_row(wm, mf) + g;
-        if (row >= p.M) continue;
+        if (row >= M) continue;
 #pragma unroll
         for (int nf = 0; nf < Cfg::NF; ++nf) {
             int col = j0 + wn * Cfg::WTN + nf * 8 + 2 * t;
-            if (col >= p.N) continue;  // N is even, so col+1 < N too
+            if (col >= N) continue;  // N is even, so col+1 < N too
             double v0 = p.alpha * acc[mf][nf][0], v1 = p.alpha * acc[mf][nf][1];
             if (D) {
                 double2 old = *reinterpret_cast<const double2*>(D + (int64_t)row * p.ldd + col);
                 v0 += old.x;
                 v1 += old.y;
             }
-            if (C) *reinterpret_cast<double2*>(C + (int64_t)row * p.ldc + col) = make_double2(v0, v1);
+            if (C) *reinterpret_cast<double2*>(C + (int64_t)row * ldc + col) = make_double2(v0, v1);
             if (Ct) {
                 Ct[(int64_t)col * p.ldct + row] = v0;
                 Ct[(int64_t)(col + 1) * p.ldct + row] = v1;

@@ -1,5 +1,8 @@
 // Internal launcher declarations shared between translation units.
 #pragma once
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace bobe {
@@ -61,6 +64,30 @@ struct FactorBuffers {
     int zero_band;  // 0: zero the whole other triangle (L / Linv handed to the caller); 2: internal use only
 };
 int64_t factor_q_elems(int64_t npad);
+
+// internal side streams + dependency events (one pool per device, created on first use)
+constexpr int POOL_STREAMS = 16;
+struct StreamPool {
+    cudaStream_t streams[POOL_STREAMS];
+    cudaEvent_t fork, join[POOL_STREAMS];
+    std::vector<cudaEvent_t> ring[POOL_STREAMS];  // per-lane dependency events, created on demand
+    std::mutex enqueue_mu;  // the events are shared: one host thread enqueues on the pool at a time
+    cudaEvent_t event(int lane, int idx);
+};
+StreamPool* stream_pool();
+
+// where one factorisation chain runs: `crit` carries the dependent chain; `bulk` (optional, with pool / lane for its
+// events) the look-ahead products.  pw = tile columns per outer panel (factor_tiled.cuh).
+struct FactorExec {
+    cudaStream_t crit;
+    cudaStream_t bulk;
+    StreamPool* pool;
+    int lane;
+    int pw;
+};
+int32_t factor_tiled(const FactorExec& ex, const FactorBuffers& fb, int npad, int batch);
+// scheme dispatch (BOBE_FACTOR knob); pool may be null (no look-ahead), lane selects the pool streams / events used
+int32_t factor_any(cudaStream_t stream, StreamPool* pool, int lane, const FactorBuffers& fb, int npad, int batch);
 int32_t factor_recursive(cudaStream_t stream, const FactorBuffers& fb, int npad, int batch);
 int32_t launch_kinv(cudaStream_t stream, const FactorBuffers& fb, int npad, int batch);  // KB <- U U^T (lower 128-tiles)
 struct SolveArgs {  // what the alpha refinement needs to rebuild K alpha

@@ -441,4 +441,372 @@ __global__ void __launch_bounds__(LEAF_THREADS) leaf128_kernel(LeafIO io) {
 }
 constexpr int LEAF128_SMEM = (6 * 64 * SLD + 2 * 512 + 2 * 128) * 8;
 
+// ==== recursive leaf: 32 x 32 elimination blocks joined by DMMA products =================================================
+// chol_inv_64_panel4 runs 64 rank-1 updates over the WHOLE 64 x 64 block (both triangles, finished rows included):
+// ~4x the useful FP64 work, all of it on one SM, which makes the leaf throughput-bound (~20 us per 64-block).  Here the
+// elimination only runs on 32 x 32 diagonal blocks (a quarter of the elements, half the steps each) and the blocks are
+// joined by small tensor-core products that skip the zero halves of their triangular operands:
+//   (L11, X11) = chol_inv_32(A11);  L21 = A21 X11^T (+ one correction step, always);  A22 -= L21 L21^T;
+//   (L22, X22) = chol_inv_32(A22);  X21 = -(X22 L21) X11
+
+// C(N x N) = alpha * A * op(B) + D on smem operands of row stride SLD, N = 32 or 64, 8 warps.
+// op(B) = B^T (BT) or B.  TRI tells which operand is lower triangular so that whole k8 steps / fragments are skipped:
+enum : int { MM_FULL = 0, MM_BT_BLOWER = 1, MM_NN_ALOWER = 2, MM_NN_BLOWER = 3, MM_SYRK_LOWER = 4 };
+//   MM_BT_BLOWER   C = A B^T, B lower:  sum over k <= column          MM_NN_ALOWER  C = A B, A lower: k <= row
+//   MM_NN_BLOWER   C = A B,   B lower:  sum over k >= column          MM_SYRK_LOWER C = A A^T-like, only fragments that touch
+//                                                                      the lower triangle are computed (others untouched)
+template <int N, bool BT, int TRI>
+__device__ __forceinline__ void mma_blk(const double* A, const double* B, double alpha, double* C, const double* D) {
+    constexpr int MF = N / 32, NF = N / 16;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int r0 = (warp & 3) * (N / 4), c0 = (warp >> 2) * (N / 2);
+    double acc[MF][NF][2];
+#pragma unroll
+    for (int mf = 0; mf < MF; ++mf)
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
+    // warp-uniform k range over all of this warp's fragments; per-fragment bounds inside
+    int kbeg = 0, kend = N;
+    if (TRI == MM_BT_BLOWER) kend = min(N, c0 + N / 2);
+    if (TRI == MM_NN_ALOWER) kend = min(N, r0 + N / 4);
+    if (TRI == MM_NN_BLOWER) kbeg = c0;
+    if (TRI == MM_SYRK_LOWER && c0 > r0 + N / 4 - 1) kend = 0;
+    for (int k0 = kbeg; k0 < kend; k0 += 8) {
+        double2 a[MF], b[NF];
+#pragma unroll
+        for (int mf = 0; mf < MF; ++mf)
+            a[mf] = *reinterpret_cast<const double2*>(A + (r0 + mf * 8 + g) * SLD + k0 + 2 * t);
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) {
+            if (BT) {
+                b[nf] = *reinterpret_cast<const double2*>(B + (c0 + nf * 8 + g) * SLD + k0 + 2 * t);
+            } else {
+                b[nf].x = B[(k0 + 2 * t) * SLD + c0 + nf * 8 + g];
+                b[nf].y = B[(k0 + 2 * t + 1) * SLD + c0 + nf * 8 + g];
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int mf = 0; mf < MF; ++mf)
+#pragma unroll
+                for (int nf = 0; nf < NF; ++nf) {
+                    bool live = true;  // warp-uniform
+                    if (TRI == MM_BT_BLOWER) live = k0 <= c0 + nf * 8 + 7;
+                    if (TRI == MM_NN_ALOWER) live = k0 <= r0 + mf * 8 + 7;
+                    if (TRI == MM_NN_BLOWER) live = k0 + 7 >= c0 + nf * 8;
+                    if (TRI == MM_SYRK_LOWER) live = c0 + nf * 8 <= r0 + mf * 8 + 7;
+                    if (live) dmma884(acc[mf][nf][0], acc[mf][nf][1], h ? a[mf].y : a[mf].x, h ? b[nf].y : b[nf].x);
+                }
+    }
+#pragma unroll
+    for (int mf = 0; mf < MF; ++mf)
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) {
+            if (TRI == MM_SYRK_LOWER && c0 + nf * 8 > r0 + mf * 8 + 7) continue;
+            int off = (r0 + mf * 8 + g) * SLD + c0 + nf * 8 + 2 * t;
+            double v0 = alpha * acc[mf][nf][0], v1 = alpha * acc[mf][nf][1];
+            if (D) {
+                double2 old = *reinterpret_cast<const double2*>(D + off);
+                v0 += old.x;
+                v1 += old.y;
+            }
+            *reinterpret_cast<double2*>(C + off) = make_double2(v0, v1);
+        }
+}
+
+// chol_inv_64_panel4 generalised to an NBk x NBk block (NBk = 32 or 64; identical operations for 64): thread (ty, tx) of
+// the 16 x 16 grid owns the E x E elements (ty + 16 a, tx + 16 b), E = NBk / 16.  A and W have row stride SLD.
+// colb / rowb: [2][4][NBk] each.  invd / dd: [NBk].
+template <int NBk>
+__device__ __forceinline__ void chol_inv_blk(double* A, double* W, double* colb, double* rowb, double* invd, double* dd) {
+    constexpr int E = NBk / 16;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    double ra[E][E], rw[E][E];
+#pragma unroll
+    for (int a = 0; a < E; ++a)
+#pragma unroll
+        for (int b = 0; b < E; ++b) {
+            int i = ty + 16 * a, k = tx + 16 * b;
+            ra[a][b] = A[i * SLD + k];
+            rw[a][b] = (i == k) ? 1.0 : 0.0;
+        }
+    for (int j0 = 0; j0 < NBk; j0 += 4) {
+        const int ja = j0 >> 4, jx0 = j0 & 15;
+        double* cb = colb + ((j0 >> 2) & 1) * (4 * NBk);
+        double* rb = rowb + ((j0 >> 2) & 1) * (4 * NBk);
+        if (tx >= jx0 && tx < jx0 + 4) {
+            double* dst = cb + (tx - jx0) * NBk;
+#pragma unroll
+            for (int a = 0; a < E; ++a) {
+                double v = ra[a][0];
+#pragma unroll
+                for (int q = 1; q < E; ++q) v = (ja == q) ? ra[a][q] : v;
+                dst[ty + 16 * a] = v;
+            }
+        }
+        if (ty >= jx0 && ty < jx0 + 4) {
+            double* dst = rb + (ty - jx0) * NBk;
+#pragma unroll
+            for (int b = 0; b < E; ++b) {
+                double v = rw[0][b];
+#pragma unroll
+                for (int q = 1; q < E; ++q) v = (ja == q) ? rw[q][b] : v;
+                dst[tx + 16 * b] = v;
+            }
+        }
+        __syncthreads();
+        double D[4][4], Ri[E][4], Ck[E][4], Wp[4][E];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) D[p][jj] = cb[jj * NBk + j0 + p];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                Ri[e][jj] = cb[jj * NBk + ty + 16 * e];
+                Ck[e][jj] = cb[jj * NBk + tx + 16 * e];
+                Wp[jj][e] = rb[jj * NBk + tx + 16 * e];
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = j0 + jj;
+            const double ajj = D[jj][jj];
+            if (tid == 0) dd[j] = ajj;
+            const double w = rcp_newton(ajj);
+            double ai[E], ak[E], wj[E], dm[4];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                ai[e] = (ty + 16 * e > j) ? Ri[e][jj] * w : 0.0;
+                ak[e] = (tx + 16 * e > j) ? Ck[e][jj] : 0.0;
+                wj[e] = Wp[jj][e];
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p) dm[p] = (p > jj) ? D[p][jj] * w : 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                if (kk <= jj) continue;
+                const double dk = D[kk][jj];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    Ri[e][kk] = fma(-ai[e], dk, Ri[e][kk]);
+                    const double ci = (tx + 16 * e > j) ? Ck[e][jj] * w : 0.0;
+                    Ck[e][kk] = fma(-ci, dk, Ck[e][kk]);
+                }
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+                    if (p > jj) D[p][kk] = fma(-dm[p], dk, D[p][kk]);
+            }
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) {
+                if (pp <= jj) continue;
+#pragma unroll
+                for (int e = 0; e < E; ++e) Wp[pp][e] = fma(-dm[pp], wj[e], Wp[pp][e]);
+            }
+#pragma unroll
+            for (int a = 0; a < E; ++a)
+#pragma unroll
+                for (int b = 0; b < E; ++b) {
+                    ra[a][b] = fma(-ai[a], ak[b], ra[a][b]);
+                    rw[a][b] = fma(-ai[a], wj[b], rw[a][b]);
+                }
+        }
+    }
+    __syncthreads();
+    if (tid < NBk) {
+        const double piv = dd[tid];
+        double r0 = rsqrt(piv);
+        double d0 = piv * r0;
+        double d = fma(fma(-d0, d0, piv), 0.5 * r0, d0);
+        invd[tid] = fma(fma(-d, r0, 1.0), r0, r0);
+        dd[tid] = d;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < E; ++a)
+#pragma unroll
+        for (int b = 0; b < E; ++b) {
+            int i = ty + 16 * a, k = tx + 16 * b;
+            A[i * SLD + k] = (k < i) ? ra[a][b] * invd[k] : (k == i ? dd[i] : 0.0);
+            W[i * SLD + k] = (k <= i) ? rw[a][b] * invd[i] : 0.0;
+        }
+    __syncthreads();
+}
+
+// 64 x 64 block by two 32 x 32 eliminations.  A -> L (zero upper), W -> L^-1 (zero upper); invd / dd: [64].
+__device__ __forceinline__ void chol_inv_64_rec(double* A, double* W, double* colb, double* rowb, double* invd, double* dd) {
+    double* A10 = A + 32 * SLD;        // rows 32.., cols 0..31
+    double* A11 = A + 32 * SLD + 32;
+    double* W10 = W + 32 * SLD;
+    double* W11 = W + 32 * SLD + 32;
+    double* S1 = W + 32;               // rows 0..31, cols 32..63 of W: scratch, zero again at the end
+    chol_inv_blk<32>(A, W, colb, rowb, invd, dd);
+    mma_blk<32, true, MM_BT_BLOWER>(A10, W, 1.0, S1, nullptr);   // L21 = A21 X11^T
+    __syncthreads();
+    mma_blk<32, true, MM_BT_BLOWER>(S1, A, -1.0, A10, A10);      // R = A21 - L21 L11^T   (in place of A21)
+    __syncthreads();
+    mma_blk<32, true, MM_BT_BLOWER>(A10, W, 1.0, S1, S1);        // L21 += R X11^T
+    __syncthreads();
+    mma_blk<32, true, MM_SYRK_LOWER>(S1, S1, -1.0, A11, A11);    // A22 -= L21 L21^T (lower fragments)
+    for (int idx = threadIdx.x; idx < 32 * 32; idx += LEAF_THREADS) {  // L21 to its place (R is dead)
+        int r = idx >> 5, c = idx & 31;
+        A10[r * SLD + c] = S1[r * SLD + c];
+    }
+    __syncthreads();
+    chol_inv_blk<32>(A11, W11, colb, rowb, invd + 32, dd + 32);
+    mma_blk<32, false, MM_NN_ALOWER>(W11, A10, 1.0, S1, nullptr);  // T = X22 L21
+    __syncthreads();
+    mma_blk<32, false, MM_NN_BLOWER>(S1, W, -1.0, W10, nullptr);   // X21 = -T X11
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 32 * 32; idx += LEAF_THREADS) {
+        int r = idx >> 5, c = idx & 31;
+        S1[r * SLD + c] = 0.0;
+        A[r * SLD + 32 + c] = 0.0;  // upper-right block of L (the eliminations only clear inside their own blocks)
+    }
+    __syncthreads();
+}
+
+// ==== leaves of the tile-column factorisation (factor_tiled.cu) =====================================================
+// Same arithmetic as leaf64_kernel / leaf128_kernel; the outputs differ: only L (no transpose of L is kept by the tiled
+// scheme), Linv and U = Linv^T, and ALL four 64-blocks of the tile are written (zeros in the block on the other side of
+// the diagonal), so that no separate zero-fill pass is needed for anything a product may read inside a diagonal tile.
+__device__ __forceinline__ void tile_store_direct(const double* S, double* G, int npad, int r0, int c0) {
+    for (int idx = threadIdx.x; idx < 64 * 32; idx += LEAF_THREADS) {
+        int r = idx >> 5, c = (idx & 31) * 2;
+        *reinterpret_cast<double2*>(G + (int64_t)(r0 + r) * npad + c0 + c) = *reinterpret_cast<const double2*>(S + r * SLD + c);
+    }
+}
+__device__ __forceinline__ void tile_store_zero(double* G, int npad, int r0, int c0) {
+    for (int idx = threadIdx.x; idx < 64 * 32; idx += LEAF_THREADS) {
+        int r = idx >> 5, c = (idx & 31) * 2;
+        *reinterpret_cast<double2*>(G + (int64_t)(r0 + r) * npad + c0 + c) = make_double2(0.0, 0.0);
+    }
+}
+// Gt[c0 + c][r0 + r] = S[r][c] through the odd-stride staging buffer T (see leaf_store)
+__device__ __forceinline__ void tile_store_transposed(const double* S, double* T, double* Gt, int npad, int r0, int c0) {
+    for (int idx = threadIdx.x; idx < 64 * 64; idx += LEAF_THREADS) {
+        int r = idx >> 6, c = idx & 63;
+        T[c * TLD + r] = S[r * SLD + c];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 64 * 64; idx += LEAF_THREADS) {
+        int r = idx >> 6, c = idx & 63;
+        Gt[(int64_t)(c0 + r) * npad + r0 + c] = T[r * TLD + c];
+    }
+    __syncthreads();
+}
+
+template <bool REC>
+__device__ __forceinline__ void chol_inv_64_sel(int panel4, double* A, double* W, double* colb, double* rowb, double* invd,
+                                                double* dd) {
+    if (REC)
+        chol_inv_64_rec(A, W, colb, rowb, invd, dd);
+    else
+        chol_inv_64_any(panel4, A, W, colb, rowb, invd, dd);
+}
+
+// REC: recursive 32-base elimination + triangular-aware products (default); otherwise the round-1 arithmetic
+template <bool REC>
+__global__ void __launch_bounds__(LEAF_THREADS) tile_leaf64_kernel(LeafIO io) {
+    extern __shared__ __align__(16) double sm[];
+    pdl_wait();
+    pdl_trigger();
+    double* A = sm;
+    double* W = A + 64 * SLD;
+    double* colb = W + 64 * SLD;
+    double* rowb = colb + 512;
+    double* invd = rowb + 512;
+    double* dd = invd + 64;
+    double* T = dd + 64;
+    const int64_t z = blockIdx.z, zoff = z * (int64_t)io.npad * io.npad;
+    leaf_load_async(A, io.KB + zoff, io.npad, io.o, io.o);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    chol_inv_64_sel<REC>(io.panel4, A, W, colb, rowb, invd, dd);
+    tile_store_direct(A, io.L + zoff, io.npad, io.o, io.o);
+    tile_store_direct(W, io.Linv + zoff, io.npad, io.o, io.o);
+    tile_store_transposed(W, T, io.U + zoff, io.npad, io.o, io.o);
+    if (threadIdx.x < 64) io.diag[z * io.npad + io.o + threadIdx.x] = dd[threadIdx.x];
+    leaf_update_stats(io, dd, 64, z);
+}
+
+template <bool REC>
+__global__ void __launch_bounds__(LEAF_THREADS) tile_leaf128_kernel(LeafIO io) {
+    extern __shared__ __align__(16) double sm[];
+    pdl_wait();
+    pdl_trigger();
+    double* B0 = sm;              // A11 -> L11
+    double* B1 = B0 + 64 * SLD;   // X11
+    double* B2 = B1 + 64 * SLD;   // A21 -> residual -> T
+    double* B3 = B2 + 64 * SLD;   // A22 -> L22
+    double* B4 = B3 + 64 * SLD;   // X22
+    double* B5 = B4 + 64 * SLD;   // L21 -> X21
+    double* colb = B5 + 64 * SLD;
+    double* rowb = colb + 512;
+    double* invd = rowb + 512;
+    double* dd = invd + 128;
+    const int64_t z = blockIdx.z, zoff = z * (int64_t)io.npad * io.npad;
+    const int o = io.o, npad = io.npad;
+    const double* Kz = io.KB + zoff;
+    double *Lz = io.L + zoff, *Xz = io.Linv + zoff, *Uz = io.U + zoff;
+    leaf_load_async(B0, Kz, npad, o, o);
+    leaf_load_async(B2, Kz, npad, o + 64, o);
+    leaf_load_async(B3, Kz, npad, o + 64, o + 64);
+    cp_async_commit();
+    // the blocks on the other side of the diagonal, while the loads are in flight
+    tile_store_zero(Lz, npad, o, o + 64);
+    tile_store_zero(Xz, npad, o, o + 64);
+    tile_store_zero(Uz, npad, o + 64, o);
+    cp_async_wait<0>();
+    __syncthreads();
+    chol_inv_64_sel<REC>(io.panel4, B0, B1, colb, rowb, invd, dd);
+    const bool refine = leaf_update_stats(io, dd, 64, z);
+    if (REC) {
+        mma_blk<64, true, MM_BT_BLOWER>(B2, B1, 1.0, B5, nullptr);  // L21 = A21 X11^T
+        __syncthreads();
+        if (refine) {
+            mma_blk<64, true, MM_BT_BLOWER>(B5, B0, -1.0, B2, B2);  // R = A21 - L21 L11^T
+            __syncthreads();
+            mma_blk<64, true, MM_BT_BLOWER>(B2, B1, 1.0, B5, B5);   // L21 += R X11^T
+            __syncthreads();
+        }
+        mma_blk<64, true, MM_SYRK_LOWER>(B5, B5, -1.0, B3, B3);     // A22 -= L21 L21^T
+    } else {
+        mma64<true>(B2, B1, 1.0, B5, nullptr);
+        __syncthreads();
+        if (refine) {
+            mma64<true>(B5, B0, -1.0, B2, B2);
+            __syncthreads();
+            mma64<true>(B2, B1, 1.0, B5, B5);
+            __syncthreads();
+        }
+        mma64<true>(B5, B5, -1.0, B3, B3);
+    }
+    __syncthreads();
+    tile_store_direct(B5, Lz, npad, o + 64, o);  // L21
+    tile_store_direct(B0, Lz, npad, o, o);       // L11
+    chol_inv_64_sel<REC>(io.panel4, B3, B4, colb, rowb, invd + 64, dd + 64);
+    leaf_update_stats(io, dd + 64, 64, z);
+    if (REC) {
+        mma_blk<64, false, MM_NN_ALOWER>(B4, B5, 1.0, B2, nullptr);   // T = X22 L21
+        __syncthreads();
+        mma_blk<64, false, MM_NN_BLOWER>(B2, B1, -1.0, B5, nullptr);  // X21 = -T X11
+    } else {
+        mma64<false>(B4, B5, 1.0, B2, nullptr);
+        __syncthreads();
+        mma64<false>(B2, B1, -1.0, B5, nullptr);
+    }
+    __syncthreads();
+    tile_store_direct(B3, Lz, npad, o + 64, o + 64);
+    tile_store_direct(B1, Xz, npad, o, o);
+    tile_store_direct(B4, Xz, npad, o + 64, o + 64);
+    tile_store_direct(B5, Xz, npad, o + 64, o);
+    // B2 (T) is dead: transpose staging
+    tile_store_transposed(B1, B2, Uz, npad, o, o);
+    tile_store_transposed(B4, B2, Uz, npad, o + 64, o + 64);
+    tile_store_transposed(B5, B2, Uz, npad, o + 64, o);
+    if (threadIdx.x < 128) io.diag[z * npad + o + threadIdx.x] = dd[threadIdx.x];
+}
+
 }  // namespace bobe

@@ -193,39 +193,7 @@ __global__ void __launch_bounds__(256) mll_finish_kernel(const double* __restric
     if (threadIdx.x == 0) val[z] = -0.5 * quad[z] - logdet[z] - 0.5 * (double)n * 1.8378770664093454835606594728112;
 }
 
-constexpr int MLL_MAX_STREAMS = 8;
-
-// Internal side streams, created once per device.  They carry no state between calls: every call forks them
-// from the caller's stream and joins them back before returning.
-struct StreamPool {
-    cudaStream_t streams[MLL_MAX_STREAMS];
-    cudaEvent_t fork, join[MLL_MAX_STREAMS];
-    std::mutex enqueue_mu;  // the fork / join events are shared: one host thread enqueues on the pool at a time
-};
-static StreamPool* stream_pool() {
-    static std::mutex mu;
-    static StreamPool* pools[64] = {nullptr};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
-        set_error("mll_grad: cudaGetDevice failed");
-        return nullptr;
-    }
-    std::lock_guard<std::mutex> lock(mu);
-    if (!pools[dev]) {
-        StreamPool* p = new StreamPool();
-        bool ok = cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming) == cudaSuccess;
-        for (int i = 0; i < MLL_MAX_STREAMS && ok; ++i)
-            ok = cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking) == cudaSuccess &&
-                 cudaEventCreateWithFlags(&p->join[i], cudaEventDisableTiming) == cudaSuccess;
-        if (!ok) {
-            set_error("mll_grad: could not create internal streams: %s", cudaGetErrorString(cudaGetLastError()));
-            delete p;
-            return nullptr;
-        }
-        pools[dev] = p;
-    }
-    return pools[dev];
-}
+constexpr int MLL_MAX_STREAMS = POOL_STREAMS / 2;  // each sub-batch may use two pool streams (chain + look-ahead)
 
 struct MllLayout {
     int64_t npad, tiles, ntile_pairs;
@@ -309,14 +277,12 @@ extern "C" int32_t bobe_mll_grad_batched(void* stream_, int32_t kind, const doub
     static const int64_t max_streams = std::min<int64_t>(MLL_MAX_STREAMS, env_int("BOBE_MLL_STREAMS", 4));
     static const int64_t min_per_stream = std::max<int64_t>(1, env_int("BOBE_MLL_MIN_PER_STREAM", 4));
     const int S = (int)std::min<int64_t>(max_streams, std::max<int64_t>(1, R / min_per_stream));
-    StreamPool* pool = nullptr;
     // XLA may call handlers from several host threads: the record / wait pairs below must not interleave with those
     // of another caller of the same device (stream order then keeps the shared side streams correct)
-    std::unique_lock<std::mutex> pool_lock;
+    StreamPool* pool = stream_pool();
+    if (!pool) return BOBE_E_CUDA;
+    std::unique_lock<std::mutex> pool_lock(pool->enqueue_mu);
     if (S > 1) {
-        pool = stream_pool();
-        if (!pool) return BOBE_E_CUDA;
-        pool_lock = std::unique_lock<std::mutex>(pool->enqueue_mu);
         if (cudaEventRecord(pool->fork, stream) != cudaSuccess) {
             set_error("mll_grad: event record failed");
             return BOBE_E_CUDA;
@@ -325,7 +291,7 @@ extern "C" int32_t bobe_mll_grad_batched(void* stream_, int32_t kind, const doub
     int32_t rc_all = BOBE_OK;
     for (int si = 0; si < S && rc_all == BOBE_OK; ++si) {
         const int64_t r0 = si * R / S, r1 = (si + 1) * R / S, Rs = r1 - r0;
-        cudaStream_t st = (S > 1) ? pool->streams[si] : stream;
+        cudaStream_t st = (S > 1) ? pool->streams[2 * si] : stream;
         if (S > 1) cudaStreamWaitEvent(st, pool->fork, 0);
         rc_all = [&]() -> int32_t {
             FactorBuffers fb{w + l.off_KB + r0 * m2, w + l.off_L + r0 * m2, w + l.off_Lt + r0 * m2,
@@ -346,7 +312,7 @@ extern "C" int32_t bobe_mll_grad_batched(void* stream_, int32_t kind, const doub
             ka.ls_stride = d; ka.out_stride = m2; ka.noise = noise; ka.add_noise = 1; ka.pad_identity = 1;
             ka.lower_only = 1;  // the factorisation reads the lower triangle only
             if (int32_t rc = launch_kmat(st, kind, ka, (int)Rs)) return rc;
-            if (int32_t rc = factor_recursive(st, fb, npad, (int)Rs)) return rc;
+            if (int32_t rc = factor_any(st, pool, si, fb, npad, (int)Rs)) return rc;
             SolveArgs sa{kind, X, ls_s, kv_s, d, noise, xs};
             if (int32_t rc = launch_solve_vectors(st, fb, sa, y, n, npad, (int)Rs, zws, alpha, logdet, quad, info + r0))
                 return rc;

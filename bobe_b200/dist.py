@@ -124,3 +124,39 @@ def acquisition_sharded(eval_fn: Callable[[np.ndarray], np.ndarray], candidates:
     if ws == 1:
         return vals
     return allgather_rows(torch.as_tensor(vals), C).cpu().numpy()
+
+
+def wipv_sharded(gp, mc_points, candidates=None, std: bool = False):
+    """WIPV / WIPStd with the MONTE-CARLO COLUMNS sharded (BASELINE config 5: n_mc = 1e5, C = 8).
+
+    The reference maps the candidates over ONE shared ``k_train_mc`` (BOBE/acquisition.py:385-394) and averages the
+    fantasy variance over the MC points (BOBE/gp.py:552-576, acquisition.py:438-440,463-465).  The dominant cost is the
+    shared solve ``V = L^-1 K(X, MC)`` (n^2 n_mc flops), so a candidate split would make every rank redo all of it;
+    here rank r solves only its ``n_mc / G`` columns for ALL candidates and contributes the partial mean
+    ``(n_r / n_mc) mean_{j in shard r} s_j(c)``.  The C partial means are all-gathered and added in rank order on every
+    rank (fixed order: every rank returns bit-identical values; they differ from the single-GPU value only by the
+    regrouping of the mean, ~1e-16 relative).
+
+    ``candidates=None`` uses the full MC set as candidates (acquisition.py:390-397).  Returns (C,) values."""
+    rank, ws = world()
+    as_t = isinstance(mc_points, torch.Tensor)
+    n_mc = int(mc_points.shape[0])
+    cand = mc_points if candidates is None else candidates
+    C = int(cand.shape[0]) if getattr(cand, "ndim", 2) > 1 else 1
+    if ws == 1:
+        return gp.fantasy_acquisition(mc_points, candidates, std=std)
+    lo, hi = shard_bounds(n_mc, rank, ws)
+    if hi > lo:
+        part = torch.as_tensor(gp.fantasy_acquisition(mc_points[lo:hi], cand, std=std)).to(torch.float64).reshape(-1)
+        part = part * (float(hi - lo) / float(n_mc))
+    else:
+        part = torch.zeros(C, dtype=torch.float64)
+    dev = _comm_device()
+    mine = part.to(dev)
+    out = [torch.empty_like(mine) for _ in range(ws)]
+    tdist.all_gather(out, mine)
+    total = out[0].clone()
+    for r in range(1, ws):  # rank order, on every rank
+        total += out[r]
+    total = total.to(part.device)
+    return total if as_t else total.cpu().numpy()

@@ -413,6 +413,11 @@ class GP:
         comp = torch.cuda.current_stream(dev)
         copy = torch.cuda.Stream(dev)
         stage = [torch.empty((rows, d), dtype=torch.float64, device=dev) for _ in range(2)]
+        # the staging blocks come from the caching allocator on the compute stream: a recycled block may still be in use
+        # by kernels queued there, so the copy stream must not write into it before those have run
+        copy.wait_stream(comp)
+        for st in stage:
+            st.record_stream(copy)
         copied = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
         # straight from torch's caching pinned allocator (no pageable allocation + copy as .pin_memory() would do)

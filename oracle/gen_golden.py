@@ -18,6 +18,7 @@ OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 # name: (n, d, kernel, lengthscale, M queries, R restarts, n_mc, C candidates)
 CASES = {
     "A_banana_rbf_n100_d2": (100, 2, "rbf", 0.3, 256, 4, 64, 8),
+    "B_rbf_n500_d2": (500, 2, "rbf", 0.3, 256, 4, 64, 8),  # worst-conditioned BASELINE shape: cond(K) = 1.8e10
     "B_rbf_n500_d4": (500, 4, "rbf", 0.5, 256, 4, 64, 8),
     "B_rbf_n500_d6": (500, 6, "rbf", 0.5, 256, 3, 64, 8),
     "M_matern_n300_d3": (300, 3, "matern", 0.7, 256, 4, 64, 8),
@@ -37,9 +38,10 @@ def make_case(name):
     return gp, X, y, Xq, x0, mc, cand
 
 
-def main():
+def main(names=None):
+    """Regenerate all cases, or only the named ones:  python -m oracle.gen_golden B_rbf_n500_d2"""
     os.makedirs(OUT, exist_ok=True)
-    for name in CASES:
+    for name in (names or CASES):
         gp, X, y, Xq, x0, mc, cand = make_case(name)
         out = {}
         out["mean"] = gp.predict_mean_batched(Xq)
@@ -73,4 +75,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1:] or None)

@@ -39,6 +39,13 @@ class _FakeGP:
         lp = np.atleast_2d(lp)
         return (lp ** 2).sum(axis=1), 2 * lp
 
+    def fantasy_acquisition(self, mc, cand=None, std=False):
+        """mean over the MC points of a per-(candidate, MC point) quantity: what WIPV / WIPStd are structurally."""
+        mc = np.asarray(mc)
+        cand = mc if cand is None else np.atleast_2d(np.asarray(cand))
+        s = 1.0 + np.cos(cand.sum(1))[:, None] * np.sin(mc.sum(1))[None, :] ** 2
+        return (np.sqrt(s) if std else s).mean(axis=1)
+
 
 def _worker(rank, ws, port, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -63,6 +70,16 @@ def _worker(rank, ws, port, out_dir):
         assert np.allclose(v, (x0 ** 2).sum(1)) and np.allclose(g, 2 * x0)
         vals = bd.acquisition_sharded(lambda c: c.sum(1), xq[:7])
         assert np.allclose(vals, xq[:7].sum(1))
+        # WIPV with the MC columns sharded: size-weighted partial means, gathered and added in rank order
+        mc = rng.uniform(0, 1, (37, 3))  # odd count: shards of 19 and 18
+        cand = rng.uniform(0, 1, (8, 3))
+        for std in (False, True):
+            w = bd.wipv_sharded(_FakeGP(), mc, cand, std=std)
+            assert w.shape == (8,) and np.allclose(w, _FakeGP().fantasy_acquisition(mc, cand, std), rtol=1e-13, atol=0)
+            ws_self = bd.wipv_sharded(_FakeGP(), mc, None, std=std)
+            assert ws_self.shape == (37,) and np.allclose(ws_self, _FakeGP().fantasy_acquisition(mc, None, std), rtol=1e-13)
+        one = bd.wipv_sharded(_FakeGP(), mc[:1], cand)  # fewer MC points than ranks: an empty shard contributes zero
+        assert np.allclose(one, _FakeGP().fantasy_acquisition(mc[:1], cand), rtol=1e-13)
         t = bd.allgather_rows(torch.arange(rank * 3, rank * 3 + (3 if rank == 0 else 2), dtype=torch.float64), 5)
         assert torch.equal(t, torch.arange(5, dtype=torch.float64))
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
@@ -81,3 +98,5 @@ def test_single_process_paths():
     m, v = bd.predict_sharded(_FakeGP(), xq)
     assert np.allclose(m, xq.sum(1))
     assert bd.world() == (0, 1)
+    mc = np.random.default_rng(2).uniform(0, 1, (9, 2))
+    assert np.array_equal(bd.wipv_sharded(_FakeGP(), mc, mc[:3]), _FakeGP().fantasy_acquisition(mc, mc[:3]))

@@ -516,6 +516,59 @@ def test_gp_with_svm_classifier_mask_and_state(tmp_path):
         GPwithClassifier(X, y, clf_type="nn")
 
 
+def test_ei_and_input_gradients_respect_the_classifier_mask():
+    """EI / LogEI on a GPwithClassifier go through predict_single, which the reference masks to (minus_inf,
+    safe_noise_floor) where the classifier excludes the point (BOBE/clf_gp.py:197-205 under BOBE/acquisition.py:246,323):
+    -EI is ~0 there, its input gradient exactly 0, and feasible points are untouched."""
+    from bobe_b200 import EI, LogEI, GPwithClassifier
+    rng = np.random.default_rng(2)
+    n, d = 400, 3
+    X = rng.uniform(0, 1, (n, d))
+    y = -0.5 * np.sum(((X - 0.5) / 0.05) ** 2, axis=1, keepdims=True)
+    gp = GPwithClassifier(X, y, clf_type="svm", clf_use_size=10, clf_threshold=20.0, gp_threshold=60.0, kernel="rbf",
+                          lengthscales=np.full(d, 0.3), kernel_variance=1.0, lengthscale_prior=None)
+    assert gp.use_clf and gp.clf_params is not None
+    xq = rng.uniform(0.05, 0.95, (600, d))
+    dec = gp.clf_decision(xq)
+    bad, good = dec < -1e-6 * np.abs(dec).max(), dec > 1e-6 * np.abs(dec).max()
+    assert bad.sum() > 10 and good.sum() > 10
+    best = float(gp.train_y.max())
+    ms, vs = gp.predict_batched(xq)
+    assert np.all(ms[bad] == gp.minus_inf) and np.all(vs.ravel()[bad] == 1e-12)
+    for acq in (EI(), LogEI()):
+        vals = acq.fun_batched(xq, gp, best, 0.0)
+        ref_vals = (O.ei_values if acq.name == "EI" else O.logei_values)(ms, vs, best, 0.0)  # epilogue on the MASKED moments
+        assert np.allclose(vals, ref_vals, rtol=1e-9, atol=1e-300)
+        if acq.name == "EI":
+            assert np.all(np.abs(vals[bad]) < 1e-300)  # u = (minus_inf - best) / 1e-6: EI underflows to exactly 0
+        v2, g2 = acq.value_and_grad_batched(xq, gp, best, 0.0)
+        assert np.allclose(v2, vals, rtol=1e-9, atol=1e-300) and np.all(g2[bad] == 0.0)
+        assert np.any(g2[good] != 0.0)
+    mu, var, dmu, dvar = gp.predict_grad_batched(xq, standardised=True)
+    assert np.all(mu[bad] == gp.minus_inf) and np.all(var[bad] == 1e-12) and np.all(dmu[bad] == 0) and np.all(dvar[bad] == 0)
+    mu0, var0, dmu0, dvar0 = super(GPwithClassifier, gp).predict_grad_batched(xq, standardised=True)
+    assert np.array_equal(mu[good], mu0[good]) and np.array_equal(dvar[good], dvar0[good])
+
+
+def test_nan_query_propagates():
+    """A NaN query coordinate gives NaN kernel rows in the reference (jnp.exp(NaN)), hence a NaN mean; predict_var
+    propagates the NaN through clip (BOBE/gp.py:465), predict_single floors it (BOBE/gp.py:487-488)."""
+    for name in ("A_banana_rbf_n100_d2", "M_matern_n300_d3"):
+        ref, X, y, Xq, _, _, _ = make_case(name)
+        gp = make_gp(ref)
+        xq = Xq[:200].copy()
+        xq[7, 0] = np.nan
+        xq[150, -1] = np.nan
+        mean, var = gp.predict_mean_var_batched(xq)
+        nanrow = np.zeros(200, dtype=bool)
+        nanrow[[7, 150]] = True
+        assert np.array_equal(np.isnan(mean), nanrow) and np.array_equal(np.isnan(var), nanrow)
+        assert np.array_equal(np.isnan(gp.predict_mean_batched(xq)), nanrow)  # the mean-only launch path
+        ms, vs = gp.predict_batched(xq)
+        assert np.array_equal(np.isnan(ms), nanrow) and np.all(vs.ravel()[nanrow] == 1e-12)
+        assert mixed_err(mean[~nanrow], ref.predict_mean_batched(xq[~nanrow]), ref.y_std) < 3 * TOL_MEAN
+
+
 @pytest.mark.parametrize("d", [33, 64, 144])
 def test_large_input_dimension(d):
     """d up to BOBE_MAX_DIM = 144 (shared-memory staging of one 64-row tile per operand); above it a clean error."""
@@ -606,6 +659,33 @@ def test_config_c_64_restarts_full_size():
     g2 = np.concatenate([ga.cpu().numpy(), gb.cpu().numpy()])
     assert np.array_equal(np.isnan(v2), bad)
     assert np.array_equal(v2[~bad], val[~bad]) and np.array_equal(g2[~bad], grad[~bad])
+    # NaN / info pattern against the oracle for ALL 64 rows: the reference skips exactly the restarts whose Cholesky
+    # fails (non-finite value, BOBE/optim.py:326-333).  LAPACK (oracle) and the CUDA factorisation must agree on which
+    # rows are positive definite; a row may only differ if it is numerically on the boundary, i.e. if LAPACK itself
+    # flips between K - delta I and K + delta I for delta = 8 n eps max(diag K).
+    def oracle_pd(r, shift=0.0):
+        ls_r, kv_r, _ = ref._parse_hyperparams(lp[r])
+        K = ref.kernel(ref.train_x, ref.train_x, ls_r, kv_r, ref.noise, True)
+        if shift:
+            K = K + shift * 8 * K.shape[0] * np.finfo(float).eps * float(np.max(np.diag(K))) * np.eye(K.shape[0])
+        try:
+            Lr = np.linalg.cholesky(K)
+        except np.linalg.LinAlgError:
+            return False, float("nan")
+        dg = np.diag(Lr)
+        return True, float(dg.max() / dg.min())
+    pd_oracle = np.zeros(64, dtype=bool)
+    ratio = np.full(64, np.nan)
+    for r in range(64):
+        pd_oracle[r], ratio[r] = oracle_pd(r)
+    disagree = np.where(pd_oracle == bad)[0]
+    print(f"\n[config C] oracle PD rows {int(pd_oracle.sum())}/64, CUDA finite rows {int((~bad).sum())}/64, "
+          f"disagreements {disagree.tolist()}, largest pivot ratio among PD rows {np.nanmax(ratio):.2e}")
+    for r in disagree:
+        lo, hi = oracle_pd(int(r), -1.0)[0], oracle_pd(int(r), +1.0)[0]
+        print(f"  row {int(r)}: oracle PD {bool(pd_oracle[r])} (pivot ratio {ratio[r]:.2e}), CUDA info {int(info[r])}, "
+              f"LAPACK on K -/+ delta I: {lo}/{hi}")
+        assert lo != hi, f"restart {int(r)}: CUDA and LAPACK disagree on positive definiteness away from the boundary"
     # oracle on row 0 (the current hyper-parameters) and the first two PD random rows
     rows = [0] + [int(r) for r in np.where(~bad)[0][1:3]]
     for r in rows:

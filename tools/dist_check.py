@@ -31,7 +31,18 @@ cand = O.synthetic_queries(13, d, seed=6)
 a = dist.acquisition_sharded(lambda c: gp.fantasy_acquisition(mc, c), cand)
 a1 = gp.fantasy_acquisition(mc, cand)
 assert np.allclose(a, a1, rtol=1e-12), "acquisition_sharded"
+# WIPV / WIPStd with the MC columns sharded (dist.wipv_sharded): equal to the single-GPU value up to the regrouping of the mean
+mc2 = O.synthetic_queries(1001, d, seed=7)
+for std in (False, True):
+    w = dist.wipv_sharded(gp, mc2, cand, std=std)
+    w1 = gp.fantasy_acquisition(mc2, cand, std=std)
+    assert w.shape == (13,) and np.allclose(w, w1, rtol=1e-11, atol=0), ("wipv_sharded", float(np.abs(w / w1 - 1).max()))
+ws_self = dist.wipv_sharded(gp, mc, None)
+assert np.allclose(ws_self, gp.fantasy_acquisition(mc, None), rtol=1e-11), "wipv_sharded self"
+gathered = [None] * ws
+tdist.all_gather_object(gathered, w.tobytes())
+assert all(g == gathered[0] for g in gathered), "wipv_sharded must be bit-identical on every rank"
 tdist.barrier()
 if rank == 0:
-    print(f"dist_check ok on {ws} ranks: predict {m.shape}, mll {val.shape}, fit mll {res['mll']:.6f} (single-rank {res1['mll']:.6f}), acq {a.shape}")
+    print(f"dist_check ok on {ws} ranks: predict {m.shape}, mll {val.shape}, fit mll {res['mll']:.6f} (single-rank {res1['mll']:.6f}), acq {a.shape}, wipv_sharded max rel dev {float(np.abs(w / w1 - 1).max()):.1e}")
 tdist.destroy_process_group()
