@@ -4,10 +4,14 @@
   python bench.py --gpus N --steps K --warmup W          # our arm (under torchrun for N > 1)
   python bench.py --impl reference --gpus N ...          # the reference's CPU arithmetic (oracle port) on host cores
 
-Headline metric (BASELINE.json): posterior mean+variance evaluations/sec at n=2000, d=16, Matern-5/2,
-M=10^6 queries per GPU per step (weak scaling: queries shard with no data-path collective; the closing
-all-gather of the 16 B/query results is inside the timed region for N > 1).  The second BASELINE metric,
-log-ML+gradient evals/sec over 64 restarts (sharded across ranks), is reported in "secondary".
+One JSON line.  Its top-level value is the headline metric of BASELINE.json -- posterior mean+variance evaluations/sec
+at n=2000, d=16, Matern-5/2, M=10^6 queries PER GPU per step (weak scaling: queries shard with no data-path collective;
+the closing all-gather of the 16 B/query results is inside the timed region for N > 1).  Beside it, from the same run:
+  "strong"     the same sweep with M = 10^6 queries IN TOTAL split over the N GPUs (north_star's "M = 10^6 on 8 x B200");
+  "secondary"  log-ML + gradient evals/sec over 64 restarts sharded over the ranks (strong), with its own clocks record;
+  "wipv"       BASELINE config 5: WIPV over n_mc = 10^5 MC points x 8 candidates at n = 4000, d = 12, MC columns sharded.
+For N > 1 every one of them goes through the product's sharding layer bobe_b200.dist (predict_sharded, mll_grad_sharded,
+wipv_sharded), not through inline collectives.
 """
 from __future__ import annotations
 
@@ -26,9 +30,19 @@ sys.path.insert(0, ROOT)
 
 N_TRAIN, DIM, KERNEL, ELL = 2000, 16, "matern", 1.0
 M_PER_GPU = 1_000_000
+M_STRONG = 1_000_000
 R_TOTAL = 64
+E_N, E_DIM, E_NMC, E_CAND = 4000, 12, 100_000, 8  # BASELINE config 5
 CPU_CHUNK = 1024
 WORKLOAD = "H: predict mean+var, n=2000 d=16 Matern-5/2 ARD, M=1e6 queries per GPU (synthetic, SURVEY.md 8d)"
+
+
+def bench_config(world, m_per_gpu=M_PER_GPU):
+    """The SAME dictionary in both arms (the reference arm times a bounded sample of this workload; what the sample was is
+    said in its cpu_baseline.sample, not here)."""
+    return {"workload": WORKLOAD, "n": N_TRAIN, "d": DIM, "kernel": KERNEL, "m_per_gpu": m_per_gpu,
+            "l2": "inputs larger than L2 (128 MB of queries + 930 MB K* scratch per 3-chunk sweep)",
+            "parallelism": f"query-sharded x{world}, replicated factor"}
 
 
 def _peaks():
@@ -67,6 +81,7 @@ class ClockSampler:
             self.t.start()
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -99,23 +114,71 @@ class ClockSampler:
                 "power_w_max": max(power), "samples": len(sm)}
 
 
-def cpu_predict_sample(n_queries, threads=None):
-    """The oracle (NumPy/SciPy port of BOBE/gp.py) on host cores: mean+var over a bounded query sample."""
+# ---- the reference's CPU arithmetic (oracle port) on the host cores -------------------------------------------------------
+# Thread policy, fixed explicitly so that the arm is the same at every N (torch.distributed.run exports OMP_NUM_THREADS=1,
+# which silently halved this arm in round 1): either `cores` Python threads each with ONE BLAS thread over query chunks of
+# 1024, or one Python thread with an all-core BLAS over chunks of 8192; the faster of the two on a warm-up sample is used.
+def _blas_limits(n):
+    from threadpoolctl import threadpool_limits
+    return threadpool_limits(limits=int(n))
+
+
+_CPU_GP = {}
+
+
+def _cpu_gp():
     from oracle import gp_oracle as O
-    X, y = O.synthetic_training_set(N_TRAIN, DIM)
-    gp = O.OracleGP(X, y, kernel=KERNEL, lengthscales=np.full(DIM, ELL))
+    if "gp" not in _CPU_GP:
+        X, y = O.synthetic_training_set(N_TRAIN, DIM)
+        _CPU_GP["gp"] = O.OracleGP(X, y, kernel=KERNEL, lengthscales=np.full(DIM, ELL))
+    return _CPU_GP["gp"]
+
+
+def cpu_predict_sample(n_queries, policy):
+    """mean+var over a bounded query sample; policy = "threads" (cores x 1 BLAS thread) or "blas" (1 x all-core BLAS)."""
     from concurrent.futures import ThreadPoolExecutor
+    from oracle import gp_oracle as O
+    gp = _cpu_gp()
     Xq = O.synthetic_queries(n_queries, DIM)
-    threads = threads or os.cpu_count()
+    cores = os.cpu_count()
+    chunk = CPU_CHUNK if policy == "threads" else 8 * CPU_CHUNK
 
     def work(s):  # query chunks keep the temporaries cache-sized; NumPy releases the GIL inside its loops
-        gp.predict_mean_batched(Xq[s:s + CPU_CHUNK])
-        gp.predict_var_batched(Xq[s:s + CPU_CHUNK])
-    t0 = time.perf_counter()
-    with ThreadPoolExecutor(threads) as ex:
-        list(ex.map(work, range(0, n_queries, CPU_CHUNK)))
-    dt = time.perf_counter() - t0
+        gp.predict_mean_batched(Xq[s:s + chunk])
+        gp.predict_var_batched(Xq[s:s + chunk])
+    with _blas_limits(1 if policy == "threads" else cores):
+        t0 = time.perf_counter()
+        if policy == "threads":
+            with ThreadPoolExecutor(cores) as ex:
+                list(ex.map(work, range(0, n_queries, chunk)))
+        else:
+            for s in range(0, n_queries, chunk):
+                work(s)
+        dt = time.perf_counter() - t0
     return n_queries / dt, dt
+
+
+def cpu_pick_policy():
+    best = None
+    for policy in ("threads", "blas"):
+        cpu_predict_sample(4096, policy)
+        v, _ = cpu_predict_sample(16384, policy)
+        if best is None or v > best[1]:
+            best = (policy, v)
+    return best[0]
+
+
+def cpu_mll_grad_evals(n_evals):
+    """value_and_grad(neg_mll) at n = 2000 (BOBE/gp.py:385-398 through optim.py:309), all-core BLAS; evals/s."""
+    from oracle import gp_oracle as O
+    gp = _cpu_gp()
+    x0 = O.synthetic_restarts(gp, max(2, n_evals))
+    with _blas_limits(os.cpu_count()):
+        t0 = time.perf_counter()
+        for r in range(n_evals):
+            gp.neg_mll_and_grad(x0[r])
+        dt = time.perf_counter() - t0
+    return n_evals / dt, dt
 
 
 def run_reference(args):
@@ -123,23 +186,32 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count()
+    policy = cpu_pick_policy()
     sample = 65536
-    for _ in range(args.warmup):
-        cpu_predict_sample(2048)
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_predict_sample(4096, policy)
     times = []
     for _ in range(args.steps):
-        _, dt = cpu_predict_sample(sample)
+        _, dt = cpu_predict_sample(sample, policy)
         times.append(dt)
     ms = 1e3 * float(np.mean(times))
     val = sample / (ms / 1e3)
+    mll_v, mll_dt = cpu_mll_grad_evals(2)
+    pol = (f"{cores} Python threads x 1 BLAS thread, query chunks of {CPU_CHUNK}" if policy == "threads"
+           else f"1 Python thread x {cores} BLAS threads, query chunks of {8 * CPU_CHUNK}")
     line = {"impl": "reference", "metric": "gp_predict_mean_var_pts_per_sec", "value": val, "unit": "pts/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n": N_TRAIN, "d": DIM, "kernel": KERNEL},
+            "config": bench_config(args.gpus),
             "cpu_baseline": {"value": val, "unit": "pts/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample} queries per step (of the 1e6 workload), NumPy/SciPy OpenBLAS restatement "
-                                       f"of BOBE/gp.py (JAX is not installable here), {cores} threads x query chunks of {CPU_CHUNK}"},
-            "e2e": {"value": val, "unit": "pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                             "sample": f"{sample} queries per step (of the 1e6-per-GPU workload), NumPy/SciPy(OpenBLAS) "
+                                       f"restatement of BOBE/gp.py predict_mean+predict_var (JAX is not installable here); "
+                                       f"{pol} (the faster of the two policies; BLAS threads set with threadpoolctl, so the "
+                                       f"arm is identical at every N)"},
+            "e2e": {"value": val, "unit": "pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "secondary": {"metric": "gp_mll_grad_evals_per_sec", "value": mll_v, "unit": "evals/s",
+                          "sample": f"2 of the 64 restarts ({mll_dt:.1f} s), oracle neg_mll_and_grad at n={N_TRAIN}, "
+                                    f"{cores} BLAS threads", "cores": cores, "kind": "port"}}
     print(json.dumps(line), flush=True)
 
 
@@ -170,6 +242,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--m-per-gpu", type=int, default=M_PER_GPU)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true", help="headline + roofline only (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -182,7 +255,7 @@ def main():
     _ensure_native()
     import torch
     import torch.distributed as tdist
-    from bobe_b200 import GP, ops, _lib
+    from bobe_b200 import GP, ops, _lib, dist
     from oracle import gp_oracle as O  # synthetic input recipe + the cpu_baseline leg only
 
     rank = int(os.environ.get("RANK", "0"))
@@ -191,34 +264,14 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL_DEBUG=VERSION (set in this image) makes NCCL print its version banner on STDOUT, in front of the one
-        # JSON line the driver parses; keep warnings, drop the banner (an explicit INFO / TRACE request is respected)
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL_DEBUG=VERSION (set in this image) makes NCCL print its version banner on STDOUT; stdout is already
+        # redirected above, so nothing is silenced here: the setting the caller chose stays in force
         tdist.init_process_group("nccl", device_id=dev)
 
     def barrier():
         if world > 1:
             tdist.barrier()
         torch.cuda.synchronize()
-
-    M = args.m_per_gpu
-    X, y = O.synthetic_training_set(N_TRAIN, DIM)
-    gp = GP(X, y, kernel=KERNEL, lengthscales=np.full(DIM, ELL), kernel_variance=1.0, device=dev)
-    rngq = np.random.default_rng(1 + rank)
-    Xq_host = torch.from_numpy(rngq.uniform(0.0, 1.0, (M, DIM))).pin_memory()
-    Xq = Xq_host.to(dev)
-    gathered = [torch.empty(2 * M, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
-
-    def step_device():
-        mean, var = gp.predict_mean_var_batched(Xq)
-        if world > 1:  # closing all-gather of the sharded results (16 B/query)
-            tdist.all_gather(gathered, torch.cat([mean, var]))
-        return mean, var
-
-    def step_e2e():  # public API, host buffers: H2D of the queries and D2H of mean/var inside the timed region
-        mean, var = gp.predict_mean_var_batched(Xq_host)
-        return mean, var
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -235,15 +288,57 @@ def main():
             tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
         return float(ms.item()) / steps
 
+    M = args.m_per_gpu
+    M_all = M * world
+    X, y = O.synthetic_training_set(N_TRAIN, DIM)
+    gp = GP(X, y, kernel=KERNEL, lengthscales=np.full(DIM, ELL), kernel_variance=1.0, device=dev)
+    lo, hi = dist.shard_bounds(M_all, rank, world)
+    # the FULL query set is what the sharding layer takes; every rank only ever reads its own block, so only that block
+    # is filled (device copy for the device-resident number, pinned host copy for the end-to-end number)
+    gen = torch.Generator(device=dev).manual_seed(1 + rank)
+    Xq_all = torch.empty((M_all, DIM), dtype=torch.float64, device=dev)
+    Xq_all[lo:hi] = torch.rand((hi - lo, DIM), dtype=torch.float64, device=dev, generator=gen)
+    Xq_host_all = torch.empty((M_all, DIM), dtype=torch.float64, pin_memory=True) if world == 1 else None
+    if world > 1:  # pin only this rank's block (N x 128 MB of pinned memory per rank otherwise)
+        own = torch.empty((hi - lo, DIM), dtype=torch.float64, pin_memory=True)
+        own.copy_(Xq_all[lo:hi])
+
+        class _HostView:  # what dist.predict_sharded needs of the full host array: shape and the rank's own slice
+            shape = (M_all, DIM)
+
+            def __getitem__(self, s):
+                assert s.start == lo and s.stop == hi
+                return own
+        Xq_host_all = _HostView()
+    else:
+        Xq_host_all.copy_(Xq_all)
+
+    def step_device():  # device-resident queries, results gathered on every rank (16 B/query)
+        return dist.predict_sharded(gp, Xq_all, want_var=True, gather=True)
+
+    def step_e2e():  # public API, host buffers: H2D of the queries and D2H of mean/var inside the timed region
+        # (each rank keeps its block of the results on its host: the all-gather is part of the device-resident number)
+        return dist.predict_sharded(gp, Xq_host_all, want_var=True, gather=False)
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     ms_step = timed(step_device, args.steps, max(args.warmup, 3))
     clocks = sampler.stop() if rank == 0 else None
-    value = world * M / (ms_step / 1e3)
+    value = M_all / (ms_step / 1e3)
 
     ms_e2e = timed(step_e2e, max(2, min(args.steps, 3)), 1)
-    e2e_value = world * M / (ms_e2e / 1e3)
+    e2e_value = M_all / (ms_e2e / 1e3)
+
+    # ---- strong scaling of the same sweep: M = 1e6 queries in total, split over the ranks ------------------------------
+    strong = None
+    if not args.skip_extras:
+        Ms = min(M_STRONG, M_all)
+        Xq_s = Xq_all[:Ms] if world == 1 else torch.rand((Ms, DIM), dtype=torch.float64, device=dev,
+                                                         generator=torch.Generator(device=dev).manual_seed(11))
+        ms_s = timed(lambda: dist.predict_sharded(gp, Xq_s, want_var=True, gather=True), args.steps, 3)
+        strong = {"metric": "gp_predict_mean_var_pts_per_sec", "value": Ms / (ms_s / 1e3), "unit": "pts/s",
+                  "scaling": "strong", "m_total": Ms, "m_per_gpu": -(-Ms // world), "ms_per_step": ms_s, "steps": args.steps}
 
     # ---- roofline of the dominant kernel (trmm_sumsq), timed alone with CUDA events on the launching stream ----
     npad = ops.npad(N_TRAIN)
@@ -262,60 +357,90 @@ def main():
     achieved = flops_per_launch / (ms_k / 1e3) / 1e12
     chunks = -(-M // rows)
     traffic = None  # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (same chunk shape)
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01", "trmm_sumsq_ncu.json")) as f:
-            j = json.load(f)
-        traffic = float(j["dram_bytes_read"]) + float(j["dram_bytes_write"])
-    except Exception:
-        pass
+    for rnd in ("r02", "r01"):
+        try:
+            with open(os.path.join(ROOT, "profiles", rnd, "trmm_sumsq_ncu.json")) as f:
+                j = json.load(f)
+            traffic = float(j["dram_bytes_read"]) + float(j["dram_bytes_write"])
+            break
+        except Exception:
+            pass
     roofline = {"bound": "tensor", "kernel": "trmm_sumsq_tma_kernel (FP64 DMMA.8x8x4 fed by TMA on mbarriers; no tcgen05 f64 kind exists)",
                 "achieved": achieved, "peak": peaks["fp64_dgemm_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["fp64_dgemm_tflops"], "traffic": traffic,
                 "peak_source": peaks["src"], "flops_per_launch": flops_per_launch, "ms_per_launch": ms_k,
                 "share_of_step": chunks * ms_k / ms_step}
+    del kstar
 
-    # ---- secondary BASELINE metric: log-ML + gradient evals/sec, 64 restarts sharded over the ranks -------------
-    ref_gp = O.OracleGP(X, y, kernel=KERNEL, lengthscales=np.full(DIM, ELL))
-    x0 = O.synthetic_restarts(ref_gp, R_TOTAL)
-    lo, hi = rank * R_TOTAL // world, (rank + 1) * R_TOTAL // world
-    lp = torch.as_tensor(x0[lo:hi], device=dev)
-    allv = [torch.empty(hi - lo, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
+    # ---- secondary BASELINE metric: log-ML + gradient evals/sec, 64 restarts sharded over the ranks (strong) -----------
+    secondary = wipv = None
+    if not args.skip_extras:
+        ref_gp = O.OracleGP(X, y, kernel=KERNEL, lengthscales=np.full(DIM, ELL))
+        x0 = O.synthetic_restarts(ref_gp, R_TOTAL)
+        s2 = ClockSampler(local_rank)
+        if rank == 0:
+            s2.start()
+        ms_mll = timed(lambda: dist.mll_grad_sharded(gp, x0), max(10, args.steps), 3)
+        clocks2 = s2.stop() if rank == 0 else None
+        v_all, _ = dist.mll_grad_sharded(gp, x0)
+        mll_flops = R_TOTAL * (N_TRAIN ** 3 + N_TRAIN ** 2 * (5 * DIM + 10 + 8))
+        r_lo, r_hi = dist.shard_bounds(R_TOTAL, rank, world)
+        secondary = {"metric": "gp_mll_grad_evals_per_sec", "value": R_TOTAL / (ms_mll / 1e3), "unit": "evals/s",
+                     "restarts_total": R_TOTAL, "restarts_per_gpu": r_hi - r_lo, "ms_per_round": ms_mll,
+                     "steps": max(10, args.steps), "warmup": 3, "non_pd_restarts": int(np.isnan(v_all).sum()),
+                     "scaling": "strong", "api": "bobe_b200.dist.mll_grad_sharded -> GP.neg_mll_and_grad_batched (host in/out, "
+                     "priors on the host, all-gather of (value, gradient) rows inside the timed region)",
+                     "algorithmic_tflops": mll_flops / (ms_mll / 1e3) / 1e12,
+                     "frac_of_fp64_peak": mll_flops / (ms_mll / 1e3) / 1e12 / (peaks["fp64_dgemm_tflops"] * world),
+                     "clocks": clocks2}
 
-    def step_mll():
-        val, grad, info = ops.mll_grad_batched(KERNEL, gp._X_dev, gp._y_dev, lp, True, 1.0, float(gp.noise))
-        if world > 1:
-            tdist.all_gather(allv, val)
-        return val
-    ms_mll = timed(step_mll, 3, 2)
-    v_mll = step_mll()
-    n_nan = int(torch.isnan(v_mll).sum().item())
-    mll_flops = R_TOTAL * (N_TRAIN ** 3 + N_TRAIN ** 2 * (5 * DIM + 10 + 8))
-    secondary = {"metric": "gp_mll_grad_evals_per_sec", "value": R_TOTAL / (ms_mll / 1e3), "unit": "evals/s",
-                 "restarts_total": R_TOTAL, "restarts_per_gpu": hi - lo, "ms_per_round": ms_mll,
-                 "non_pd_restarts_on_rank0": n_nan, "scaling": "strong",
-                 "algorithmic_tflops": mll_flops / (ms_mll / 1e3) / 1e12,
-                 "frac_of_fp64_peak": mll_flops / (ms_mll / 1e3) / 1e12 / (peaks["fp64_dgemm_tflops"] * world)}
+        # ---- BASELINE config 5: WIPV, n = 4000, d = 12, n_mc = 1e5, C = 8, MC columns sharded (strong) ----------------
+        Xe, ye = O.synthetic_training_set(E_N, E_DIM)
+        gpe = GP(Xe, ye, kernel="rbf", lengthscales=np.full(E_DIM, 1.0), kernel_variance=1.0, device=dev)
+        mc = torch.rand((E_NMC, E_DIM), dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+        cand = torch.rand((E_CAND, E_DIM), dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(6))
+        ms_w = timed(lambda: dist.wipv_sharded(gpe, mc, cand), max(5, args.steps), 2)
+        w_flops = float(E_N) ** 2 * (E_NMC + E_CAND) + E_N * E_NMC * (3 * E_DIM + 3) + 2.0 * E_N * E_CAND * E_NMC
+        wipv = {"metric": "wipv_acquisitions_per_sec", "value": 1e3 / ms_w, "unit": "calls/s", "ms_per_call": ms_w,
+                "scaling": "strong", "n": E_N, "d": E_DIM, "n_mc": E_NMC, "candidates": E_CAND,
+                "mc_points_per_sec": E_NMC / (ms_w / 1e3), "api": "bobe_b200.dist.wipv_sharded (MC columns sharded)",
+                "algorithmic_tflops": w_flops / (ms_w / 1e3) / 1e12,
+                "frac_of_fp64_peak": w_flops / (ms_w / 1e3) / 1e12 / (peaks["fp64_dgemm_tflops"] * world)}
+        del gpe, mc
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
-        cpu_predict_sample(2048)
+        policy = cpu_pick_policy()
         sample = 131072
-        v, dt = cpu_predict_sample(sample)
-        cpu_baseline = {"value": v, "unit": "pts/s", "cores": os.cpu_count(), "kind": "port",
+        v, dt = cpu_predict_sample(sample, policy)
+        cores = os.cpu_count()
+        pol = (f"{cores} Python threads x 1 BLAS thread, chunks of {CPU_CHUNK}" if policy == "threads"
+               else f"1 Python thread x {cores} BLAS threads, chunks of {8 * CPU_CHUNK}")
+        cpu_baseline = {"value": v, "unit": "pts/s", "cores": cores, "kind": "port",
                         "sample": f"{sample} of the 1e6 queries ({dt:.1f} s), NumPy/SciPy(OpenBLAS) restatement of "
-                                  f"BOBE/gp.py predict_mean+predict_var, {os.cpu_count()} threads x query chunks of {CPU_CHUNK}; JAX is not installable here"}
+                                  f"BOBE/gp.py predict_mean+predict_var, {pol}; JAX is not installable here"}
+        if secondary is not None:
+            mv, mdt = cpu_mll_grad_evals(2)
+            secondary["cpu_baseline"] = {"value": mv, "unit": "evals/s", "cores": cores, "kind": "port",
+                                         "sample": f"2 of the 64 restarts ({mdt:.1f} s): oracle neg_mll_and_grad at n={N_TRAIN}, "
+                                                   f"{cores} BLAS threads"}
 
     if rank == 0:
         line = {"metric": "gp_predict_mean_var_pts_per_sec", "value": value, "unit": "pts/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "n": N_TRAIN, "d": DIM, "kernel": KERNEL, "m_per_gpu": M,
-                           "l2": "inputs larger than L2 (128 MB of queries + 930 MB K* scratch per 3-chunk sweep)",
-                           "parallelism": f"query-sharded x{world}, replicated factor"},
-                "e2e": {"value": e2e_value, "unit": "pts/s", "h2d_bytes_per_step": M * DIM * 8,
-                        "d2h_bytes_per_step": M * 16, "ms_per_step": ms_e2e},
+                "config": bench_config(world, M),
+                "e2e": {"value": e2e_value, "unit": "pts/s", "h2d_bytes_per_step": (hi - lo) * DIM * 8,
+                        "d2h_bytes_per_step": (hi - lo) * 16, "ms_per_step": ms_e2e,
+                        "api": "bobe_b200.dist.predict_sharded(gp, host queries) -> GP._predict (pinned staging, pipelined)"},
                 "gpu_launches": args.steps * (chunks + -(-chunks // 3) + 1),  # per step: prescale + trmm_sumsq per chunk + kmat per 3 chunks
-                "clocks": clocks, "roofline": roofline, "secondary": secondary}
+                "clocks": clocks, "roofline": roofline}
+        if strong is not None:
+            line["strong"] = strong
+        if secondary is not None:
+            line["secondary"] = secondary
+        if wipv is not None:
+            line["wipv"] = wipv
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         sys.stdout.flush()

@@ -224,7 +224,7 @@ FactorLayout factor_layout(void* ws, int64_t ws_bytes, int64_t n, int64_t d, int
     l.Linv = c.take(need_Linv ? batch * m2 : 0);
     l.Q = c.take(batch * factor_q_elems(npad));
     l.diag = c.take(batch * npad);
-    l.stat = c.take(3 * batch);
+    l.stat = c.take(2 * batch + (factor_gate_rows(npad) * batch + 1) / 2);  // min / max pivot + the gate rows (ints)
     l.z = c.take(solve_ws_doubles(npad, batch));
     l.alpha = c.take(batch * npad);
     l.xs = c.take(batch * d * npad);
@@ -272,11 +272,75 @@ extern "C" int32_t bobe_factorize(void* stream_, int32_t kind, const double* X, 
         StreamPool* pool = stream_pool();
         if (!pool) return BOBE_E_CUDA;
         std::lock_guard<std::mutex> pool_lock(pool->enqueue_mu);
-        if (int32_t rc = factor_any(stream, pool, 0, fb, npad, (int)batch)) return rc;
+        if (int32_t rc = factor_on_pool(stream, pool, fb, npad, (int)batch)) return rc;
     }
     SolveArgs sa{kind, X, ls, kv, d, noise, l.xs};
     return launch_solve_vectors(stream, fb, sa, y, n, npad, (int)batch, l.z, alpha ? alpha : l.alpha, logdet, quad,
                                 info);
+}
+
+// ---- factorise a caller-supplied K (gp_mll) ---------------------------------------------------------------------
+extern "C" int64_t bobe_cholesky_workspace_bytes(int64_t n, int64_t batch) {
+    if (n <= 0 || batch <= 0) return 0;
+    return factor_layout(nullptr, 0, n, 1, batch, true, true).bytes;
+}
+
+extern "C" int32_t bobe_cholesky_batched(void* stream_, const double* K, int64_t n, int64_t ldk, int64_t batch,
+                                         const double* y, double* L, double* Linv, double* alpha, double* logdet,
+                                         double* quad, int32_t* info, void* ws, int64_t ws_bytes) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!K || !y || !ws || n <= 0 || ldk < n || batch <= 0) {
+        set_error("cholesky_batched: bad arguments");
+        return BOBE_E_ARG;
+    }
+    FactorLayout l = factor_layout(ws, ws_bytes, n, 1, batch, L == nullptr, Linv == nullptr);
+    if (!l.fits) {
+        set_error("cholesky_batched: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)l.bytes);
+        return BOBE_E_WORKSPACE;
+    }
+    if ((L && !aligned16(L)) || (Linv && !aligned16(Linv))) {
+        set_error("cholesky_batched: L / Linv must be 16-byte aligned");
+        return BOBE_E_ARG;
+    }
+    const int npad = (int)npad_of(n);
+    FactorBuffers fb{l.KB, L ? L : l.L, l.Lt, Linv ? Linv : l.Linv, l.U, l.Q, l.diag, l.stat, (int*)(l.stat + 2 * batch), 0, 0};
+    if (int32_t rc = launch_pad_k(stream, K, ldk, n * ldk, (int)n, npad, (int)batch, fb.KB)) return rc;
+    {
+        StreamPool* pool = stream_pool();
+        if (!pool) return BOBE_E_CUDA;
+        std::lock_guard<std::mutex> pool_lock(pool->enqueue_mu);
+        if (int32_t rc = factor_on_pool(stream, pool, fb, npad, (int)batch)) return rc;
+    }
+    SolveArgs sa{};
+    sa.Kin = K; sa.ldk = ldk; sa.kstride = n * ldk;
+    return launch_solve_vectors(stream, fb, sa, y, n, npad, (int)batch, l.z, alpha ? alpha : l.alpha, logdet, quad, info);
+}
+
+// ---- squared distances ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) dist_sq_kernel(const double* __restrict__ xa, int64_t n1, const double* __restrict__ xb,
+                                                      int64_t n2, int d, double* __restrict__ out, int64_t ldo) {
+    const int64_t i = (int64_t)blockIdx.y * 16 + (threadIdx.x >> 4), j = (int64_t)blockIdx.x * 16 + (threadIdx.x & 15);
+    if (i >= n1 || j >= n2) return;
+    double s = 0.0;
+    for (int k = 0; k < d; ++k) {  // direct differences, summed in index order (BOBE/gp.py:94-96)
+        const double df = xa[i * d + k] - xb[j * d + k];
+        s = fma(df, df, s);
+    }
+    out[i * ldo + j] = s;
+}
+}  // namespace
+
+extern "C" int32_t bobe_dist_sq(void* stream, const double* xa, int64_t n1, const double* xb, int64_t n2, int64_t d,
+                                double* out, int64_t ldo) {
+    if (!xa || !xb || !out || n1 < 0 || n2 < 0 || d <= 0 || ldo < n2 || n1 > 65535 * 16) {
+        set_error("dist_sq: bad arguments");
+        return BOBE_E_ARG;
+    }
+    if (n1 == 0 || n2 == 0) return BOBE_OK;
+    dist_sq_kernel<<<dim3((unsigned)((n2 + 15) / 16), (unsigned)((n1 + 15) / 16)), 256, 0, (cudaStream_t)stream>>>(
+        xa, n1, xb, n2, (int)d, out, ldo);
+    return check_launch("dist_sq_kernel");
 }
 
 // ---- rank-b append ------------------------------------------------------------------------------------------

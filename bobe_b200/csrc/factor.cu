@@ -48,7 +48,7 @@ struct Rec {
         int nb = b1 - b0;
         if (nb <= 2) {  // leaf: one CTA per matrix does the whole 64- or 128-block in shared memory
             static const int panel4 = (int)env_int("BOBE_LEAF_PANEL4", 1);
-            LeafIO io{fb.KB, fb.L, fb.Lt, fb.Linv, fb.U, fb.diag, fb.dstat, fb.gate, npad, b0 * NB, panel4};
+            LeafIO io{fb.KB, fb.L, fb.Lt, fb.Linv, fb.U, fb.diag, fb.dstat, fb.gate, npad, b0 * NB, panel4, fb.gate, fb.gate, 3};
             if (nb == 1) {
                 if ((rc = ensure_smem<leaf64_kernel>(LEAF64_SMEM)) != BOBE_OK) return;
                 launch_pdl(leaf64_kernel, dim3(1, 1, batch), dim3(LEAF_THREADS), LEAF64_SMEM, stream, io);
@@ -175,11 +175,27 @@ int32_t factor_any(cudaStream_t stream, StreamPool* pool, int lane, const Factor
         }
         return factor_recursive(stream, fb, npad, batch);
     }
+    return factor_tiled(factor_exec(stream, pool, lane, batch), fb, npad, batch);
+}
+
+int32_t factor_on_pool(cudaStream_t stream, StreamPool* pool, const FactorBuffers& fb, int npad, int batch) {
+    cudaStream_t st = pool->streams[0];
+    if (cudaEventRecord(pool->fork, stream) != cudaSuccess || cudaStreamWaitEvent(st, pool->fork, 0) != cudaSuccess) {
+        set_error("factor: fork failed");
+        return BOBE_E_CUDA;
+    }
+    const int32_t rc = factor_any(st, pool, 0, fb, npad, batch);
+    cudaEventRecord(pool->join[0], st);  // join also on failure
+    cudaStreamWaitEvent(stream, pool->join[0], 0);
+    return rc;
+}
+
+FactorExec factor_exec(cudaStream_t stream, StreamPool* pool, int lane, int batch) {
     static const int64_t la_max = env_int("BOBE_LOOKAHEAD_MAX", 16);
     static const int64_t pw = env_int("BOBE_FACTOR_PW", 4);  // tile columns per outer panel (the same for every batch size)
-    const bool la = pool && batch <= la_max && lane >= 0 && 2 * lane + 1 < POOL_STREAMS;
-    FactorExec ex{stream, la ? pool->streams[2 * lane + 1] : nullptr, pool, lane < 0 ? 0 : lane, (int)pw};
-    return factor_tiled(ex, fb, npad, batch);
+    const bool la = pool && batch <= la_max && lane >= 0 && POOL_LANE_STREAMS * lane + 3 < POOL_STREAMS;
+    cudaStream_t* ps = pool ? pool->streams + POOL_LANE_STREAMS * (lane < 0 ? 0 : lane) : nullptr;
+    return FactorExec{stream, la ? ps[1] : nullptr, la ? ps[2] : nullptr, la ? ps[3] : nullptr, pool, lane < 0 ? 0 : lane, (int)pw};
 }
 
 int32_t launch_kinv(cudaStream_t stream, const FactorBuffers& fb, int npad, int batch) {
@@ -227,6 +243,39 @@ __global__ void __launch_bounds__(256) residual_kernel(const double* __restrict_
     if (i >= npad || (gate && gate[z] == 0)) return;
     int64_t o = z * npad + i;
     r[o] = i < n ? (ypad[i] - k0a[o]) - noise * alpha[o] : 0.0;
+}
+
+// out[z][i] = sum_j Ksym[i][j] x[z][j] for a symmetric matrix of which only the LOWER triangle is stored (one warp per
+// row; the j > i part walks down column i).  Only runs for gated (ill-conditioned) matrices.
+__global__ void __launch_bounds__(256) symv_lower_kernel(const double* __restrict__ K, int64_t ldk, int64_t kstride, int n,
+                                                         const double* __restrict__ x, int64_t xstride,
+                                                         double* __restrict__ out, int64_t ostride,
+                                                         const int* __restrict__ gate) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int64_t z = blockIdx.y;
+    if (row >= n || (gate && gate[z] == 0)) return;
+    const double* Kz = K + z * kstride;
+    const double* xv = x + z * xstride;
+    double s = 0.0;
+    for (int j = lane; j <= row; j += 32) s = fma(Kz[(int64_t)row * ldk + j], xv[j], s);
+    for (int j = row + 1 + lane; j < n; j += 32) s = fma(Kz[(int64_t)j * ldk + row], xv[j], s);
+    s = warp_sum(s);
+    if (lane == 0) out[z * ostride + row] = s;
+}
+
+// KB[z] = [K[z] lower 0; 0 I] padded to npad (the factorisation reads the lower triangle only)
+__global__ void __launch_bounds__(256) pad_k_kernel(const double* __restrict__ K, int64_t ldk, int64_t kstride, int n,
+                                                    int npad, double* __restrict__ KB) {
+    const int64_t z = blockIdx.z;
+    const int i = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= npad) return;
+    double v = (i == j) ? 1.0 : 0.0;
+    if (i < n && j <= i) v = K[z * kstride + (int64_t)i * ldk + j];
+    KB[z * (int64_t)npad * npad + (int64_t)i * npad + j] = v;
+}
+int32_t launch_pad_k(cudaStream_t stream, const double* K, int64_t ldk, int64_t kstride, int n, int npad, int batch, double* KB) {
+    pad_k_kernel<<<dim3((npad + 255) / 256, npad, batch), 256, 0, stream>>>(K, ldk, kstride, n, npad, KB);
+    return check_launch("pad_k_kernel");
 }
 
 __global__ void __launch_bounds__(256) factor_scalars_kernel(const double* __restrict__ diag,
@@ -285,7 +334,12 @@ int32_t launch_solve_vectors(cudaStream_t stream, const FactorBuffers& fb, const
     matvec_tri_kernel<<<grid, 256, 0, stream>>>(fb.Linv, ypad, 0, zv, npad, npad, 0, 0, nullptr);
     matvec_tri_kernel<<<grid, 256, 0, stream>>>(fb.U, zv, npad, alpha, npad, npad, 1, 0, nullptr);
     if (int32_t rc = check_launch("solve_vectors")) return rc;
-    {
+    if (sa.Kin) {  // caller-supplied K: residual against K itself (its diagonal already holds the noise)
+        symv_lower_kernel<<<grid, 256, 0, stream>>>(sa.Kin, sa.ldk, sa.kstride, (int)n, alpha, npad, k0a, npad, fb.gate);
+        residual_kernel<<<dim3((npad + 255) / 256, batch), 256, 0, stream>>>(ypad, k0a, alpha, 0.0, n, npad, rv, fb.gate);
+        matvec_tri_kernel<<<grid, 256, 0, stream>>>(fb.Linv, rv, npad, k0a, npad, npad, 0, 0, fb.gate);
+        matvec_tri_kernel<<<grid, 256, 0, stream>>>(fb.U, k0a, npad, alpha, npad, npad, 1, 1, fb.gate);
+    } else {
         KmatArgs ka{};
         ka.xa = sa.X; ka.xb = sa.X; ka.ls = sa.ls; ka.kv_ptr = sa.kv; ka.alpha = alpha; ka.mean_out = k0a;
         ka.xbs = sa.xs; ka.xbs_ld = npad; ka.xbs_stride = sa.d * (int64_t)npad;

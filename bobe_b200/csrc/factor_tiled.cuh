@@ -20,9 +20,13 @@
 // The critical path of one matrix is T x (small update + leaf + panel) instead of the ~230 dependent launches and 16
 // serial 128-leaves of the recursive scheme this replaces; the O(n^3) products run beside it.
 //
-// Phase 2 -- inverse.  X = L^-1 by recursive doubling over the tiles: the nodes of one level of the tree are independent,
-// so each level is TWO launches for all its nodes and all matrices (GemmArgs node mode):
+// Phase 2 -- inverse.  X = L^-1 by recursive doubling over the tiles; per node of the tree (left half X11, right half X22)
 //     P^T = U11 L21^T   then   X21 = -X22 P      (U = X^T is kept alongside X: every product stays "NT")
+// Single-stream mode: the nodes of one level are independent, so each level is TWO launches for all its nodes and all
+// matrices (GemmArgs node mode), after phase 1.  Look-ahead mode: every product is issued on a third stream as soon as its
+// inputs exist -- P^T of a node when its left half is complete (half-way through the node's tile columns), X21 when its
+// right half is -- so that phase 2 runs in the shadow of the phase-1 chain and only the last X21 of each level (the
+// right spine of the tree) is left when the last leaf finishes.  Same products, same results either way.
 //
 // A non-PD matrix yields NaN outputs and info = 1 for that batch entry only, never an error.
 // (included by factor.cu after the helper kernels it shares with the vector solves)
@@ -46,9 +50,16 @@ StreamPool* stream_pool() {
     if (!pools[dev]) {
         StreamPool* p = new StreamPool();
         bool ok = cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming) == cudaSuccess;
-        for (int i = 0; i < POOL_STREAMS && ok; ++i)
-            ok = cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking) == cudaSuccess &&
+        // four streams per lane, in falling priority: the dependent chain, the rest of the current column, the trailing
+        // products, the inverse tree -- when an SM slot frees up, a waiting CTA of the chain goes first
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);  // lo: least priority (numerically largest), hi: greatest
+        for (int i = 0; i < POOL_STREAMS && ok; ++i) {
+            const int r = i % POOL_LANE_STREAMS;  // 0 chain, 1 rest of column, 2 trailing products, 3 inverse tree
+            const int prio = r == 0 ? hi : (r == 1 ? hi + (lo - hi) / 3 : (r == 2 ? hi + 2 * (lo - hi) / 3 : lo));
+            ok = cudaStreamCreateWithPriority(&p->streams[i], cudaStreamNonBlocking, prio) == cudaSuccess &&
                  cudaEventCreateWithFlags(&p->join[i], cudaEventDisableTiming) == cudaSuccess;
+        }
         if (!ok) {
             set_error("stream_pool: could not create internal streams: %s", cudaGetErrorString(cudaGetLastError()));
             delete p;
@@ -80,14 +91,28 @@ struct Tiled {
     int64_t mstride, qstride;
     int32_t rc = BOBE_OK;
     int T;
-    bool two;                        // look-ahead on a second stream
-    std::vector<int> last_writer;    // per tile column: index of the bulk event of the last bulk op that wrote it (-1: none)
-    int n_bulk = 0;                  // bulk ops issued so far (their events are ring[lane][T + idx])
-    int crit_waited = -1;            // highest bulk event index the critical stream already waited for
-    int bulk_waited = -1;            // highest column event the bulk stream already waited for
+    bool two;                        // look-ahead mode: chain / rest-of-column / trailing products / inverse on four streams
+    int inv_waited = -1;             // highest column the inverse stream already waited for
+    bool inv_used = false;
+    std::vector<int> last_writer;    // per tile column: index of the last bulk op that wrote it (-1: none)
+    int n_bulk = 0;                  // bulk ops issued so far
+    int crit_waited = -1, mid_waited = -1;  // highest bulk op the critical / mid stream already waited for
+    int bulk_waited = -1;            // highest column the bulk stream already waited for
 
     int off(int j) const { return j * TW; }
     int width(int j) const { return npad - off(j) < TW ? npad - off(j) : TW; }
+
+    // events of lane ex.lane:  [j] top tile of panel j done (critical stream);  [T + j] leaf j done;
+    // [2T + j] column j complete (mid stream);  [3T + j] rows of tile j+1 of column j updated (mid stream);
+    // [4T + i] bulk op i done;  [5T + 1] inverse stream done
+    cudaEvent_t ev_top(int j) const { return ex.pool->event(ex.lane, j); }
+    cudaEvent_t ev_leaf(int j) const { return ex.pool->event(ex.lane, T + j); }
+    cudaEvent_t ev_col(int j) const { return ex.pool->event(ex.lane, 2 * T + j); }
+    cudaEvent_t ev_u1(int j) const { return ex.pool->event(ex.lane, 3 * T + j); }
+    cudaEvent_t ev_bulk(int i) const { return ex.pool->event(ex.lane, 4 * T + i); }
+    cudaEvent_t ev_inv() const { return ex.pool->event(ex.lane, 5 * T + 1); }
+    cudaStream_t s_mid() const { return two ? ex.mid : ex.crit; }
+    cudaStream_t s_bulk() const { return two ? ex.bulk : ex.crit; }
 
     GemmArgs base() const {
         GemmArgs g{};
@@ -106,39 +131,42 @@ struct Tiled {
         }
         return e == cudaSuccess;
     }
+    void record(cudaEvent_t e, cudaStream_t st) {
+        if (two) ok(cudaEventRecord(e, st), "event record");
+    }
+    void wait(cudaStream_t st, cudaEvent_t e) {
+        if (two) ok(cudaStreamWaitEvent(st, e, 0), "event wait");
+    }
 
-    // KB[oc:, oc:oc+ncols] -= L[oc:, k0:k1] L[oc:oc+ncols, k0:k1]^T   (tiles above the diagonal skipped)
-    void update(cudaStream_t st, int oc, int ncols, int k0, int k1) {
-        if (k1 <= k0 || ncols <= 0) return;
+    // KB[r0 : r0+nrows, oc : oc+ncols] -= L[r0.., k0:k1] L[oc : oc+ncols, k0:k1]^T.  r0 == oc: the block starts on the
+    // diagonal and tiles above it are skipped; r0 >= oc + ncols: a block strictly below the diagonal.
+    void update(cudaStream_t st, int r0, int nrows, int oc, int ncols, int k0, int k1) {
+        if (k1 <= k0 || ncols <= 0 || nrows <= 0) return;
         GemmArgs g = base();
-        g.A = fb.L + (int64_t)oc * npad + k0;
-        g.Bt = g.A;
-        g.C = fb.KB + (int64_t)oc * npad + oc;
+        g.A = fb.L + (int64_t)r0 * npad + k0;
+        g.Bt = fb.L + (int64_t)oc * npad + k0;
+        g.C = fb.KB + (int64_t)r0 * npad + oc;
         g.D = g.C;
-        g.M = npad - oc; g.N = ncols; g.K = k1 - k0; g.alpha = -1.0; g.flags = GEMM_C_LOWER;
+        g.M = nrows; g.N = ncols; g.K = k1 - k0; g.alpha = -1.0; g.flags = (r0 == oc) ? GEMM_C_LOWER : 0;
         gemm(st, g);
     }
 
-    // column events of the critical stream: ring[lane][j];  bulk events: ring[lane][T + idx]
-    void crit_done(int j) {
-        if (two) ok(cudaEventRecord(ex.pool->event(ex.lane, j), ex.crit), "event record");
-    }
     void bulk_needs_col(int j) {  // the next bulk op reads L columns <= j
         if (two && j > bulk_waited) {
-            ok(cudaStreamWaitEvent(ex.bulk, ex.pool->event(ex.lane, j), 0), "event wait");
+            wait(ex.bulk, ev_col(j));
             bulk_waited = j;
         }
     }
     void bulk_wrote(int c0, int c1) {  // the bulk op just issued wrote the tile columns [c0, c1)
         if (!two) return;
-        ok(cudaEventRecord(ex.pool->event(ex.lane, T + n_bulk), ex.bulk), "event record");
+        record(ev_bulk(n_bulk), ex.bulk);
         for (int c = c0; c < c1 && c < T; ++c) last_writer[c] = n_bulk;
         ++n_bulk;
     }
-    void crit_needs_col(int j) {  // the critical stream is about to touch KB column j
-        if (two && last_writer[j] > crit_waited) {
-            ok(cudaStreamWaitEvent(ex.crit, ex.pool->event(ex.lane, T + last_writer[j]), 0), "event wait");
-            crit_waited = last_writer[j];
+    void needs_col(cudaStream_t st, int& waited, int j) {  // `st` is about to touch KB column j
+        if (two && last_writer[j] > waited) {
+            wait(st, ev_bulk(last_writer[j]));
+            waited = last_writer[j];
         }
     }
 
@@ -146,7 +174,12 @@ struct Tiled {
         if (rc != BOBE_OK) return;
         // BOBE_LEAF: 2 (default) recursive 32-base elimination, 1 four columns per barrier on the 64-block, 0 one column
         static const int mode = (int)env_int("BOBE_LEAF", 2);
-        LeafIO io{fb.KB, fb.L, nullptr, fb.Linv, fb.U, fb.diag, fb.dstat, fb.gate, npad, off(j), mode == 0 ? 0 : 1};
+        // products with 128-row tiles read whole diagonal tiles: then (and only then) the leaf also zeroes the 64-blocks
+        // on the other side of the diagonal (the external path has zeroed the whole triangle beforehand anyway)
+        static const bool wide_tiles = env_int("BOBE_TILE", 0) > 1 || env_int("BOBE_GEMM_TMA", 0) != 0;
+        // gate rows: [0] latest state (initial value before leaf 0), [j + 1] snapshot after leaf j
+        LeafIO io{fb.KB, fb.L, nullptr, fb.Linv, fb.U, fb.diag, fb.dstat, fb.gate + (int64_t)(j == 0 ? 0 : j) * batch, npad,
+                  off(j), mode == 0 ? 0 : 1, fb.gate + (int64_t)(j + 1) * batch, fb.gate, wide_tiles ? 1 : 0};
         auto go = [&](auto kernel, int smem) {
             if ((rc = ensure_smem_fn(kernel, smem)) != BOBE_OK) return;
             launch_pdl(kernel, dim3(1, 1, batch), dim3(LEAF_THREADS), smem, ex.crit, io);
@@ -159,64 +192,171 @@ struct Tiled {
         }
     }
 
-    // L[o+w:, o:o+w] = KB[o+w:, o:o+w] X_jj^T, then for gated (ill-conditioned) matrices one correction step
+    // L[r0 : r0+nrows, o:o+w] = KB[r0.., o:o+w] X_jj^T, then for gated (ill-conditioned) matrices one correction step
     //   R = C - L_col L_jj^T,  L_col += R X_jj^T
-    // (a product with an explicit inverse is not backward stable; measured in profiles/r01/accuracy_probe.txt)
-    void panel(int j) {
-        const int o = off(j), w = width(j), below = npad - o - w;
-        if (below <= 0) return;
-        const int64_t col = (int64_t)(o + w) * npad + o, dg = (int64_t)o * npad + o;
+    // (a product with an explicit inverse is not backward stable; measured in profiles/r01/accuracy_probe.txt).
+    // q: scratch of nrows x w doubles per matrix for R.
+    void panel(cudaStream_t st, int j, int r0, int nrows, double* q) {
+        if (nrows <= 0) return;
+        const int o = off(j), w = width(j);
+        const int64_t col = (int64_t)r0 * npad + o, dg = (int64_t)o * npad + o;
+        const int* gate = fb.gate + (int64_t)(j + 1) * batch;  // the state right after leaf j (see leaf())
         GemmArgs g = base();
         g.A = fb.KB + col; g.Bt = fb.Linv + dg; g.C = fb.L + col;
-        g.M = below; g.N = w; g.K = w; g.flags = GEMM_B_LOWER;
-        gemm(ex.crit, g);
+        g.M = nrows; g.N = w; g.K = w; g.flags = GEMM_B_LOWER;
+        gemm(st, g);
         g = base();
-        g.A = fb.L + col; g.Bt = fb.L + dg; g.D = fb.KB + col; g.C = fb.Q; g.ldc = w; g.strideC = qstride;
-        g.M = below; g.N = w; g.K = w; g.alpha = -1.0; g.flags = GEMM_B_LOWER; g.gate = fb.gate;
-        gemm(ex.crit, g);
+        g.A = fb.L + col; g.Bt = fb.L + dg; g.D = fb.KB + col; g.C = q; g.ldc = w; g.strideC = qstride;
+        g.M = nrows; g.N = w; g.K = w; g.alpha = -1.0; g.flags = GEMM_B_LOWER; g.gate = gate;
+        gemm(st, g);
         g = base();
-        g.A = fb.Q; g.lda = w; g.strideA = qstride; g.Bt = fb.Linv + dg; g.D = fb.L + col; g.C = fb.L + col;
-        g.M = below; g.N = w; g.K = w; g.flags = GEMM_B_LOWER; g.gate = fb.gate;
-        gemm(ex.crit, g);
+        g.A = q; g.lda = w; g.strideA = qstride; g.Bt = fb.Linv + dg; g.D = fb.L + col; g.C = fb.L + col;
+        g.M = nrows; g.N = w; g.K = w; g.flags = GEMM_B_LOWER; g.gate = gate;
+        gemm(st, g);
     }
 
-    void phase1() {
-        const int PW = ex.pw < 1 ? 1 : (ex.pw > T ? T : ex.pw);
-        cudaStream_t bulk = two ? ex.bulk : ex.crit;
-        for (int j = 0; j < T && rc == BOBE_OK; ++j) {
-            const int s = (j / PW) * PW;  // first tile column of this outer panel
-            crit_needs_col(j);
-            if (j > 0) {
-                if (j == s) {
-                    update(ex.crit, off(j), width(j), off(s - PW), off(s));  // the previous panel, for this column only
-                } else {
-                    update(ex.crit, off(j), width(j), off(j - 1), off(j));   // a2: the column just finished
+    // ---- inverse tree, one node at a time (look-ahead mode) ----------------------------------------------------
+    // scratch of level m inside fb.Lt (not used as L^T by this scheme): levels are laid out one after the other
+    double* pbuf(int m) const {
+        int64_t o = 0;
+        for (int mm = TW; mm < m; mm *= 2) o += (int64_t)mm * mm;
+        return fb.Lt + o;
+    }
+    void node_p1(cudaStream_t st, int m, int o) {  // P^T = U11 L21^T
+        const int m2 = npad - o - m < m ? npad - o - m : m;
+        if (m2 <= 0) return;
+        GemmArgs g = base();
+        g.A = fb.U + (int64_t)o * npad + o; g.Bt = fb.L + (int64_t)(o + m) * npad + o; g.C = pbuf(m); g.ldc = m2;
+        g.M = m; g.N = m2; g.K = m; g.flags = GEMM_A_UPPER;
+        gemm(st, g);
+    }
+    void node_p2(cudaStream_t st, int m, int o) {  // X21 = -X22 P
+        const int m2 = npad - o - m < m ? npad - o - m : m;
+        if (m2 <= 0) return;
+        GemmArgs g = base();
+        g.A = fb.Linv + (int64_t)(o + m) * (npad + 1); g.Bt = pbuf(m); g.ldb = m2;
+        g.C = fb.Linv + (int64_t)(o + m) * npad + o; g.Ct = fb.U + (int64_t)o * npad + (o + m);
+        g.M = m2; g.N = m; g.K = m2; g.alpha = -1.0; g.flags = GEMM_A_LOWER;
+        gemm(st, g);
+    }
+    // everything of the inverse tree that tile column j (just finished on the critical stream) makes possible
+    void eager_inverse(int j) {
+        const int done = j + 1;  // tile columns complete
+        bool first = true;
+        auto stream = [&]() {
+            if (first) {
+                first = false;
+                inv_used = true;
+                if (j > inv_waited) {
+                    wait(ex.inv, ev_col(j));
+                    inv_waited = j;
                 }
             }
-            leaf(j);
-            panel(j);
-            crit_done(j);
-            if (j + 1 >= T) break;
-            const bool panel_end = (j + 1) % PW == 0;
-            if (panel_end) {
-                // trailing update of everything behind the next column with this panel's k range
-                if (j + 2 < T) {
-                    bulk_needs_col(j);
-                    update(bulk, off(j + 2), npad - off(j + 2), off(s), off(j + 1));
-                    bulk_wrote(j + 2, T);
-                }
-            } else if (j + 2 < T && j + 2 < s + PW) {
-                // a1 of column j+2: the in-panel columns s .. j (column j+1 follows on the critical stream as a2)
-                bulk_needs_col(j);
-                update(bulk, off(j + 2), width(j + 2), off(s), off(j + 1));
-                bulk_wrote(j + 2, j + 3);
+            return ex.inv;
+        };
+        // X21 of every node whose right half ends here (at a node boundary, or at the end of the matrix), small to large
+        for (int m = TW; m < npad; m *= 2) {
+            const int w = m / TW;  // tiles per half
+            int t;
+            if (done == T)
+                t = (npad - 1) / (2 * m);
+            else if (done % (2 * w) == 0)
+                t = done / (2 * w) - 1;
+            else
+                continue;
+            const int o = 2 * m * t;
+            if (o + m < npad && o + m < done * TW) node_p2(stream(), m, o);
+        }
+        // P^T of the node whose left half ends here
+        if (done < T) {
+            int w = 1;
+            while (done % (2 * w) == 0) w *= 2;  // largest power of two dividing `done`
+            const int m = w * TW, t = (done / w - 1) / 2, o = 2 * m * t;
+            if ((done / w) % 2 == 1 && o + m == done * TW && o + m < npad) node_p1(stream(), m, o);
+        }
+    }
+
+    // One tile column.  Only ONE tile of each product is on the critical path: the next leaf needs tile (j+1, j+1) of the
+    // working matrix, which needs the rows of tile j+1 of this column's panel ("top").  Everything below follows on the mid
+    // stream while the next leaf runs -- for a batch of matrices those products are throughput-bound and would otherwise
+    // double the length of the chain.  Per column:
+    //   critical:  update of the diagonal tile;  leaf;  [after the mid stream's U1]  panel rows of tile j+1
+    //   mid:       U1 = update of the rows of tile j+1 (first, and signalled: the critical stream's panel reads them),
+    //              update of the rows below;  [after the leaf]  panel rows below tile j+1
+    void step(int j, int PW) {
+        const int s = (j / PW) * PW;  // first tile column of this outer panel
+        const int o = off(j), w = width(j), below = npad - o - w;
+        const int top = below < TW ? below : TW;  // rows of tile j+1
+        needs_col(ex.crit, crit_waited, j);
+        if (below > 0) needs_col(s_mid(), mid_waited, j);
+        if (j > 0) {
+            // the products of this column not applied yet: the previous outer panel (j == s) or the previous column
+            const int k0 = (j == s) ? off(s - PW) : off(j - 1), k1 = off(j);
+            // diagonal tile: its operand rows L[tile j, k0:k1) are the top of panel j-1 (this stream) and, at the start
+            // of an outer panel, lower rows of the columns before it (mid stream)
+            if (j == s && j >= 2) wait(ex.crit, ev_col(j - 2));
+            update(ex.crit, o, w, o, w, k0, k1);
+            if (below > 0) {
+                wait(s_mid(), ev_top(j - 1));  // the Bt operand L[tile j, k0:k1) includes the top of panel j-1
+                update(s_mid(), o + w, top, o, w, k0, k1);
+                record(ev_u1(j), s_mid());
+                update(s_mid(), o + w + top, below - top, o, w, k0, k1);
             }
         }
-        if (two && n_bulk > 0 && crit_waited < n_bulk - 1)  // join
-            ok(cudaStreamWaitEvent(ex.crit, ex.pool->event(ex.lane, T + n_bulk - 1), 0), "event wait");
+        leaf(j);
+        record(ev_leaf(j), ex.crit);
+        {   // U tile = (X tile)^T, off the critical path (first read by the inverse tree)
+            cudaStream_t st = two ? ex.inv : ex.crit;
+            if (two) {
+                wait(ex.inv, ev_leaf(j));
+                inv_used = true;
+            }
+            if (rc == BOBE_OK) {
+                launch_pdl(tile_transpose_kernel, dim3(w / 32, w / 32, batch), dim3(256), 0, st, (const double*)fb.Linv, fb.U, npad, o);
+                rc = check_launch("tile_transpose_kernel");
+            }
+        }
+        if (below > 0) {
+            if (j > 0) wait(ex.crit, ev_u1(j));
+            panel(ex.crit, j, o + w, top, fb.Q);                                   // rows of tile j+1
+            wait(s_mid(), ev_leaf(j));
+            panel(s_mid(), j, o + w + top, below - top, fb.Q + (int64_t)TW * TW);  // the rest
+        }
+        record(ev_top(j), ex.crit);
+        if (two) {  // column j complete = both parts
+            wait(s_mid(), ev_top(j));
+            record(ev_col(j), s_mid());
+            eager_inverse(j);
+        }
+        if (j + 1 >= T) return;
+        const bool panel_end = (j + 1) % PW == 0;
+        if (panel_end) {
+            // trailing update of everything behind the next column with this panel's k range
+            if (j + 2 < T) {
+                bulk_needs_col(j);
+                update(s_bulk(), off(j + 2), npad - off(j + 2), off(j + 2), npad - off(j + 2), off(s), off(j + 1));
+                bulk_wrote(j + 2, T);
+            }
+        } else if (j + 2 < T && j + 2 < s + PW) {
+            // a1 of column j+2: the in-panel columns s .. j (column j+1 follows as a2)
+            bulk_needs_col(j);
+            update(s_bulk(), off(j + 2), npad - off(j + 2), off(j + 2), width(j + 2), off(s), off(j + 1));
+            bulk_wrote(j + 2, j + 3);
+        }
+    }
+
+    void finish_phase1() {
+        if (!two) return;
+        if (n_bulk > 0 && crit_waited < n_bulk - 1) wait(ex.crit, ev_bulk(n_bulk - 1));  // join the bulk stream,
+        wait(ex.crit, ev_col(T - 1));                                                    // the mid stream
+        if (inv_used) {                                                                  // and the inverse stream
+            record(ev_inv(), ex.inv);
+            wait(ex.crit, ev_inv());
+        }
     }
 
     void phase2() {
+        if (two) return;  // done eagerly
         for (int m = TW; m < npad && rc == BOBE_OK; m *= 2) {
             const int nodes = (npad + 2 * m - 1) / (2 * m);
             GemmArgs g = base();
@@ -235,27 +375,60 @@ struct Tiled {
 
 }  // namespace
 
-int32_t factor_tiled(const FactorExec& ex, const FactorBuffers& fb, int npad, int batch) {
+// Stepwise interface: several sub-batches (each with its own streams) are advanced in lock step by the caller, so that the
+// host enqueues step j of every chain before step j + 1 of any (a chain is ~100 launches: enqueued one after the other,
+// the second chain would start half a millisecond late).
+struct TiledFactor {
+    FactorExec ex;
+    FactorBuffers fb;
+    Tiled t;
+    int pw;
+    TiledFactor(const FactorExec& e, const FactorBuffers& f, int npad, int batch)
+        : ex(e), fb(f), t{ex, fb, npad, batch, (int64_t)npad * npad, factor_q_elems(npad)} {}
+};
+
+TiledFactor* tiled_begin(const FactorExec& ex, const FactorBuffers& fb, int npad, int batch, int32_t* rc_out) {
+    *rc_out = BOBE_OK;
     if (npad % NB) {
         set_error("factor: npad=%d not a multiple of %d", npad, NB);
-        return BOBE_E_ARG;
+        *rc_out = BOBE_E_ARG;
+        return nullptr;
     }
     init_stat_kernel<<<(batch + 127) / 128, 128, 0, ex.crit>>>(fb.dstat, fb.gate, batch, fb.force_refine);
-    if (int32_t rc = check_launch("init_stat_kernel")) return rc;
+    if ((*rc_out = check_launch("init_stat_kernel")) != BOBE_OK) return nullptr;
     if (fb.zero_band == 0 && npad > NB) {  // buffers handed to the caller: the whole other triangle must read as zero
         zero_other_triangle_kernel<<<dim3(npad / NB, npad / NB, batch), 256, 0, ex.crit>>>(fb.L, nullptr, fb.Linv, fb.U, npad, 0);
-        if (int32_t rc = check_launch("zero_other_triangle_kernel")) return rc;
+        if ((*rc_out = check_launch("zero_other_triangle_kernel")) != BOBE_OK) return nullptr;
     }
-    Tiled t{ex, fb, npad, batch, (int64_t)npad * npad, factor_q_elems(npad)};
+    TiledFactor* f = new TiledFactor(ex, fb, npad, batch);
+    Tiled& t = f->t;
     t.T = (npad + TW - 1) / TW;
-    t.two = ex.bulk != nullptr && ex.pool != nullptr && t.T > 2;
+    t.two = ex.bulk != nullptr && ex.mid != nullptr && ex.inv != nullptr && ex.pool != nullptr && t.T > 2 && fb.Lt != nullptr;
     t.last_writer.assign(t.T, -1);
     if (t.two) {  // make sure every event exists before the first record (creation failure -> single-stream fallback)
-        if (!ex.pool->event(ex.lane, 2 * t.T + 2)) t.two = false;
+        if (!ex.pool->event(ex.lane, 5 * t.T + 2)) t.two = false;
     }
-    t.phase1();
-    if (t.rc == BOBE_OK) t.phase2();
-    return t.rc;
+    f->pw = ex.pw < 1 ? 1 : (ex.pw > t.T ? t.T : ex.pw);
+    return f;
+}
+int tiled_steps(const TiledFactor* f) { return f->t.T; }
+void tiled_step(TiledFactor* f, int j) {
+    if (f->t.rc == BOBE_OK && j < f->t.T) f->t.step(j, f->pw);
+}
+int32_t tiled_finish(TiledFactor* f) {
+    if (f->t.rc == BOBE_OK) f->t.finish_phase1();
+    if (f->t.rc == BOBE_OK) f->t.phase2();
+    const int32_t rc = f->t.rc;
+    delete f;
+    return rc;
+}
+
+int32_t factor_tiled(const FactorExec& ex, const FactorBuffers& fb, int npad, int batch) {
+    int32_t rc;
+    TiledFactor* f = tiled_begin(ex, fb, npad, batch, &rc);
+    if (!f) return rc;
+    for (int j = 0; j < tiled_steps(f); ++j) tiled_step(f, j);
+    return tiled_finish(f);
 }
 
 }  // namespace bobe

@@ -136,12 +136,19 @@ int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& a, int batch) {
             return go_tma(std::integral_constant<int, TRI_NONE>{});
         }
     }
+    // small batches of matrices with triangular structure: batch index fastest, heavy tile rows first (GEMM_ORDER_BATCH_FIRST)
+    static const int64_t bf_max = env_int("BOBE_BATCH_FIRST_MAX", 8);
+    GemmArgs ao = a;
+    const int64_t zdim = (int64_t)batch * (a.node_count > 0 ? a.node_count : 1);
+    if (zdim > 1 && zdim <= bf_max && zdim <= 65535 && (a.flags & (GEMM_A_LOWER | GEMM_A_UPPER)) && a.M >= 256)
+        ao.flags |= GEMM_ORDER_BATCH_FIRST;
     auto go = [&](auto cfg, auto mode_c) -> int32_t {
         using Cfg = decltype(cfg);
         constexpr int MODE = decltype(mode_c)::value;
         if (int32_t rc = ensure_smem<gemm_nt_kernel<Cfg, MODE>>(Cfg::SMEM_BYTES)) return rc;
-        dim3 grid((a.N + Cfg::BN - 1) / Cfg::BN, (a.M + Cfg::BM - 1) / Cfg::BM, batch * (a.node_count > 0 ? a.node_count : 1));
-        if (launch_pdl(gemm_nt_kernel<Cfg, MODE>, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, a) != cudaSuccess) {
+        const unsigned tn = (a.N + Cfg::BN - 1) / Cfg::BN, tm = (a.M + Cfg::BM - 1) / Cfg::BM;
+        dim3 grid = (ao.flags & GEMM_ORDER_BATCH_FIRST) ? dim3((unsigned)zdim, tn, tm) : dim3(tn, tm, (unsigned)zdim);
+        if (launch_pdl(gemm_nt_kernel<Cfg, MODE>, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, ao) != cudaSuccess) {
             set_error("gemm_nt: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             return BOBE_E_CUDA;
         }
@@ -151,7 +158,14 @@ int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& a, int batch) {
     using M1 = std::integral_constant<int, TRI_LOWER>;
     using M2 = std::integral_constant<int, TRI_UPPER>;
     int32_t rc;
-    if (tile == 1)
+    // under-filled launch: fewer 64x64 tiles than SMs (BOBE_TINY_MAX_TILES, default two per SM) -> 32x64 tiles
+    static const int64_t tiny_max = env_int("BOBE_TINY_MAX_TILES", 2 * sm_count());
+    const int64_t nodes = a.node_count > 0 ? a.node_count : 1;
+    int64_t tiles64 = (int64_t)((a.M + 63) / 64) * ((a.N + 63) / 64) * batch * nodes;
+    if (a.flags & GEMM_C_LOWER) tiles64 = tiles64 / 2 + ((a.M < a.N ? a.M : a.N) + 63) / 64 * batch;
+    if (tile == 1 && !forced && tiles64 <= tiny_max && a.M > 32)
+        rc = mode == TRI_LOWER ? go(CfgTiny{}, M1{}) : (mode == TRI_UPPER ? go(CfgTiny{}, M2{}) : go(CfgTiny{}, M0{}));
+    else if (tile == 1)
         rc = mode == TRI_LOWER ? go(CfgSmall{}, M1{}) : (mode == TRI_UPPER ? go(CfgSmall{}, M2{}) : go(CfgSmall{}, M0{}));
     else if (tile == 2)
         rc = mode == TRI_LOWER ? go(CfgMed{}, M1{}) : (mode == TRI_UPPER ? go(CfgMed{}, M2{}) : go(CfgMed{}, M0{}));

@@ -44,6 +44,11 @@ enum : int {
     GEMM_B_LOWER = 4,   // Bt[j][k] == 0 for k > j
     GEMM_B_UPPER = 8,   // Bt[j][k] == 0 for k < j
     GEMM_C_LOWER = 16,  // only tiles touching the lower triangle (j0 <= i0 + BM - 1) are computed
+    // launch-order hint (set by the launcher for small batches): grid = (batch, tiles_n, tiles_m) instead of
+    // (tiles_n, tiles_m, batch), i.e. the batch index varies fastest and the tile rows come heaviest first (reversed for a
+    // lower-triangular A, whose last rows have the longest k range) -- all matrices start with their long tiles and the
+    // last wave consists of short ones.  With the default order the heavy tiles of the LAST matrix start at 7/8 of the run.
+    GEMM_ORDER_BATCH_FIRST = 32,
 };
 
 enum : int { TRI_NONE = 0, TRI_LOWER = 1, TRI_UPPER = 2 };  // what Mainloop::run knows about A inside a tile
@@ -349,9 +354,15 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_kernel(GemmAr
     extern __shared__ __align__(16) double smem[];
     pdl_wait();     // launched with the PDL attribute: everything below reads what the previous launch wrote
     pdl_trigger();  // the next launch of the chain may become resident as soon as all CTAs of this one have started
-    const int i0 = blockIdx.y * Cfg::BM, j0 = blockIdx.x * Cfg::BN;
-    if ((p.flags & GEMM_C_LOWER) && j0 > i0 + Cfg::BM - 1) return;
+    int by = blockIdx.y, bx = blockIdx.x;
     int64_t z = blockIdx.z;
+    if (p.flags & GEMM_ORDER_BATCH_FIRST) {
+        z = blockIdx.x;
+        bx = blockIdx.y;
+        by = (p.flags & GEMM_A_LOWER) ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
+    }
+    const int i0 = by * Cfg::BM, j0 = bx * Cfg::BN;
+    if ((p.flags & GEMM_C_LOWER) && j0 > i0 + Cfg::BM - 1) return;
     const double* A = p.A;
     const double* Bt = p.Bt;
     double* C = p.C;
@@ -394,14 +405,29 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_kernel(GemmAr
 #pragma unroll
         for (int nf = 0; nf < Cfg::NF; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
 
-    Mainloop<Cfg>::template run<MODE>(acc, A, p.lda, min(Cfg::BM, M - i0), Bt, ldb, min(Cfg::BN, N - j0), kb, ke, smem, i0);
-
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp / Cfg::WN, wn = warp % Cfg::WN;
     C = C ? C + z * p.strideC : nullptr;
     Ct = Ct ? Ct + z * p.strideCt : nullptr;
     const double* D = p.D ? p.D + z * p.strideD : nullptr;
+    if (D && t == 0) {
+        // The addend tile is read once, in the epilogue, straight from HBM when many matrices are in flight: ask L2 for
+        // its 64-byte row segments now, so that the k loop hides the DRAM latency instead of the epilogue exposing it
+#pragma unroll
+        for (int mf = 0; mf < Cfg::MF; ++mf) {
+            const int row = i0 + Cfg::frag_row(wm, mf) + g;
+            if (row >= M) continue;
+#pragma unroll
+            for (int nf = 0; nf < Cfg::NF; ++nf) {
+                const int col = j0 + wn * Cfg::WTN + nf * 8;
+                if (col < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(D + (int64_t)row * p.ldd + col));
+            }
+        }
+    }
+
+    Mainloop<Cfg>::template run<MODE>(acc, A, p.lda, min(Cfg::BM, M - i0), Bt, ldb, min(Cfg::BN, N - j0), kb, ke, smem, i0);
+
 #pragma unroll
     for (int mf = 0; mf < Cfg::MF; ++mf) {
         int row = i0 + Cfg::frag_row(wm, mf) + g;
@@ -525,6 +551,9 @@ using CfgBig = TileCfg<128, 128, 4, 4, 3, 32, true>;   // 512 threads, warp tile
 using CfgTrmm = CfgBig;
 using CfgSmall = TileCfg<64, 64, 2, 2, 3, 16, true, 4>;  // 128 threads, warp tile 32x32, 48 KB smem: four CTAs per SM
 using CfgMed = TileCfg<128, 64, 4, 2, 4, 16, true, 2>; // 256 threads, warp tile 32x32, 96 KB smem: two CTAs per SM
+// Launches whose 64x64 tiles cannot give every SM a tile (the k = 128 products on the critical path of the tile-column
+// factorisation: one 64x64x128 tile is 4.2 us of ONE SM's tensor pipe): half-height tiles, twice the CTAs
+using CfgTiny = TileCfg<32, 64, 1, 4, 3, 16, true, 4>;  // 128 threads, warp tile 32x16, 36 KB smem
 
 int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& args, int batch);
 

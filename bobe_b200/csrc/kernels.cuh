@@ -59,14 +59,17 @@ struct FactorBuffers {
     double* Q;     // (batch, npad/2+NB, npad/2+NB) scratch
     double* diag;  // (batch, npad) diagonal of L
     double* dstat; // (batch, 2) running min / max pivot
-    int* gate;     // (batch) 1 once max/min pivot exceeds the refinement ratio
+    int* gate;     // (factor_gate_rows(npad), batch) ints: row 0 = latest state (1 once max/min pivot exceeds the refinement
+                   // ratio), row j + 1 = snapshot after tile column j (factor_tiled.cuh)
     int force_refine;
     int zero_band;  // 0: zero the whole other triangle (L / Linv handed to the caller); 2: internal use only
 };
 int64_t factor_q_elems(int64_t npad);
+inline int64_t factor_gate_rows(int64_t npad) { return (npad + 127) / 128 + 2; }
 
 // internal side streams + dependency events (one pool per device, created on first use)
-constexpr int POOL_STREAMS = 16;
+constexpr int POOL_LANE_STREAMS = 4;  // per lane: chain, rest of the current column, trailing products, inverse tree
+constexpr int POOL_STREAMS = 8 * POOL_LANE_STREAMS;
 struct StreamPool {
     cudaStream_t streams[POOL_STREAMS];
     cudaEvent_t fork, join[POOL_STREAMS];
@@ -76,18 +79,30 @@ struct StreamPool {
 };
 StreamPool* stream_pool();
 
-// where one factorisation chain runs: `crit` carries the dependent chain; `bulk` (optional, with pool / lane for its
-// events) the look-ahead products.  pw = tile columns per outer panel (factor_tiled.cuh).
+// where one factorisation chain runs: `crit` carries the dependent chain; `bulk` / `inv` (optional, with pool / lane for
+// their events) the look-ahead products and the inverse tree.  pw = tile columns per outer panel (factor_tiled.cuh).
 struct FactorExec {
     cudaStream_t crit;
+    cudaStream_t mid;
     cudaStream_t bulk;
+    cudaStream_t inv;
     StreamPool* pool;
     int lane;
     int pw;
 };
 int32_t factor_tiled(const FactorExec& ex, const FactorBuffers& fb, int npad, int batch);
+// the same, one tile column at a time (sub-batches advanced in lock step); tiled_finish frees the handle
+struct TiledFactor;
+TiledFactor* tiled_begin(const FactorExec& ex, const FactorBuffers& fb, int npad, int batch, int32_t* rc_out);
+int tiled_steps(const TiledFactor* f);
+void tiled_step(TiledFactor* f, int j);
+int32_t tiled_finish(TiledFactor* f);
+// streams / knobs of lane `lane` (BOBE_FACTOR_PW, BOBE_LOOKAHEAD_MAX); bulk / inv are null when look-ahead is off
+FactorExec factor_exec(cudaStream_t stream, StreamPool* pool, int lane, int batch);
 // scheme dispatch (BOBE_FACTOR knob); pool may be null (no look-ahead), lane selects the pool streams / events used
 int32_t factor_any(cudaStream_t stream, StreamPool* pool, int lane, const FactorBuffers& fb, int npad, int batch);
+// factor_any on the pool's lane-0 chain stream (higher priority than the look-ahead streams), forked from / joined to `stream`
+int32_t factor_on_pool(cudaStream_t stream, StreamPool* pool, const FactorBuffers& fb, int npad, int batch);
 int32_t factor_recursive(cudaStream_t stream, const FactorBuffers& fb, int npad, int batch);
 int32_t launch_kinv(cudaStream_t stream, const FactorBuffers& fb, int npad, int batch);  // KB <- U U^T (lower 128-tiles)
 struct SolveArgs {  // what the alpha refinement needs to rebuild K alpha
@@ -98,8 +113,13 @@ struct SolveArgs {  // what the alpha refinement needs to rebuild K alpha
     int64_t d;
     double noise;
     const double* xs;  // (batch, d, npad) scaled, transposed X from launch_prescale (same ls)
+    // caller-supplied K instead of (X, ls, kv): (batch, n, ldk) row-major, lower triangle used, noise already inside
+    // (bobe_cholesky_batched); null otherwise
+    const double* Kin = nullptr;
+    int64_t ldk = 0, kstride = 0;
 };
 int64_t solve_ws_doubles(int64_t npad, int64_t batch);
+int32_t launch_pad_k(cudaStream_t stream, const double* K, int64_t ldk, int64_t kstride, int n, int npad, int batch, double* KB);
 int32_t launch_solve_vectors(cudaStream_t stream, const FactorBuffers& fb, const SolveArgs& sa, const double* y,
                              int64_t n, int npad, int batch, double* z_ws, double* alpha, double* logdet,
                              double* quad, int32_t* info);

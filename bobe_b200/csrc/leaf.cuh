@@ -25,6 +25,17 @@ __device__ __forceinline__ double rcp_newton(double x) {
     return fma(r, e, r);
 }
 
+// Same seed, ONE third-order step: r = r0 (1 + e + e^2), e = 1 - x r0 (|e| ~ 2^-20, so the truncation error e^3 is far
+// below the rounding): three dependent FP64 operations after the MUFU instead of four.  Used on the pivot chain of the
+// recursive leaf, where each FP64 latency is paid 128 times per tile.
+__device__ __forceinline__ double rcp_cubic(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(-x, r, 1.0);
+    const double p = fma(e, e, e);
+    return fma(r, p, r);
+}
+
 // ---- 64x64 Cholesky + inverse, register-blocked ----------------------------------------------------------
 // Thread (ty, tx) of a 16x16 grid owns A[ty+16a][tx+16b] and W[ty+16a][tx+16b] (a, b < 4) in REGISTERS for the
 // whole sweep.  Step j: the owners publish column j of A and row j of W to a double-buffered smem line (one
@@ -287,12 +298,35 @@ __device__ __forceinline__ void mma64(const double* A, const double* B, double a
         }
 }
 
+// development aid (tools/leaf_bench.cu): per-phase clock stamps of CTA 0, compiled in only with -DBOBE_LEAF_TIMING
+#ifdef BOBE_LEAF_TIMING
+#define LEAF_STAMP(io, i)                                                       \
+    do {                                                                        \
+        if ((io).stamps && threadIdx.x == 0 && blockIdx.z == 0) (io).stamps[i] = clock64(); \
+    } while (0)
+#else
+#define LEAF_STAMP(io, i) \
+    do {                  \
+    } while (0)
+#endif
+
 struct LeafIO {
     const double* KB;
     double *L, *Lt, *Linv, *U, *diag, *dstat;
     int* gate;
     int npad, o;  // o = first row/column of the block
     int panel4;   // 1: chol_inv_64_panel4 (four columns per barrier), 0: chol_inv_64
+    // gate: state BEFORE this leaf; gate_out: snapshot after it (what the products of THIS tile column read -- they may
+    // run while later leaves already update the state); gate_final: latest state.  All three may be the same array.
+    int* gate_out;
+    int* gate_final;
+    // tile leaves only.  bit 0: also write the zero 64-blocks on the other side of the diagonal (needed when a product may
+    // read a whole 128 x 128 diagonal tile, i.e. with the 128-row tile configurations); bit 1: also write U = X^T
+    // (otherwise tile_transpose_kernel does it off the critical path)
+    int flags;
+#ifdef BOBE_LEAF_TIMING
+    long long* stamps;
+#endif
 };
 __device__ __forceinline__ void chol_inv_64_any(int panel4, double* A, double* W, double* colb, double* rowb, double* invd,
                                                 double* dd) {
@@ -334,7 +368,8 @@ __device__ __forceinline__ void leaf_store(const double* S, double* T, double* G
 
 // running extreme pivots of this matrix (leaves of one matrix run in stream order: no atomics needed).
 // max/min pivot is a lower bound on cond(L); beyond REFINE_RATIO the panel solves get a correction step.
-__device__ __forceinline__ bool leaf_update_stats(const LeafIO& io, const double* dd, int count, int64_t z) {
+__device__ __forceinline__ bool leaf_update_stats(const LeafIO& io, const double* dd, int count, int64_t z,
+                                                  bool second = false) {
     __shared__ int s_gate;
     if (threadIdx.x < 32) {  // warp 0: min / max of the pivots by shuffles (fmin / fmax skip NaN pivots, as a serial scan would)
         double lo = 1e300, hi = 0.0;
@@ -352,9 +387,10 @@ __device__ __forceinline__ bool leaf_update_stats(const LeafIO& io, const double
             hi = fmax(hi, io.dstat[z * 2 + 1]);
             io.dstat[z * 2] = lo;
             io.dstat[z * 2 + 1] = hi;
-            int gte = io.gate[z];
+            int gte = second ? io.gate_out[z] : io.gate[z];
             if (hi > REFINE_RATIO * lo) gte = 1;
-            io.gate[z] = gte;
+            io.gate_out[z] = gte;
+            io.gate_final[z] = gte;
             s_gate = gte;
         }
     }
@@ -426,7 +462,7 @@ __global__ void __launch_bounds__(LEAF_THREADS) leaf128_kernel(LeafIO io) {
     __syncthreads();
     leaf_store(B5, B2, io.L + zoff, io.Lt + zoff, npad, o + 64, o);  // L21 (B2 = A21 / residual is dead: staging)
     chol_inv_64_any(io.panel4, B3, B4, colb, rowb, invd + 64, dd + 64);
-    leaf_update_stats(io, dd + 64, 64, z);
+    leaf_update_stats(io, dd + 64, 64, z, true);
     mma64<false>(B4, B5, 1.0, B2, nullptr);  // T = X22 L21
     __syncthreads();
     mma64<false>(B2, B1, -1.0, B5, nullptr);  // X21 = -T X11
@@ -573,7 +609,7 @@ __device__ __forceinline__ void chol_inv_blk(double* A, double* W, double* colb,
             const int j = j0 + jj;
             const double ajj = D[jj][jj];
             if (tid == 0) dd[j] = ajj;
-            const double w = rcp_newton(ajj);
+            const double w = rcp_cubic(ajj);
             double ai[E], ak[E], wj[E], dm[4];
 #pragma unroll
             for (int e = 0; e < E; ++e) {
@@ -593,9 +629,11 @@ __device__ __forceinline__ void chol_inv_blk(double* A, double* W, double* colb,
                     const double ci = (tx + 16 * e > j) ? Ck[e][jj] * w : 0.0;
                     Ck[e][kk] = fma(-ci, dk, Ck[e][kk]);
                 }
+                // pivot block: the product of the two column entries does not depend on w, so only ONE operation (the fma
+                // with w) sits between the reciprocal and the next pivot
 #pragma unroll
                 for (int p = 0; p < 4; ++p)
-                    if (p > jj) D[p][kk] = fma(-dm[p], dk, D[p][kk]);
+                    if (p > jj) D[p][kk] = fma(-(D[p][jj] * dk), w, D[p][kk]);
             }
 #pragma unroll
             for (int pp = 0; pp < 4; ++pp) {
@@ -726,7 +764,7 @@ __global__ void __launch_bounds__(LEAF_THREADS) tile_leaf64_kernel(LeafIO io) {
     chol_inv_64_sel<REC>(io.panel4, A, W, colb, rowb, invd, dd);
     tile_store_direct(A, io.L + zoff, io.npad, io.o, io.o);
     tile_store_direct(W, io.Linv + zoff, io.npad, io.o, io.o);
-    tile_store_transposed(W, T, io.U + zoff, io.npad, io.o, io.o);
+    if (io.flags & 2) tile_store_transposed(W, T, io.U + zoff, io.npad, io.o, io.o);
     if (threadIdx.x < 64) io.diag[z * io.npad + io.o + threadIdx.x] = dd[threadIdx.x];
     leaf_update_stats(io, dd, 64, z);
 }
@@ -750,17 +788,21 @@ __global__ void __launch_bounds__(LEAF_THREADS) tile_leaf128_kernel(LeafIO io) {
     const int o = io.o, npad = io.npad;
     const double* Kz = io.KB + zoff;
     double *Lz = io.L + zoff, *Xz = io.Linv + zoff, *Uz = io.U + zoff;
+    LEAF_STAMP(io, 0);
     leaf_load_async(B0, Kz, npad, o, o);
     leaf_load_async(B2, Kz, npad, o + 64, o);
     leaf_load_async(B3, Kz, npad, o + 64, o + 64);
     cp_async_commit();
-    // the blocks on the other side of the diagonal, while the loads are in flight
-    tile_store_zero(Lz, npad, o, o + 64);
-    tile_store_zero(Xz, npad, o, o + 64);
-    tile_store_zero(Uz, npad, o + 64, o);
+    if (io.flags & 1) {  // the blocks on the other side of the diagonal, while the loads are in flight
+        tile_store_zero(Lz, npad, o, o + 64);
+        tile_store_zero(Xz, npad, o, o + 64);
+        tile_store_zero(Uz, npad, o + 64, o);
+    }
     cp_async_wait<0>();
     __syncthreads();
+    LEAF_STAMP(io, 1);
     chol_inv_64_sel<REC>(io.panel4, B0, B1, colb, rowb, invd, dd);
+    LEAF_STAMP(io, 2);
     const bool refine = leaf_update_stats(io, dd, 64, z);
     if (REC) {
         mma_blk<64, true, MM_BT_BLOWER>(B2, B1, 1.0, B5, nullptr);  // L21 = A21 X11^T
@@ -784,10 +826,13 @@ __global__ void __launch_bounds__(LEAF_THREADS) tile_leaf128_kernel(LeafIO io) {
         mma64<true>(B5, B5, -1.0, B3, B3);
     }
     __syncthreads();
+    LEAF_STAMP(io, 3);
     tile_store_direct(B5, Lz, npad, o + 64, o);  // L21
     tile_store_direct(B0, Lz, npad, o, o);       // L11
+    LEAF_STAMP(io, 4);
     chol_inv_64_sel<REC>(io.panel4, B3, B4, colb, rowb, invd + 64, dd + 64);
-    leaf_update_stats(io, dd + 64, 64, z);
+    LEAF_STAMP(io, 5);
+    leaf_update_stats(io, dd + 64, 64, z, true);
     if (REC) {
         mma_blk<64, false, MM_NN_ALOWER>(B4, B5, 1.0, B2, nullptr);   // T = X22 L21
         __syncthreads();
@@ -798,15 +843,35 @@ __global__ void __launch_bounds__(LEAF_THREADS) tile_leaf128_kernel(LeafIO io) {
         mma64<false>(B2, B1, -1.0, B5, nullptr);
     }
     __syncthreads();
+    LEAF_STAMP(io, 6);
     tile_store_direct(B3, Lz, npad, o + 64, o + 64);
     tile_store_direct(B1, Xz, npad, o, o);
     tile_store_direct(B4, Xz, npad, o + 64, o + 64);
     tile_store_direct(B5, Xz, npad, o + 64, o);
-    // B2 (T) is dead: transpose staging
-    tile_store_transposed(B1, B2, Uz, npad, o, o);
-    tile_store_transposed(B4, B2, Uz, npad, o + 64, o + 64);
-    tile_store_transposed(B5, B2, Uz, npad, o + 64, o);
+    LEAF_STAMP(io, 7);
+    if (io.flags & 2) {  // B2 (T) is dead: transpose staging
+        tile_store_transposed(B1, B2, Uz, npad, o, o);
+        tile_store_transposed(B4, B2, Uz, npad, o + 64, o + 64);
+        tile_store_transposed(B5, B2, Uz, npad, o + 64, o);
+    }
     if (threadIdx.x < 128) io.diag[z * npad + o + threadIdx.x] = dd[threadIdx.x];
+    LEAF_STAMP(io, 8);
+}
+
+// U tile = (X tile)^T for the 64-blocks on and below the diagonal of tile column `o` (w = 64 or 128 wide): what the
+// leaves leave out when LeafIO::flags bit 1 is clear.  grid = (w / 32, w / 32, batch), 256 threads (32 x 8).
+__global__ void __launch_bounds__(256) tile_transpose_kernel(const double* __restrict__ X, double* __restrict__ U, int npad,
+                                                             int o) {
+    __shared__ double t[32][33];
+    pdl_wait();
+    pdl_trigger();
+    const int br = blockIdx.y, bc = blockIdx.x;  // 32-blocks: rows br, columns bc of the tile
+    if ((bc >> 1) > (br >> 1)) return;           // 64-block above the diagonal: not part of X
+    const int64_t zoff = (int64_t)blockIdx.z * npad * npad;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) t[r][tx] = X[zoff + (int64_t)(o + br * 32 + r) * npad + o + bc * 32 + tx];
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) U[zoff + (int64_t)(o + bc * 32 + r) * npad + o + br * 32 + tx] = t[tx][r];
 }
 
 }  // namespace bobe

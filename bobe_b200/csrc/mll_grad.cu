@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <mutex>
+#include <vector>
 
 #include "gemm_nt.cuh"
 #include "kernels.cuh"
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(256) mll_finish_kernel(const double* __restric
     if (threadIdx.x == 0) val[z] = -0.5 * quad[z] - logdet[z] - 0.5 * (double)n * 1.8378770664093454835606594728112;
 }
 
-constexpr int MLL_MAX_STREAMS = POOL_STREAMS / 2;  // each sub-batch may use two pool streams (chain + look-ahead)
+constexpr int MLL_MAX_STREAMS = POOL_STREAMS / POOL_LANE_STREAMS;  // one lane of pool streams per sub-batch
 
 struct MllLayout {
     int64_t npad, tiles, ntile_pairs;
@@ -221,7 +222,7 @@ static MllLayout mll_layout(int64_t n, int64_t d, int64_t R) {
     l.off_U = take(R * m2);
     l.off_Q = take(R * factor_q_elems(l.npad));
     l.off_diag = take(R * l.npad);
-    l.off_stat = take(3 * R);
+    l.off_stat = take(2 * R + (factor_gate_rows(l.npad) * R + 1) / 2);  // min / max pivot + the gate rows (ints)
     l.off_z = take((3 * R + MLL_MAX_STREAMS) * l.npad);
     l.off_alpha = take(R * l.npad);
     l.off_logdet = take(R);
@@ -270,72 +271,120 @@ extern "C" int32_t bobe_mll_grad_batched(void* stream_, int32_t kind, const doub
     exp_params_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(log_params, R, P, d, has_kv, fixed_kv, ls, kv);
     if (int32_t rc = check_launch("exp_params_kernel")) return rc;
 
-    // The recursion is a chain of ~230 dependent launches whose lower levels cannot fill 148 SMs.  The restarts are
-    // therefore cut into sub-batches that run the whole chain on separate internal streams (forked from and
-    // joined to the caller's stream with events): one sub-batch's latency-bound leaves and small products overlap
-    // with another's large tensor-core products.
+    // The factorisation is a chain of dependent launches whose small products cannot fill 148 SMs.  The restarts are
+    // therefore cut into sub-batches that run the whole chain on separate internal streams (forked from and joined to
+    // the caller's stream with events): one sub-batch's latency-bound leaves and small products overlap with another's
+    // large tensor-core products.  The host enqueues the sub-batches STAGE BY STAGE (and the factorisation tile column
+    // by tile column): enqueued one chain after the other, the second would start half a millisecond behind the first.
     static const int64_t max_streams = std::min<int64_t>(MLL_MAX_STREAMS, env_int("BOBE_MLL_STREAMS", 4));
     static const int64_t min_per_stream = std::max<int64_t>(1, env_int("BOBE_MLL_MIN_PER_STREAM", 4));
+    static const int64_t scheme = env_int("BOBE_FACTOR", 1);
     const int S = (int)std::min<int64_t>(max_streams, std::max<int64_t>(1, R / min_per_stream));
     // XLA may call handlers from several host threads: the record / wait pairs below must not interleave with those
     // of another caller of the same device (stream order then keeps the shared side streams correct)
     StreamPool* pool = stream_pool();
     if (!pool) return BOBE_E_CUDA;
     std::unique_lock<std::mutex> pool_lock(pool->enqueue_mu);
-    if (S > 1) {
+    // (also for a single sub-batch: the pool's chain streams have a higher priority than its look-ahead streams)
+    static const bool own_stream = env_int("BOBE_MLL_OWN_STREAM", 1) != 0;
+    const bool forked = S > 1 || own_stream;
+    if (forked) {
         if (cudaEventRecord(pool->fork, stream) != cudaSuccess) {
             set_error("mll_grad: event record failed");
             return BOBE_E_CUDA;
         }
     }
-    int32_t rc_all = BOBE_OK;
-    for (int si = 0; si < S && rc_all == BOBE_OK; ++si) {
-        const int64_t r0 = si * R / S, r1 = (si + 1) * R / S, Rs = r1 - r0;
-        cudaStream_t st = (S > 1) ? pool->streams[2 * si] : stream;
-        if (S > 1) cudaStreamWaitEvent(st, pool->fork, 0);
-        rc_all = [&]() -> int32_t {
-            FactorBuffers fb{w + l.off_KB + r0 * m2, w + l.off_L + r0 * m2, w + l.off_Lt + r0 * m2,
+    struct Sub {
+        int64_t r0, Rs;
+        cudaStream_t st;
+        FactorBuffers fb;
+        double *zws, *alpha, *logdet, *quad, *partial, *xs;
+        const double *ls_s, *kv_s;
+        TiledFactor* tf = nullptr;
+        int32_t rc = BOBE_OK;
+    };
+    std::vector<Sub> subs(S);
+    for (int si = 0; si < S; ++si) {
+        Sub& u = subs[si];
+        u.r0 = si * R / S;
+        u.Rs = (si + 1) * R / S - u.r0;
+        const int64_t r0 = u.r0;
+        u.st = forked ? pool->streams[POOL_LANE_STREAMS * si] : stream;
+        if (forked) cudaStreamWaitEvent(u.st, pool->fork, 0);
+        u.fb = FactorBuffers{w + l.off_KB + r0 * m2, w + l.off_L + r0 * m2, w + l.off_Lt + r0 * m2,
                              w + l.off_Linv + r0 * m2, w + l.off_U + r0 * m2, w + l.off_Q + r0 * qel,
-                             w + l.off_diag + r0 * npad, w + l.off_stat + 2 * r0, (int*)(w + l.off_stat + 2 * R) + r0, 0, 2};
-            double* zws = w + l.off_z + (3 * r0 + si) * npad;  // each sub-batch: own padded y + 3 vectors per restart
-            double *alpha = w + l.off_alpha + r0 * npad, *logdet = w + l.off_logdet + r0, *quad = w + l.off_quad + r0;
-            double* partial = w + l.off_partial + r0 * l.ntile_pairs * (d + 1);
-            const double *ls_s = ls + r0 * d, *kv_s = kv + r0;
-
-            double* xs = w + l.off_xs + r0 * d * npad;
-            if (int32_t rc = launch_prescale(st, X, n, d, ls_s, d, xs, npad, d * (int64_t)npad, (int)Rs)) return rc;
-            KmatArgs ka{};
-            ka.xa = X; ka.xb = X; ka.ls = ls_s; ka.kv_ptr = kv_s; ka.out = fb.KB;
-            ka.xbs = xs; ka.xbs_ld = npad; ka.xbs_stride = d * (int64_t)npad;
-            ka.n1 = n; ka.n2 = n; ka.d = d; ka.ldo = npad; ka.rows_pad = npad; ka.cols_pad = npad;
-            ka.store_rows = npad; ka.store_cols = npad; ka.vec_ok = 1;
-            ka.ls_stride = d; ka.out_stride = m2; ka.noise = noise; ka.add_noise = 1; ka.pad_identity = 1;
-            ka.lower_only = 1;  // the factorisation reads the lower triangle only
-            if (int32_t rc = launch_kmat(st, kind, ka, (int)Rs)) return rc;
-            if (int32_t rc = factor_any(st, pool, si, fb, npad, (int)Rs)) return rc;
-            SolveArgs sa{kind, X, ls_s, kv_s, d, noise, xs};
-            if (int32_t rc = launch_solve_vectors(st, fb, sa, y, n, npad, (int)Rs, zws, alpha, logdet, quad, info + r0))
-                return rc;
-            if (int32_t rc = launch_kinv(st, fb, npad, (int)Rs)) return rc;
-
-            int smem = (int)((2 * d * GLD + 2 * GT + 8 * (d + 1)) * sizeof(double));
-            dim3 grid((unsigned)l.ntile_pairs, (unsigned)Rs);
-            if (kind == BOBE_KERNEL_RBF) {
-                if (int32_t rc = ensure_smem<mll_grad_tile_kernel<BOBE_KERNEL_RBF>>(smem)) return rc;
-                mll_grad_tile_kernel<BOBE_KERNEL_RBF><<<grid, 256, smem, st>>>(
-                    xs, n, (int)d, kv_s, fb.KB, npad, alpha, has_kv, (int)P, partial, (int)l.ntile_pairs);
-            } else {
-                if (int32_t rc = ensure_smem<mll_grad_tile_kernel<BOBE_KERNEL_MATERN52>>(smem)) return rc;
-                mll_grad_tile_kernel<BOBE_KERNEL_MATERN52><<<grid, 256, smem, st>>>(
-                    xs, n, (int)d, kv_s, fb.KB, npad, alpha, has_kv, (int)P, partial, (int)l.ntile_pairs);
+                             w + l.off_diag + r0 * npad, w + l.off_stat + 2 * r0, (int*)(w + l.off_stat + 2 * R) + r0 * factor_gate_rows(npad), 0, 2};
+        u.zws = w + l.off_z + (3 * r0 + si) * npad;  // each sub-batch: own padded y + 3 vectors per restart
+        u.alpha = w + l.off_alpha + r0 * npad;
+        u.logdet = w + l.off_logdet + r0;
+        u.quad = w + l.off_quad + r0;
+        u.partial = w + l.off_partial + r0 * l.ntile_pairs * (d + 1);
+        u.ls_s = ls + r0 * d;
+        u.kv_s = kv + r0;
+        u.xs = w + l.off_xs + r0 * d * npad;
+    }
+    auto each = [&](auto&& stage) {  // one stage for every sub-batch that is still healthy
+        for (int si = 0; si < S; ++si)
+            if (subs[si].rc == BOBE_OK) subs[si].rc = stage(subs[si], si);
+    };
+    each([&](Sub& u, int) -> int32_t {
+        if (int32_t rc = launch_prescale(u.st, X, n, d, u.ls_s, d, u.xs, npad, d * (int64_t)npad, (int)u.Rs)) return rc;
+        KmatArgs ka{};
+        ka.xa = X; ka.xb = X; ka.ls = u.ls_s; ka.kv_ptr = u.kv_s; ka.out = u.fb.KB;
+        ka.xbs = u.xs; ka.xbs_ld = npad; ka.xbs_stride = d * (int64_t)npad;
+        ka.n1 = n; ka.n2 = n; ka.d = d; ka.ldo = npad; ka.rows_pad = npad; ka.cols_pad = npad;
+        ka.store_rows = npad; ka.store_cols = npad; ka.vec_ok = 1;
+        ka.ls_stride = d; ka.out_stride = m2; ka.noise = noise; ka.add_noise = 1; ka.pad_identity = 1;
+        ka.lower_only = 1;  // the factorisation reads the lower triangle only
+        return launch_kmat(u.st, kind, ka, (int)u.Rs);
+    });
+    if (scheme == 0) {
+        each([&](Sub& u, int) -> int32_t { return factor_recursive(u.st, u.fb, npad, (int)u.Rs); });
+    } else {
+        int steps = 0;
+        each([&](Sub& u, int si) -> int32_t {
+            int32_t rc;
+            u.tf = tiled_begin(factor_exec(u.st, pool, si, (int)u.Rs), u.fb, npad, (int)u.Rs, &rc);
+            if (u.tf) steps = std::max(steps, tiled_steps(u.tf));
+            return rc;
+        });
+        for (int j = 0; j < steps; ++j)
+            for (int si = 0; si < S; ++si)
+                if (subs[si].tf) tiled_step(subs[si].tf, j);
+        for (int si = 0; si < S; ++si)
+            if (subs[si].tf) {
+                const int32_t rc = tiled_finish(subs[si].tf);
+                subs[si].tf = nullptr;
+                if (subs[si].rc == BOBE_OK) subs[si].rc = rc;
             }
-            if (int32_t rc = check_launch("mll_grad_tile_kernel")) return rc;
-            mll_finish_kernel<<<(unsigned)Rs, 256, 0, st>>>(partial, (int)l.ntile_pairs, (int)d, (int)P, has_kv, n, logdet,
-                                                           quad, info + r0, val + r0, grad + r0 * P);
-            return check_launch("mll_finish_kernel");
-        }();
-        if (S > 1) {  // join (also on failure, so that the caller's stream never runs ahead of stray work)
-            cudaEventRecord(pool->join[si], st);
+    }
+    each([&](Sub& u, int) -> int32_t {
+        SolveArgs sa{kind, X, u.ls_s, u.kv_s, d, noise, u.xs};
+        return launch_solve_vectors(u.st, u.fb, sa, y, n, npad, (int)u.Rs, u.zws, u.alpha, u.logdet, u.quad, info + u.r0);
+    });
+    each([&](Sub& u, int) -> int32_t { return launch_kinv(u.st, u.fb, npad, (int)u.Rs); });
+    each([&](Sub& u, int) -> int32_t {
+        int smem = (int)((2 * d * GLD + 2 * GT + 8 * (d + 1)) * sizeof(double));
+        dim3 grid((unsigned)l.ntile_pairs, (unsigned)u.Rs);
+        if (kind == BOBE_KERNEL_RBF) {
+            if (int32_t rc = ensure_smem<mll_grad_tile_kernel<BOBE_KERNEL_RBF>>(smem)) return rc;
+            mll_grad_tile_kernel<BOBE_KERNEL_RBF><<<grid, 256, smem, u.st>>>(
+                u.xs, n, (int)d, u.kv_s, u.fb.KB, npad, u.alpha, has_kv, (int)P, u.partial, (int)l.ntile_pairs);
+        } else {
+            if (int32_t rc = ensure_smem<mll_grad_tile_kernel<BOBE_KERNEL_MATERN52>>(smem)) return rc;
+            mll_grad_tile_kernel<BOBE_KERNEL_MATERN52><<<grid, 256, smem, u.st>>>(
+                u.xs, n, (int)d, u.kv_s, u.fb.KB, npad, u.alpha, has_kv, (int)P, u.partial, (int)l.ntile_pairs);
+        }
+        if (int32_t rc = check_launch("mll_grad_tile_kernel")) return rc;
+        mll_finish_kernel<<<(unsigned)u.Rs, 256, 0, u.st>>>(u.partial, (int)l.ntile_pairs, (int)d, (int)P, has_kv, n, u.logdet,
+                                                           u.quad, info + u.r0, val + u.r0, grad + u.r0 * P);
+        return check_launch("mll_finish_kernel");
+    });
+    int32_t rc_all = BOBE_OK;
+    for (int si = 0; si < S; ++si) {
+        if (subs[si].rc != BOBE_OK && rc_all == BOBE_OK) rc_all = subs[si].rc;
+        if (forked) {  // join (also on failure, so that the caller's stream never runs ahead of stray work)
+            cudaEventRecord(pool->join[si], subs[si].st);
             cudaStreamWaitEvent(stream, pool->join[si], 0);
         }
     }

@@ -318,13 +318,15 @@ class GP:
         val, grad, _info = ops.mll_grad_batched(self.kernel_name, self._X_dev, self._y_dev, _to_dev(lp, dev),
                                                 not self.fixed_kernel_variance, float(self.kernel_variance),
                                                 float(self.noise))
-        val, grad = val.cpu().numpy(), grad.cpu().numpy()
-        out_v, out_g = np.empty(lp.shape[0]), np.empty_like(lp)
+        # the device call above is asynchronous: the O(R d) prior terms are evaluated on the host WHILE it runs, and only
+        # then are the results fetched (the .cpu() below is the first synchronisation)
+        pv, pg = np.empty(lp.shape[0]), np.empty_like(lp)
         for r in range(lp.shape[0]):
             ls, kv, tausq = self._parse_hyperparams(lp[r])
-            out_v[r] = -(val[r] + self.prior_func(ls, kv, tausq))
-            out_g[r] = -(grad[r] + self._prior_grad(ls, kv, tausq))
-        return out_v, out_g
+            pv[r] = self.prior_func(ls, kv, tausq)
+            pg[r] = self._prior_grad(ls, kv, tausq)
+        both = torch.cat([val[:, None], grad], dim=1).cpu().numpy()  # one D2H copy
+        return -(both[:, 0] + pv), -(both[:, 1:] + pg)
 
     def neg_mll_and_grad(self, log_params):
         v, g = self.neg_mll_and_grad_batched(np.asarray(log_params, dtype=np.float64)[None, :])

@@ -70,6 +70,18 @@ int32_t bobe_factorize(void* stream, int32_t kind, const double* X, const double
                        const double* ls, const double* kv, double noise, int64_t batch, double* L, double* Linv,
                        double* alpha, double* logdet, double* quad, int32_t* info, void* ws, int64_t ws_bytes);
 
+/* The same for caller-supplied kernel matrices K (batch, n, ldk) (lower triangle read, noise already on the diagonal)
+ * -- gp_mll(k, train_y, num_points), BOBE/gp.py:170-178: jnp.linalg.cholesky(k) + cho_solve((L, True), train_y).
+ * y is (n), shared by the batch.  Outputs as bobe_factorize; gp_mll = -quad/2 - logdet - n/2 log(2 pi). */
+int64_t bobe_cholesky_workspace_bytes(int64_t n, int64_t batch);
+int32_t bobe_cholesky_batched(void* stream, const double* K, int64_t n, int64_t ldk, int64_t batch, const double* y,
+                              double* L, double* Linv, double* alpha, double* logdet, double* quad, int32_t* info,
+                              void* ws, int64_t ws_bytes);
+
+/* out[i][j] = sum_k (xa[i][k] - xb[j][k])^2 by direct differences -- dist_sq, BOBE/gp.py:80-96.  out is (n1, ldo). */
+int32_t bobe_dist_sq(void* stream, const double* xa, int64_t n1, const double* xb, int64_t n2, int64_t d, double* out,
+                     int64_t ldo);
+
 /* Rank-b append: the factorisation of the first n_old points, held in buffers already sized for the padded
  * npad(n_old + b) (identity beyond n_old), is extended IN PLACE by the points n_old .. n_old+b-1 of X, and alpha is
  * re-solved for the targets y of all n_old + b points -- GP.update, BOBE/gp.py:495-541, whose hyper-parameters are

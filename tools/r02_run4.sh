@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+out=gpurun_out/r02_run4.log; : > $out
+run() { echo "=== $*" >> $out; env "$@" >> $out 2>&1; echo "rc=$?" >> $out; }
+run BOBE_X=1 timeout 600 python tools/factor_ab.py check
+run BOBE_X=1 timeout 600 python tools/factor_ab.py time
+run BOBE_MLL_MIN_PER_STREAM=8 timeout 600 python tools/factor_ab.py time
+run BOBE_MLL_MIN_PER_STREAM=16 BOBE_LOOKAHEAD_MAX=64 timeout 600 python tools/factor_ab.py time
+run BOBE_MLL_MIN_PER_STREAM=32 BOBE_LOOKAHEAD_MAX=64 timeout 600 python tools/factor_ab.py time
+run BOBE_MLL_OWN_STREAM=0 timeout 600 python tools/factor_ab.py time
+grep -v "^n=" $out | grep "===\|factorize n=2000\|R=8\|R=1:\|R=16\|R=64\|check ok\|FAILED"

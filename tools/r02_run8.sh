@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+tools/leaf_bench > gpurun_out/r02_leaf_bench6.txt 2>&1
+out=gpurun_out/r02_run8.log; : > $out
+run() { echo "=== $*" >> $out; env "$@" >> $out 2>&1; echo "rc=$?" >> $out; }
+run BOBE_X=1 timeout 600 python tools/factor_ab.py check
+run BOBE_LOOKAHEAD_MAX=0 timeout 600 python tools/factor_ab.py check
+run BOBE_X=1 timeout 600 python tools/factor_ab.py time
+run BOBE_BATCH_FIRST_MAX=0 timeout 600 python tools/factor_ab.py time
+run BOBE_BATCH_FIRST_MAX=16 BOBE_MLL_MIN_PER_STREAM=8 timeout 600 python tools/factor_ab.py time
+BOBE_MLL_MIN_PER_STREAM=8 python tools/timeline.py mll 8 > gpurun_out/r02_tl8_mll8_s1.txt 2>&1
+python tools/timeline.py factor 2000 > gpurun_out/r02_tl8_factor.txt 2>&1
+grep -v "^n=" $out | grep "===\|factorize n=\|R=8\|R=1:\|R=16\|R=64\|check ok\|FAILED\|rror"
+grep "recursive" gpurun_out/r02_leaf_bench6.txt

@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+out=gpurun_out/r02_run9.log; : > $out
+run() { echo "=== $*" >> $out; env "$@" >> $out 2>&1; echo "rc=$?" >> $out; }
+for i in 1 2 3; do run BOBE_X=$i timeout 600 python tools/factor_ab.py check; done
+run BOBE_FACTOR_PW=1 timeout 600 python tools/factor_ab.py check
+run BOBE_FACTOR_PW=3 timeout 600 python tools/factor_ab.py check
+run BOBE_X=1 timeout 600 python tools/factor_ab.py time
+run BOBE_MLL_MIN_PER_STREAM=8 timeout 600 python tools/factor_ab.py time
+BOBE_MLL_MIN_PER_STREAM=8 python tools/timeline.py mll 8 > gpurun_out/r02_tl9_mll8_s1.txt 2>&1
+python tools/timeline.py factor 2000 > gpurun_out/r02_tl9_factor.txt 2>&1
+grep -v "^n=" $out | grep "===\|factorize n=\|R=8\|R=1:\|R=16\|R=64\|check ok\|FAILED\|rror"
