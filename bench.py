@@ -116,8 +116,8 @@ class ClockSampler:
 
 # ---- the reference's CPU arithmetic (oracle port) on the host cores -------------------------------------------------------
 # Thread policy, fixed explicitly so that the arm is the same at every N (torch.distributed.run exports OMP_NUM_THREADS=1,
-# which silently halved this arm in round 1): either `cores` Python threads each with ONE BLAS thread over query chunks of
-# 1024, or one Python thread with an all-core BLAS over chunks of 8192; the faster of the two on a warm-up sample is used.
+# which silently halved this arm in round 1): the fastest of POLICIES (below) on a warm-up sample is used, with the BLAS
+# thread count set through threadpoolctl rather than inherited from the environment.
 def _blas_limits(n):
     from threadpoolctl import threadpool_limits
     return threadpool_limits(limits=int(n))
@@ -134,22 +134,35 @@ def _cpu_gp():
     return _CPU_GP["gp"]
 
 
+POLICIES = {  # name: (Python threads, BLAS threads per call, query chunk); None = all cores
+    "threads": (None, 1, CPU_CHUNK),        # cores x 1: no oversubscription
+    "blas": (1, None, 8 * CPU_CHUNK),       # 1 x cores
+    "both": (None, None, CPU_CHUNK),        # cores x cores (round 1's arm; oversubscribed, but the NumPy kernel build holds
+}                                           # the GIL between BLAS calls, so the extra BLAS threads fill those gaps)
+
+
+def _policy_text(policy):
+    cores = os.cpu_count()
+    pt, bt, chunk = POLICIES[policy]
+    return f"{pt or cores} Python threads x {bt or cores} BLAS threads, query chunks of {chunk}"
+
+
 def cpu_predict_sample(n_queries, policy):
-    """mean+var over a bounded query sample; policy = "threads" (cores x 1 BLAS thread) or "blas" (1 x all-core BLAS)."""
+    """mean+var over a bounded query sample under one of the thread POLICIES."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import gp_oracle as O
     gp = _cpu_gp()
     Xq = O.synthetic_queries(n_queries, DIM)
     cores = os.cpu_count()
-    chunk = CPU_CHUNK if policy == "threads" else 8 * CPU_CHUNK
+    pt, bt, chunk = POLICIES[policy]
 
     def work(s):  # query chunks keep the temporaries cache-sized; NumPy releases the GIL inside its loops
         gp.predict_mean_batched(Xq[s:s + chunk])
         gp.predict_var_batched(Xq[s:s + chunk])
-    with _blas_limits(1 if policy == "threads" else cores):
+    with _blas_limits(bt or cores):
         t0 = time.perf_counter()
-        if policy == "threads":
-            with ThreadPoolExecutor(cores) as ex:
+        if (pt or cores) > 1:
+            with ThreadPoolExecutor(pt or cores) as ex:
                 list(ex.map(work, range(0, n_queries, chunk)))
         else:
             for s in range(0, n_queries, chunk):
@@ -160,7 +173,7 @@ def cpu_predict_sample(n_queries, policy):
 
 def cpu_pick_policy():
     best = None
-    for policy in ("threads", "blas"):
+    for policy in POLICIES:
         cpu_predict_sample(4096, policy)
         v, _ = cpu_predict_sample(16384, policy)
         if best is None or v > best[1]:
@@ -197,8 +210,7 @@ def run_reference(args):
     ms = 1e3 * float(np.mean(times))
     val = sample / (ms / 1e3)
     mll_v, mll_dt = cpu_mll_grad_evals(2)
-    pol = (f"{cores} Python threads x 1 BLAS thread, query chunks of {CPU_CHUNK}" if policy == "threads"
-           else f"1 Python thread x {cores} BLAS threads, query chunks of {8 * CPU_CHUNK}")
+    pol = _policy_text(policy)
     line = {"impl": "reference", "metric": "gp_predict_mean_var_pts_per_sec", "value": val, "unit": "pts/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -206,8 +218,8 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": "pts/s", "cores": cores, "kind": "port",
                              "sample": f"{sample} queries per step (of the 1e6-per-GPU workload), NumPy/SciPy(OpenBLAS) "
                                        f"restatement of BOBE/gp.py predict_mean+predict_var (JAX is not installable here); "
-                                       f"{pol} (the faster of the two policies; BLAS threads set with threadpoolctl, so the "
-                                       f"arm is identical at every N)"},
+                                       f"{pol} (the fastest of {len(POLICIES)} thread policies on a warm-up sample; BLAS threads "
+                                       f"set with threadpoolctl, so the arm is identical at every N)"},
             "e2e": {"value": val, "unit": "pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "secondary": {"metric": "gp_mll_grad_evals_per_sec", "value": mll_v, "unit": "evals/s",
                           "sample": f"2 of the 64 restarts ({mll_dt:.1f} s), oracle neg_mll_and_grad at n={N_TRAIN}, "
@@ -414,8 +426,7 @@ def main():
         sample = 131072
         v, dt = cpu_predict_sample(sample, policy)
         cores = os.cpu_count()
-        pol = (f"{cores} Python threads x 1 BLAS thread, chunks of {CPU_CHUNK}" if policy == "threads"
-               else f"1 Python thread x {cores} BLAS threads, chunks of {8 * CPU_CHUNK}")
+        pol = _policy_text(policy)
         cpu_baseline = {"value": v, "unit": "pts/s", "cores": cores, "kind": "port",
                         "sample": f"{sample} of the 1e6 queries ({dt:.1f} s), NumPy/SciPy(OpenBLAS) restatement of "
                                   f"BOBE/gp.py predict_mean+predict_var, {pol}; JAX is not installable here"}

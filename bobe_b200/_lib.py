@@ -26,6 +26,9 @@ SIGNATURES = {
     "bobe_factorize_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "bobe_factorize": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _vp, _vp, _f64, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
                               _vp, _i64]),
+    "bobe_cholesky_workspace_bytes": (_i64, [_i64, _i64]),
+    "bobe_cholesky_batched": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
+    "bobe_dist_sq": (_i32, [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _i64]),
     "bobe_factor_append_workspace_bytes": (_i64, [_i64, _i64]),
     "bobe_factor_append": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _i64]),
     "bobe_mll_grad_workspace_bytes": (_i64, [_i64, _i64, _i64]),

@@ -175,27 +175,25 @@ int32_t factor_any(cudaStream_t stream, StreamPool* pool, int lane, const Factor
         }
         return factor_recursive(stream, fb, npad, batch);
     }
-    return factor_tiled(factor_exec(stream, pool, lane, batch), fb, npad, batch);
+    return factor_tiled(factor_exec(stream, pool, lane, batch, batch), fb, npad, batch);
 }
 
 int32_t factor_on_pool(cudaStream_t stream, StreamPool* pool, const FactorBuffers& fb, int npad, int batch) {
-    cudaStream_t st = pool->streams[0];
-    if (cudaEventRecord(pool->fork, stream) != cudaSuccess || cudaStreamWaitEvent(st, pool->fork, 0) != cudaSuccess) {
-        set_error("factor: fork failed");
-        return BOBE_E_CUDA;
-    }
-    const int32_t rc = factor_any(st, pool, 0, fb, npad, batch);
-    cudaEventRecord(pool->join[0], st);  // join also on failure
-    cudaStreamWaitEvent(stream, pool->join[0], 0);
-    return rc;
+    return factor_any(stream, pool, 0, fb, npad, batch);  // (the tiled scheme forks / joins its own streams)
 }
 
-FactorExec factor_exec(cudaStream_t stream, StreamPool* pool, int lane, int batch) {
+FactorExec factor_exec(cudaStream_t stream, StreamPool* pool, int lane, int batch, int total_batch) {
     static const int64_t la_max = env_int("BOBE_LOOKAHEAD_MAX", 16);
     static const int64_t pw = env_int("BOBE_FACTOR_PW", 4);  // tile columns per outer panel (the same for every batch size)
+    static const int64_t green_max = env_int("BOBE_GREEN_MAX", 16);  // most matrices in flight for the chain partition
     const bool la = pool && batch <= la_max && lane >= 0 && POOL_LANE_STREAMS * lane + 3 < POOL_STREAMS;
-    cudaStream_t* ps = pool ? pool->streams + POOL_LANE_STREAMS * (lane < 0 ? 0 : lane) : nullptr;
-    return FactorExec{stream, la ? ps[1] : nullptr, la ? ps[2] : nullptr, la ? ps[3] : nullptr, pool, lane < 0 ? 0 : lane, (int)pw};
+    if (!la) return FactorExec{stream, stream, nullptr, nullptr, nullptr, pool, lane < 0 ? 0 : lane, (int)pw};
+    if (pool->green && total_batch <= green_max && total_batch <= pool->green_sms) {
+        cudaStream_t* g = pool->gstreams + POOL_LANE_STREAMS * lane;
+        return FactorExec{stream, g[0], g[1], g[2], g[3], pool, lane, (int)pw};
+    }
+    cudaStream_t* ps = pool->streams + POOL_LANE_STREAMS * lane;
+    return FactorExec{stream, stream, ps[1], ps[2], ps[3], pool, lane, (int)pw};
 }
 
 int32_t launch_kinv(cudaStream_t stream, const FactorBuffers& fb, int npad, int batch) {

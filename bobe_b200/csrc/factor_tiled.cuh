@@ -34,10 +34,53 @@
 #include <mutex>
 #include <vector>
 
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 namespace bobe {
 
 // ---- internal side streams + dependency events, one pool per device ---------------------------------------------------
 // They carry no state between calls: every call forks them from the caller's stream and joins them back before returning.
+// Two green contexts: BOBE_GREEN_SMS SMs for the chains, the rest for everything else (experiment knob, default off).  Entry points are
+// fetched through the runtime (no link dependency on libcuda); any failure leaves pool->green false.
+static void make_green_streams(StreamPool* p, int dev, int prio_lo, int prio_hi) {
+    for (int i = 0; i < POOL_STREAMS; ++i) p->gstreams[i] = nullptr;
+    const int64_t want = env_int("BOBE_GREEN_SMS", 0);  // off by default, see profiles/r02/README.md
+    if (want <= 0) return;
+    auto entry = [](const char* name, unsigned ver) -> void* {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPointByVersion(name, &fn, ver, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return fn;
+    };
+    auto get_res = (PFN_cuDeviceGetDevResource_v12040)entry("cuDeviceGetDevResource", 12040);
+    auto split = (PFN_cuDevSmResourceSplitByCount_v12040)entry("cuDevSmResourceSplitByCount", 12040);
+    auto gen_desc = (PFN_cuDevResourceGenerateDesc_v12040)entry("cuDevResourceGenerateDesc", 12040);
+    auto ctx_create = (PFN_cuGreenCtxCreate_v12040)entry("cuGreenCtxCreate", 12040);
+    auto stream_create = (PFN_cuGreenCtxStreamCreate_v12050)entry("cuGreenCtxStreamCreate", 12050);
+    if (!get_res || !split || !gen_desc || !ctx_create || !stream_create) return;
+    CUdevResource all, chain, rest;
+    unsigned groups = 1;
+    if (get_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS || all.sm.smCount < 2 * (unsigned)want) return;
+    if (split(&chain, &groups, &all, &rest, 0, (unsigned)want) != CUDA_SUCCESS || groups != 1 || rest.sm.smCount == 0) return;
+    CUdevResourceDesc d_chain, d_rest;
+    CUgreenCtx g_chain, g_rest;
+    if (gen_desc(&d_chain, &chain, 1) != CUDA_SUCCESS || gen_desc(&d_rest, &rest, 1) != CUDA_SUCCESS) return;
+    if (ctx_create(&g_chain, d_chain, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS ||
+        ctx_create(&g_rest, d_rest, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS)
+        return;  // (contexts live as long as the process, like the pool)
+    for (int i = 0; i < POOL_STREAMS; ++i) {
+        const int r = i % POOL_LANE_STREAMS;
+        const int prio = r == 0 ? prio_hi : (r == 1 ? prio_hi + (prio_lo - prio_hi) / 3 : (r == 2 ? prio_hi + 2 * (prio_lo - prio_hi) / 3 : prio_lo));
+        CUstream st = nullptr;
+        if (stream_create(&st, r == 0 ? g_chain : g_rest, CU_STREAM_NON_BLOCKING, prio) != CUDA_SUCCESS) return;
+        p->gstreams[i] = (cudaStream_t)st;
+    }
+    p->green = true;
+    p->green_sms = (int)chain.sm.smCount;
+}
+
 StreamPool* stream_pool() {
     static std::mutex mu;
     static StreamPool* pools[64] = {nullptr};
@@ -65,6 +108,7 @@ StreamPool* stream_pool() {
             delete p;
             return nullptr;
         }
+        make_green_streams(p, dev, lo, hi);
         pools[dev] = p;
     }
     return pools[dev];
@@ -104,13 +148,13 @@ struct Tiled {
 
     // events of lane ex.lane:  [j] top tile of panel j done (critical stream);  [T + j] leaf j done;
     // [2T + j] column j complete (mid stream);  [3T + j] rows of tile j+1 of column j updated (mid stream);
-    // [4T + i] bulk op i done;  [5T + 1] inverse stream done
+    // [4T + i] bulk op i done (fewer than 3T of them);  [7T + 1] inverse stream done
     cudaEvent_t ev_top(int j) const { return ex.pool->event(ex.lane, j); }
     cudaEvent_t ev_leaf(int j) const { return ex.pool->event(ex.lane, T + j); }
     cudaEvent_t ev_col(int j) const { return ex.pool->event(ex.lane, 2 * T + j); }
     cudaEvent_t ev_u1(int j) const { return ex.pool->event(ex.lane, 3 * T + j); }
     cudaEvent_t ev_bulk(int i) const { return ex.pool->event(ex.lane, 4 * T + i); }
-    cudaEvent_t ev_inv() const { return ex.pool->event(ex.lane, 5 * T + 1); }
+    cudaEvent_t ev_inv() const { return ex.pool->event(ex.lane, 7 * T + 1); }
     cudaStream_t s_mid() const { return two ? ex.mid : ex.crit; }
     cudaStream_t s_bulk() const { return two ? ex.bulk : ex.crit; }
 
@@ -303,6 +347,10 @@ struct Tiled {
                 update(s_mid(), o + w + top, below - top, o, w, k0, k1);
             }
         }
+        // (the critical stream's panel below reads rows the mid stream's U1 updated; that finished about when the diagonal
+        // update above did, so the wait goes in FRONT of the leaf, where it costs nothing: behind it, it would break the
+        // programmatic chaining leaf -> panel and expose a full launch latency on every step)
+        if (below > 0 && j > 0) wait(ex.crit, ev_u1(j));
         leaf(j);
         record(ev_leaf(j), ex.crit);
         {   // U tile = (X tile)^T, off the critical path (first read by the inverse tree)
@@ -317,7 +365,6 @@ struct Tiled {
             }
         }
         if (below > 0) {
-            if (j > 0) wait(ex.crit, ev_u1(j));
             panel(ex.crit, j, o + w, top, fb.Q);                                   // rows of tile j+1
             wait(s_mid(), ev_leaf(j));
             panel(s_mid(), j, o + w + top, below - top, fb.Q + (int64_t)TW * TW);  // the rest
@@ -331,7 +378,9 @@ struct Tiled {
         if (j + 1 >= T) return;
         const bool panel_end = (j + 1) % PW == 0;
         if (panel_end) {
-            // trailing update of everything behind the next column with this panel's k range
+            // trailing update of everything behind the next column with this panel's k range.  (Issuing the next panel's
+            // columns as separate, earlier-finishing launches was measured and lost: for a batch of matrices the chain is
+            // bound by the throughput of these products, and the narrow pieces run less efficiently than the square.)
             if (j + 2 < T) {
                 bulk_needs_col(j);
                 update(s_bulk(), off(j + 2), npad - off(j + 2), off(j + 2), npad - off(j + 2), off(s), off(j + 1));
@@ -394,19 +443,41 @@ TiledFactor* tiled_begin(const FactorExec& ex, const FactorBuffers& fb, int npad
         *rc_out = BOBE_E_ARG;
         return nullptr;
     }
+    const int T_ = (npad + TW - 1) / TW;
+    if (ex.crit != ex.home) {  // the chain runs on a stream of its own: fork it from the caller's
+        cudaEvent_t e = ex.pool->event(ex.lane, 7 * T_ + 4);
+        if (!e || cudaEventRecord(e, ex.home) != cudaSuccess || cudaStreamWaitEvent(ex.crit, e, 0) != cudaSuccess) {
+            set_error("factor: fork failed");
+            *rc_out = BOBE_E_CUDA;
+            return nullptr;
+        }
+    }
     init_stat_kernel<<<(batch + 127) / 128, 128, 0, ex.crit>>>(fb.dstat, fb.gate, batch, fb.force_refine);
     if ((*rc_out = check_launch("init_stat_kernel")) != BOBE_OK) return nullptr;
-    if (fb.zero_band == 0 && npad > NB) {  // buffers handed to the caller: the whole other triangle must read as zero
-        zero_other_triangle_kernel<<<dim3(npad / NB, npad / NB, batch), 256, 0, ex.crit>>>(fb.L, nullptr, fb.Linv, fb.U, npad, 0);
-        if ((*rc_out = check_launch("zero_other_triangle_kernel")) != BOBE_OK) return nullptr;
-    }
     TiledFactor* f = new TiledFactor(ex, fb, npad, batch);
     Tiled& t = f->t;
     t.T = (npad + TW - 1) / TW;
     t.two = ex.bulk != nullptr && ex.mid != nullptr && ex.inv != nullptr && ex.pool != nullptr && t.T > 2 && fb.Lt != nullptr;
     t.last_writer.assign(t.T, -1);
     if (t.two) {  // make sure every event exists before the first record (creation failure -> single-stream fallback)
-        if (!ex.pool->event(ex.lane, 5 * t.T + 2)) t.two = false;
+        if (!ex.pool->event(ex.lane, 7 * t.T + 5)) t.two = false;
+    }
+    if (fb.zero_band == 0 && npad > NB) {
+        // buffers handed to the caller: the whole other triangle must read as zero.  Nothing in the factorisation reads
+        // or writes those blocks, so in look-ahead mode the fill runs on the inverse stream, beside the chain
+        cudaStream_t st = ex.crit;
+        if (t.two) {
+            cudaEvent_t e = ex.pool->event(ex.lane, 7 * t.T + 2);
+            t.ok(cudaEventRecord(e, ex.crit), "event record");
+            t.ok(cudaStreamWaitEvent(ex.inv, e, 0), "event wait");
+            t.inv_used = true;
+            st = ex.inv;
+        }
+        zero_other_triangle_kernel<<<dim3(npad / NB, npad / NB, batch), 256, 0, st>>>(fb.L, nullptr, fb.Linv, fb.U, npad, 0);
+        if ((*rc_out = check_launch("zero_other_triangle_kernel")) != BOBE_OK) {
+            delete f;
+            return nullptr;
+        }
     }
     f->pw = ex.pw < 1 ? 1 : (ex.pw > t.T ? t.T : ex.pw);
     return f;
@@ -418,6 +489,15 @@ void tiled_step(TiledFactor* f, int j) {
 int32_t tiled_finish(TiledFactor* f) {
     if (f->t.rc == BOBE_OK) f->t.finish_phase1();
     if (f->t.rc == BOBE_OK) f->t.phase2();
+    if (f->ex.crit != f->ex.home) {  // join (also after an error: the caller's stream must not run ahead of stray work)
+        cudaEvent_t e = f->ex.pool->event(f->ex.lane, 7 * f->t.T + 3);
+        if (!e || cudaEventRecord(e, f->ex.crit) != cudaSuccess || cudaStreamWaitEvent(f->ex.home, e, 0) != cudaSuccess) {
+            if (f->t.rc == BOBE_OK) {
+                set_error("factor: join failed");
+                f->t.rc = BOBE_E_CUDA;
+            }
+        }
+    }
     const int32_t rc = f->t.rc;
     delete f;
     return rc;

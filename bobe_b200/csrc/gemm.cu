@@ -113,7 +113,9 @@ int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& a, int batch) {
     // Products whose 128 x 128 tiles can fill the machine: the persistent TMA kernel (trmm_tma.cuh)
     static const int64_t tma_gemm = env_int("BOBE_GEMM_TMA", 0);
     static const int64_t tma_min_tiles = env_int("BOBE_GEMM_TMA_MIN_TILES", 2);  // live tiles per SM
-    if (tma_gemm && !forced && a.node_count == 0 && a.M >= 256 && a.N >= 256 && a.K >= 128 && ((((uintptr_t)a.A) | ((uintptr_t)a.Bt)) & 15) == 0 &&
+    // BOBE_GEMM_TMA: 1 = every large product, 2 = only products without a triangular row operand (experiment knobs)
+    if (tma_gemm && !forced && a.node_count == 0 && a.M >= 256 && a.N >= (tma_gemm == 2 ? 128 : 256) && a.K >= 128 &&
+        (tma_gemm != 2 || mode == TRI_NONE) && ((((uintptr_t)a.A) | ((uintptr_t)a.Bt)) & 15) == 0 &&
         (a.strideA % 2) == 0 && (a.strideB % 2) == 0) {
         using Cfg = CfgBig;
         const int tiles_m = (a.M + Cfg::BM - 1) / Cfg::BM, tiles_n = (a.N + Cfg::BN - 1) / Cfg::BN;

@@ -72,6 +72,14 @@ constexpr int POOL_LANE_STREAMS = 4;  // per lane: chain, rest of the current co
 constexpr int POOL_STREAMS = 8 * POOL_LANE_STREAMS;
 struct StreamPool {
     cudaStream_t streams[POOL_STREAMS];
+    // the same roles on two GREEN CONTEXTS with disjoint SM sets (driver API, CUDA >= 12.4): role 0 (the dependent chain:
+    // leaves + the small products between them) on a partition of a few SMs of its own, roles 1-3 on the rest.  A leaf
+    // needs a whole SM's shared memory; on a machine filled with the look-ahead products of a batch of matrices it waited
+    // for an SM to drain completely, several hundred microseconds at a time (stream priorities do not reserve anything).
+    // Null when the driver refuses (then `streams` is used).
+    cudaStream_t gstreams[POOL_STREAMS];
+    bool green = false;
+    int green_sms = 0;
     cudaEvent_t fork, join[POOL_STREAMS];
     std::vector<cudaEvent_t> ring[POOL_STREAMS];  // per-lane dependency events, created on demand
     std::mutex enqueue_mu;  // the events are shared: one host thread enqueues on the pool at a time
@@ -82,6 +90,7 @@ StreamPool* stream_pool();
 // where one factorisation chain runs: `crit` carries the dependent chain; `bulk` / `inv` (optional, with pool / lane for
 // their events) the look-ahead products and the inverse tree.  pw = tile columns per outer panel (factor_tiled.cuh).
 struct FactorExec {
+    cudaStream_t home;  // the stream the caller's stages before / after the factorisation run on (crit is forked from it)
     cudaStream_t crit;
     cudaStream_t mid;
     cudaStream_t bulk;
@@ -98,10 +107,11 @@ int tiled_steps(const TiledFactor* f);
 void tiled_step(TiledFactor* f, int j);
 int32_t tiled_finish(TiledFactor* f);
 // streams / knobs of lane `lane` (BOBE_FACTOR_PW, BOBE_LOOKAHEAD_MAX); bulk / inv are null when look-ahead is off
-FactorExec factor_exec(cudaStream_t stream, StreamPool* pool, int lane, int batch);
+// total_batch: matrices in flight over ALL lanes of this call (decides whether the chain gets its own SM partition)
+FactorExec factor_exec(cudaStream_t stream, StreamPool* pool, int lane, int batch, int total_batch);
 // scheme dispatch (BOBE_FACTOR knob); pool may be null (no look-ahead), lane selects the pool streams / events used
 int32_t factor_any(cudaStream_t stream, StreamPool* pool, int lane, const FactorBuffers& fb, int npad, int batch);
-// factor_any on the pool's lane-0 chain stream (higher priority than the look-ahead streams), forked from / joined to `stream`
+// factor_any on lane 0 of the pool (entry points that factorise outside bobe_mll_grad_batched)
 int32_t factor_on_pool(cudaStream_t stream, StreamPool* pool, const FactorBuffers& fb, int npad, int batch);
 int32_t factor_recursive(cudaStream_t stream, const FactorBuffers& fb, int npad, int batch);
 int32_t launch_kinv(cudaStream_t stream, const FactorBuffers& fb, int npad, int batch);  // KB <- U U^T (lower 128-tiles)

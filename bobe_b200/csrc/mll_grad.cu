@@ -344,7 +344,7 @@ extern "C" int32_t bobe_mll_grad_batched(void* stream_, int32_t kind, const doub
         int steps = 0;
         each([&](Sub& u, int si) -> int32_t {
             int32_t rc;
-            u.tf = tiled_begin(factor_exec(u.st, pool, si, (int)u.Rs), u.fb, npad, (int)u.Rs, &rc);
+            u.tf = tiled_begin(factor_exec(u.st, pool, si, (int)u.Rs, (int)R), u.fb, npad, (int)u.Rs, &rc);
             if (u.tf) steps = std::max(steps, tiled_steps(u.tf));
             return rc;
         });

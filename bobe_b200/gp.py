@@ -76,13 +76,21 @@ def kernel_diag(x, kernel_variance, noise, include_noise=True):
 
 
 def dist_sq(x, y):
-    """BOBE/gp.py:80-96, via the RBF kernel with unit lengthscales: q = -2 log k."""
-    raise NotImplementedError("dist_sq is fused into the kernel builds; use rbf_kernel/matern_kernel")
+    """BOBE/gp.py:80-96 -- squared distances by direct differences (``bobe_dist_sq``)."""
+    as_t = _is_t(x)
+    dev = x.device if as_t and x.is_cuda else _dev()
+    out = ops.dist_sq(_to_dev(np.atleast_2d(x) if not as_t else x, dev), _to_dev(np.atleast_2d(y) if not _is_t(y) else y, dev))
+    return out if as_t else out.cpu().numpy()
 
 
 def gp_mll(k, train_y, num_points):
-    raise NotImplementedError("gp_mll is fused into GP.neg_mll / bobe_mll_grad_batched (the kernel matrix "
-                              "never leaves the device); use GP.neg_mll")
+    """BOBE/gp.py:170-178 -- log marginal likelihood of a caller-supplied kernel matrix (``bobe_cholesky_batched``):
+    ``-1/2 y^T K^-1 y - sum log L_ii - n/2 log 2 pi``; NaN when K is not positive definite (jnp.linalg.cholesky)."""
+    as_t = _is_t(k)
+    dev = k.device if as_t and k.is_cuda else _dev()
+    _, _, logdet, quad, _ = ops.cholesky_solve(_to_dev(k, dev), _to_dev(train_y, dev).reshape(-1))
+    val = -0.5 * quad[0] - logdet[0] - 0.5 * float(num_points) * float(np.log(2.0 * np.pi))
+    return val if as_t else float(val.item())
 
 
 def fast_update_cholesky(L, k, k_self):

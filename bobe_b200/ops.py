@@ -94,6 +94,44 @@ def factorize(kind: str, X, y, ls, kv, noise: float, want_L: bool = True):
     return L, Linv, alpha, logdet, quad, info
 
 
+def cholesky_solve(K, y):
+    """Factorise caller-supplied kernel matrices K (B, n, n) (or (n, n)) and solve for ``y`` (n,):
+    returns (L (B, npad, npad), alpha (B, npad), logdet (B), quad (B), info (B)) -- ``jnp.linalg.cholesky`` +
+    ``cho_solve`` of gp_mll, BOBE/gp.py:170-178.  Only the lower triangle of K is read."""
+    K, y = _chk(K, "K"), _chk(y, "y").reshape(-1)
+    if K.dim() == 2:
+        K = K[None]
+    B, n, n2 = K.shape
+    if n != n2 or y.shape[0] != n:
+        raise ValueError("cholesky_solve: K must be (B, n, n) and y (n,)")
+    p = npad(n)
+    dev = K.device
+    L = torch.empty((B, p, p), dtype=torch.float64, device=dev)
+    alpha = torch.empty((B, p), dtype=torch.float64, device=dev)
+    logdet = torch.empty(B, dtype=torch.float64, device=dev)
+    quad = torch.empty(B, dtype=torch.float64, device=dev)
+    info = torch.empty(B, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.bobe_cholesky_workspace_bytes(n, B), dev)
+        check(lib.bobe_cholesky_batched(_stream(), K.data_ptr(), n, n, B, y.data_ptr(), L.data_ptr(), None, alpha.data_ptr(),
+                                        logdet.data_ptr(), quad.data_ptr(), info.data_ptr(), ws.data_ptr(), ws.numel()),
+              "bobe_cholesky_batched")
+    return L, alpha, logdet, quad, info
+
+
+def dist_sq(xa, xb) -> torch.Tensor:
+    """sum_k (xa_ik - xb_jk)^2 by direct differences -- BOBE/gp.py:80-96."""
+    xa, xb = _chk(xa, "xa"), _chk(xb, "xb")
+    n1, d = xa.shape
+    n2 = xb.shape[0]
+    if xb.shape[1] != d:
+        raise ValueError("dist_sq: column counts differ")
+    out = torch.empty((n1, n2), dtype=torch.float64, device=xa.device)
+    with torch.cuda.device(xa.device):
+        check(lib.bobe_dist_sq(_stream(), xa.data_ptr(), n1, xb.data_ptr(), n2, d, out.data_ptr(), n2), "bobe_dist_sq")
+    return out
+
+
 def factor_append(kind: str, X, y, n_old: int, ls, kv: float, noise: float, L, Linv):
     """Extend the padded factors of the first ``n_old`` rows of X by the remaining rows, in O(b n^2), and re-solve
     alpha for all targets ``y`` -- GP.update (BOBE/gp.py:495-541) without the full re-factorisation.

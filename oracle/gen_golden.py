@@ -70,6 +70,13 @@ def main(names=None):
             out["truth_mll"] = np.array(T.mll())  # at the current hyper-parameters = restart 0
             if X.shape[0] <= 100:
                 out["truth_mll_grad"] = T.mll_grad()
+            # ... and at every restart row (random hyper-parameters: often far worse conditioned than row 0), so that
+            # the CUDA log-ML of every row can be read against the exact value and the oracle's own rounding noise
+            rows = []
+            for r in range(x0.shape[0]):
+                ls_r, kv_r, _ = gp._parse_hyperparams(x0[r])
+                rows.append(float(TruthGP(gp.kernel_name, X, gp.train_y, ls_r, kv_r, gp.noise).mll()))
+            out["truth_mll_rows"] = np.array(rows)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
         print(name, {k: np.asarray(v).shape for k, v in out.items()})
 
