@@ -183,7 +183,7 @@ int32_t factor_on_pool(cudaStream_t stream, StreamPool* pool, const FactorBuffer
 }
 
 FactorExec factor_exec(cudaStream_t stream, StreamPool* pool, int lane, int batch, int total_batch) {
-    static const int64_t la_max = env_int("BOBE_LOOKAHEAD_MAX", 16);
+    static const int64_t la_max = env_int("BOBE_LOOKAHEAD_MAX", 8);
     static const int64_t pw = env_int("BOBE_FACTOR_PW", 4);  // tile columns per outer panel (the same for every batch size)
     static const int64_t green_max = env_int("BOBE_GREEN_MAX", 16);  // most matrices in flight for the chain partition
     const bool la = pool && batch <= la_max && lane >= 0 && POOL_LANE_STREAMS * lane + 3 < POOL_STREAMS;

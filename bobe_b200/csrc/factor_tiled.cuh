@@ -223,7 +223,7 @@ struct Tiled {
         static const bool wide_tiles = env_int("BOBE_TILE", 0) > 1 || env_int("BOBE_GEMM_TMA", 0) != 0;
         // gate rows: [0] latest state (initial value before leaf 0), [j + 1] snapshot after leaf j
         LeafIO io{fb.KB, fb.L, nullptr, fb.Linv, fb.U, fb.diag, fb.dstat, fb.gate + (int64_t)(j == 0 ? 0 : j) * batch, npad,
-                  off(j), mode == 0 ? 0 : 1, fb.gate + (int64_t)(j + 1) * batch, fb.gate, wide_tiles ? 1 : 0};
+                  off(j), mode == 0 ? 0 : 1, fb.gate + (int64_t)(j + 1) * batch, fb.gate, (wide_tiles ? 1 : 0) | (two ? 0 : 2)};
         auto go = [&](auto kernel, int smem) {
             if ((rc = ensure_smem_fn(kernel, smem)) != BOBE_OK) return;
             launch_pdl(kernel, dim3(1, 1, batch), dim3(LEAF_THREADS), smem, ex.crit, io);
@@ -339,8 +339,13 @@ struct Tiled {
             // diagonal tile: its operand rows L[tile j, k0:k1) are the top of panel j-1 (this stream) and, at the start
             // of an outer panel, lower rows of the columns before it (mid stream)
             if (j == s && j >= 2) wait(ex.crit, ev_col(j - 2));
-            update(ex.crit, o, w, o, w, k0, k1);
-            if (below > 0) {
+            if (!two) {
+                // single stream: the three row ranges in ONE launch (same arithmetic per element; fewer, larger launches)
+                update(ex.crit, o, w + below, o, w, k0, k1);
+            } else {
+                update(ex.crit, o, w, o, w, k0, k1);
+            }
+            if (two && below > 0) {
                 wait(s_mid(), ev_top(j - 1));  // the Bt operand L[tile j, k0:k1) includes the top of panel j-1
                 update(s_mid(), o + w, top, o, w, k0, k1);
                 record(ev_u1(j), s_mid());
@@ -353,18 +358,17 @@ struct Tiled {
         if (below > 0 && j > 0) wait(ex.crit, ev_u1(j));
         leaf(j);
         record(ev_leaf(j), ex.crit);
-        {   // U tile = (X tile)^T, off the critical path (first read by the inverse tree)
-            cudaStream_t st = two ? ex.inv : ex.crit;
-            if (two) {
-                wait(ex.inv, ev_leaf(j));
-                inv_used = true;
-            }
+        if (two) {  // U tile = (X tile)^T, off the critical path (single-stream mode: the leaf writes it itself)
+            wait(ex.inv, ev_leaf(j));
+            inv_used = true;
             if (rc == BOBE_OK) {
-                launch_pdl(tile_transpose_kernel, dim3(w / 32, w / 32, batch), dim3(256), 0, st, (const double*)fb.Linv, fb.U, npad, o);
+                launch_pdl(tile_transpose_kernel, dim3(w / 32, w / 32, batch), dim3(256), 0, ex.inv, (const double*)fb.Linv, fb.U, npad, o);
                 rc = check_launch("tile_transpose_kernel");
             }
         }
-        if (below > 0) {
+        if (below > 0 && !two) {
+            panel(ex.crit, j, o + w, below, fb.Q);  // single stream: all rows in one launch
+        } else if (below > 0) {
             panel(ex.crit, j, o + w, top, fb.Q);                                   // rows of tile j+1
             wait(s_mid(), ev_leaf(j));
             panel(s_mid(), j, o + w + top, below - top, fb.Q + (int64_t)TW * TW);  // the rest

@@ -242,11 +242,103 @@ extern "C" int64_t bobe_mll_grad_workspace_bytes(int64_t n, int64_t d, int64_t R
     return mll_layout(n, d, R).total * 8 + 256;
 }
 
+// One call is several hundred launches and event operations on up to sixteen streams: 1 - 2 ms of host time, more than
+// a third of the device time of a small batch, and exposed whenever the caller needs the result before it can issue the
+// next call (every optimiser step).  A call whose arguments (all pointers, sizes and scalars) repeat is therefore captured
+// ONCE into a CUDA graph -- the same launches, dependencies and programmatic-launch edges -- and replayed from then on:
+// one graph launch instead of the enqueue.  First sighting of a key: plain enqueue; second: capture + instantiate.
+// BOBE_MLL_GRAPH=0 turns this off; a caller that is itself capturing (XLA command buffers, torch.cuda.graph) is left alone.
+namespace {
+struct GraphKey {
+    const void *X, *y, *lp, *val, *grad, *info, *ws;
+    int64_t n, d, R, P, ws_bytes;
+    int32_t kind, has_kv;
+    double fixed_kv, noise;
+    int dev;
+    bool operator==(const GraphKey& o) const {
+        return X == o.X && y == o.y && lp == o.lp && val == o.val && grad == o.grad && info == o.info && ws == o.ws && n == o.n &&
+               d == o.d && R == o.R && P == o.P && ws_bytes == o.ws_bytes && kind == o.kind && has_kv == o.has_kv &&
+               fixed_kv == o.fixed_kv && noise == o.noise && dev == o.dev;
+    }
+};
+struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec;  // null: key seen once, not captured yet
+    uint64_t stamp;
+};
+constexpr size_t GRAPH_CACHE = 16;
+std::mutex g_graph_mu;
+std::vector<GraphEntry> g_graphs;
+uint64_t g_graph_clock = 0;
+
+int32_t mll_grad_enqueue(cudaStream_t stream, int32_t kind, const double* X, const double* y, int64_t n, int64_t d,
+                         const double* log_params, int64_t R, int64_t P, int32_t has_kv, double fixed_kv, double noise,
+                         double* val, double* grad, int32_t* info, void* ws, int64_t ws_bytes);
+}  // namespace
+
 extern "C" int32_t bobe_mll_grad_batched(void* stream_, int32_t kind, const double* X, const double* y, int64_t n,
                                          int64_t d, const double* log_params, int64_t R, int64_t P, int32_t has_kv,
                                          double fixed_kv, double noise, double* val, double* grad, int32_t* info,
                                          void* ws, int64_t ws_bytes) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    static const bool graphs = env_int("BOBE_MLL_GRAPH", 1) != 0;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    int dev = 0;
+    if (!graphs || cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone ||
+        cudaGetDevice(&dev) != cudaSuccess)
+        return mll_grad_enqueue(stream, kind, X, y, n, d, log_params, R, P, has_kv, fixed_kv, noise, val, grad, info, ws, ws_bytes);
+    const GraphKey key{X, y, log_params, val, grad, info, ws, n, d, R, P, ws_bytes, kind, has_kv, fixed_kv, noise, dev};
+    std::lock_guard<std::mutex> lock(g_graph_mu);
+    GraphEntry* hit = nullptr;
+    for (auto& e : g_graphs)
+        if (e.key == key) hit = &e;
+    if (hit && hit->exec) {
+        hit->stamp = ++g_graph_clock;
+        if (cudaGraphLaunch(hit->exec, stream) == cudaSuccess) return BOBE_OK;
+        cudaGetLastError();
+        cudaGraphExecDestroy(hit->exec);  // should not happen; fall back to the plain path for good
+        hit->exec = nullptr;
+        return mll_grad_enqueue(stream, kind, X, y, n, d, log_params, R, P, has_kv, fixed_kv, noise, val, grad, info, ws, ws_bytes);
+    }
+    if (!hit) {  // first sighting: remember the key, run plainly (also warms every function attribute / pool object)
+        if (g_graphs.size() >= GRAPH_CACHE) {
+            size_t old = 0;
+            for (size_t i = 1; i < g_graphs.size(); ++i)
+                if (g_graphs[i].stamp < g_graphs[old].stamp) old = i;
+            if (g_graphs[old].exec) cudaGraphExecDestroy(g_graphs[old].exec);
+            g_graphs.erase(g_graphs.begin() + old);
+        }
+        g_graphs.push_back(GraphEntry{key, nullptr, ++g_graph_clock});
+        return mll_grad_enqueue(stream, kind, X, y, n, d, log_params, R, P, has_kv, fixed_kv, noise, val, grad, info, ws, ws_bytes);
+    }
+    // second sighting: capture
+    hit->stamp = ++g_graph_clock;
+    if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        return mll_grad_enqueue(stream, kind, X, y, n, d, log_params, R, P, has_kv, fixed_kv, noise, val, grad, info, ws, ws_bytes);
+    }
+    const int32_t rc = mll_grad_enqueue(stream, kind, X, y, n, d, log_params, R, P, has_kv, fixed_kv, noise, val, grad, info, ws, ws_bytes);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+    cudaGraphExec_t exec = nullptr;
+    if (rc == BOBE_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess &&
+        cudaGraphLaunch(exec, stream) == cudaSuccess) {
+        cudaGraphDestroy(graph);
+        hit->exec = exec;
+        return BOBE_OK;
+    }
+    cudaGetLastError();  // capture did not work out here: nothing was executed, so run the call plainly (and stop trying)
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    hit->key.dev = -1;  // never matches again
+    if (rc != BOBE_OK) return rc;
+    return mll_grad_enqueue(stream, kind, X, y, n, d, log_params, R, P, has_kv, fixed_kv, noise, val, grad, info, ws, ws_bytes);
+}
+
+namespace {
+int32_t mll_grad_enqueue(cudaStream_t stream, int32_t kind, const double* X, const double* y, int64_t n, int64_t d,
+                         const double* log_params, int64_t R, int64_t P, int32_t has_kv, double fixed_kv, double noise,
+                         double* val, double* grad, int32_t* info, void* ws, int64_t ws_bytes) {
     if (!X || !y || !log_params || !val || !grad || !info || !ws) {
         set_error("mll_grad: null pointer");
         return BOBE_E_ARG;
@@ -390,3 +482,4 @@ extern "C" int32_t bobe_mll_grad_batched(void* stream_, int32_t kind, const doub
     }
     return rc_all;
 }
+}  // namespace

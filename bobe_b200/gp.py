@@ -320,12 +320,14 @@ class GP:
 
         One lock-step device call for all rows; prior terms added on the host.
         """
-        lp = np.atleast_2d(np.asarray(log_params, dtype=np.float64))
+        lp = np.ascontiguousarray(np.atleast_2d(np.asarray(log_params, dtype=np.float64)))
         self._ensure_factor()
         dev = self.device
-        val, grad, _info = ops.mll_grad_batched(self.kernel_name, self._X_dev, self._y_dev, _to_dev(lp, dev),
+        # (persistent staging buffers: the same device pointers on every optimiser step, so the native call replays its
+        # captured CUDA graph instead of enqueueing several hundred launches)
+        val, grad, _info = ops.mll_grad_batched(self.kernel_name, self._X_dev, self._y_dev, torch.from_numpy(lp),
                                                 not self.fixed_kernel_variance, float(self.kernel_variance),
-                                                float(self.noise))
+                                                float(self.noise), reuse_buffers=True)
         # the device call above is asynchronous: the O(R d) prior terms are evaluated on the host WHILE it runs, and only
         # then are the results fetched (the .cpu() below is the first synchronisation)
         pv, pg = np.empty(lp.shape[0]), np.empty_like(lp)

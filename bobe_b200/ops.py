@@ -43,6 +43,7 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
 
 def release_workspace():
     _ws_cache.clear()
+    _mll_io_cache.clear()
 
 
 def _chk(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -163,18 +164,46 @@ def factor_append(kind: str, X, y, n_old: int, ls, kv: float, noise: float, L, L
     return L, Linv, alpha, info
 
 
+_mll_io_cache = OrderedDict()  # (device, stream, R, P) -> (log_params, val, grad, info) staging buffers
+
+
 def mll_grad_batched(kind: str, X, y, log_params, has_kv: bool, fixed_kv: float, noise: float,
-                     max_batch: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """log p(y | theta_r) and d/d theta for R restarts -- BOBE/gp.py:385-398 via BOBE/optim.py:309."""
-    X, y, lp = _chk(X, "X"), _chk(y, "y").reshape(-1), _chk(log_params, "log_params")
-    if lp.dim() == 1:
-        lp = lp[None, :]
-    R, P = lp.shape
+                     max_batch: Optional[int] = None, reuse_buffers: bool = False
+                     ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """log p(y | theta_r) and d/d theta for R restarts -- BOBE/gp.py:385-398 via BOBE/optim.py:309.
+
+    ``reuse_buffers=True``: the parameters are copied into, and the results returned in, buffers that persist per
+    (device, stream, R, P).  The native call then sees the same pointers every time and replays its captured CUDA graph
+    (one graph launch instead of several hundred kernel launches on the host).  The returned tensors are only valid until
+    the next call with the same shape on the same stream -- for callers that fetch the results at once (the optimisers)."""
+    X, y = _chk(X, "X"), _chk(y, "y").reshape(-1)
     n, d = X.shape
     dev = X.device
-    val = torch.empty(R, dtype=torch.float64, device=dev)
-    grad = torch.empty((R, P), dtype=torch.float64, device=dev)
-    info = torch.empty(R, dtype=torch.int32, device=dev)
+    if reuse_buffers:
+        lp_in = log_params if isinstance(log_params, torch.Tensor) else torch.as_tensor(log_params, dtype=torch.float64)
+        if lp_in.dim() == 1:
+            lp_in = lp_in[None, :]
+        R, P = lp_in.shape
+        di = dev.index if dev.index is not None else torch.cuda.current_device()
+        key = (di, torch.cuda.current_stream(di).cuda_stream, R, P)
+        bufs = _mll_io_cache.get(key)
+        if bufs is None:
+            bufs = (torch.empty((R, P), dtype=torch.float64, device=dev), torch.empty(R, dtype=torch.float64, device=dev),
+                    torch.empty((R, P), dtype=torch.float64, device=dev), torch.empty(R, dtype=torch.int32, device=dev))
+            _mll_io_cache[key] = bufs
+            while len(_mll_io_cache) > 8:
+                _mll_io_cache.popitem(last=False)
+        _mll_io_cache.move_to_end(key)
+        lp, val, grad, info = bufs
+        lp.copy_(lp_in, non_blocking=True)
+    else:
+        lp = _chk(log_params, "log_params")
+        if lp.dim() == 1:
+            lp = lp[None, :]
+        R, P = lp.shape
+        val = torch.empty(R, dtype=torch.float64, device=dev)
+        grad = torch.empty((R, P), dtype=torch.float64, device=dev)
+        info = torch.empty(R, dtype=torch.int32, device=dev)
     if max_batch is None:  # keep the workspace under ~1/3 of device memory
         per = lib.bobe_mll_grad_workspace_bytes(n, d, 1)
         free = torch.cuda.get_device_properties(dev).total_memory // 3
