@@ -246,7 +246,8 @@ extern "C" int64_t bobe_mll_grad_workspace_bytes(int64_t n, int64_t d, int64_t R
 // a third of the device time of a small batch, and exposed whenever the caller needs the result before it can issue the
 // next call (every optimiser step).  A call whose arguments (all pointers, sizes and scalars) repeat is therefore captured
 // ONCE into a CUDA graph -- the same launches, dependencies and programmatic-launch edges -- and replayed from then on:
-// one graph launch instead of the enqueue.  First sighting of a key: plain enqueue; second: capture + instantiate.
+// one graph launch instead of the enqueue.  A key is captured at its third sighting (capture + instantiate cost several
+// plain enqueues; a caller whose output pointers cycle through a few allocator blocks must not pay that every call).
 // BOBE_MLL_GRAPH=0 turns this off; a caller that is itself capturing (XLA command buffers, torch.cuda.graph) is left alone.
 namespace {
 struct GraphKey {
@@ -263,9 +264,11 @@ struct GraphKey {
 };
 struct GraphEntry {
     GraphKey key;
-    cudaGraphExec_t exec;  // null: key seen once, not captured yet
+    cudaGraphExec_t exec;  // null: not captured yet
     uint64_t stamp;
+    int sightings;
 };
+constexpr int GRAPH_CAPTURE_AFTER = 3;  // capture + instantiate costs several plain enqueues: only for keys that keep coming
 constexpr size_t GRAPH_CACHE = 16;
 std::mutex g_graph_mu;
 std::vector<GraphEntry> g_graphs;
@@ -308,11 +311,13 @@ extern "C" int32_t bobe_mll_grad_batched(void* stream_, int32_t kind, const doub
             if (g_graphs[old].exec) cudaGraphExecDestroy(g_graphs[old].exec);
             g_graphs.erase(g_graphs.begin() + old);
         }
-        g_graphs.push_back(GraphEntry{key, nullptr, ++g_graph_clock});
+        g_graphs.push_back(GraphEntry{key, nullptr, ++g_graph_clock, 1});
         return mll_grad_enqueue(stream, kind, X, y, n, d, log_params, R, P, has_kv, fixed_kv, noise, val, grad, info, ws, ws_bytes);
     }
-    // second sighting: capture
     hit->stamp = ++g_graph_clock;
+    if (++hit->sightings < GRAPH_CAPTURE_AFTER)
+        return mll_grad_enqueue(stream, kind, X, y, n, d, log_params, R, P, has_kv, fixed_kv, noise, val, grad, info, ws, ws_bytes);
+    // the key keeps coming: capture
     if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
         cudaGetLastError();
         return mll_grad_enqueue(stream, kind, X, y, n, d, log_params, R, P, has_kv, fixed_kv, noise, val, grad, info, ws, ws_bytes);
@@ -368,10 +373,17 @@ int32_t mll_grad_enqueue(cudaStream_t stream, int32_t kind, const double* X, con
     // the caller's stream with events): one sub-batch's latency-bound leaves and small products overlap with another's
     // large tensor-core products.  The host enqueues the sub-batches STAGE BY STAGE (and the factorisation tile column
     // by tile column): enqueued one chain after the other, the second would start half a millisecond behind the first.
-    static const int64_t max_streams = std::min<int64_t>(MLL_MAX_STREAMS, env_int("BOBE_MLL_STREAMS", 4));
-    static const int64_t min_per_stream = std::max<int64_t>(1, env_int("BOBE_MLL_MIN_PER_STREAM", 4));
+    // Measured policy (profiles/r02/sub_batch_sweep.log, n = 2000): two sub-batches from 8 restarts on, three from 32 on.
+    // BOBE_MLL_STREAMS / BOBE_MLL_MIN_PER_STREAM force S = min(streams, R / min_per_stream) instead (experiments).
+    static const int64_t forced_streams = env_int("BOBE_MLL_STREAMS", 0);
+    static const int64_t max_streams = std::min<int64_t>(MLL_MAX_STREAMS, forced_streams > 0 ? forced_streams : 4);
+    static const int64_t min_per_stream = std::max<int64_t>(1, env_int("BOBE_MLL_MIN_PER_STREAM", forced_streams > 0 ? 4 : 0));
     static const int64_t scheme = env_int("BOBE_FACTOR", 1);
-    const int S = (int)std::min<int64_t>(max_streams, std::max<int64_t>(1, R / min_per_stream));
+    int S;
+    if (forced_streams > 0 || min_per_stream > 0)
+        S = (int)std::min<int64_t>(max_streams, std::max<int64_t>(1, R / std::max<int64_t>(1, min_per_stream)));
+    else
+        S = R < 8 ? 1 : (R < 32 ? 2 : 3);
     // XLA may call handlers from several host threads: the record / wait pairs below must not interleave with those
     // of another caller of the same device (stream order then keeps the shared side streams correct)
     StreamPool* pool = stream_pool();

@@ -27,8 +27,16 @@ for n, d in ((200, 2), (500, 6), (1500, 12)):
     timed("predict_mean_single", lambda: gp.predict_mean_single(rng.uniform(0, 1, d)), reps=20)
     timed("predict_single (mean+var)", lambda: gp.predict_single(rng.uniform(0, 1, d)), reps=20)
     best = float(gp.train_y.max())
-    timed("EI.get_next_point (20 restarts, maxiter 250)", lambda: EI().get_next_point(gp, {'best_y': best, 'zeta': 0.01}, verbose=False, rng=rng))
-    timed("LogEI.get_next_point", lambda: LogEI().get_next_point(gp, {'best_y': best, 'zeta': 0.01}, verbose=False, rng=rng))
+    for cls in (EI, LogEI):  # wall time AND the number of batched value-and-gradient calls / points the optimiser issued
+        acq = cls()
+        cnt = {"calls": 0, "pts": 0}
+        orig = acq.value_and_grad_batched
+        def counted(xs, *a, _o=orig, **k):
+            cnt["calls"] += 1; cnt["pts"] += len(np.atleast_2d(xs))
+            return _o(xs, *a, **k)
+        acq.value_and_grad_batched = counted
+        timed(f"{cls.__name__}.get_next_point (20 restarts, maxiter 250)", lambda: acq.get_next_point(gp, {'best_y': best, 'zeta': 0.01}, verbose=False, rng=rng))
+        print(f"    -> {cnt['calls']} batched value+gradient calls, {cnt['pts']} point evaluations")
     mc = {'x': rng.uniform(0, 1, (2048, d))}
     timed("WIPV.get_next_point (mc_points_size=256)", lambda: WIPV().get_next_point(gp, {'mc_samples': mc, 'mc_points_size': 256}, verbose=False, rng=rng))
     timed("WIPV.get_next_batch (n_batch=4)", lambda: WIPV().get_next_batch(gp, n_batch=4, acq_kwargs={'mc_samples': mc, 'mc_points_size': 256}, verbose=False, rng=rng))
