@@ -317,21 +317,31 @@ extern "C" int32_t bobe_mll_grad_batched(void* stream_, int32_t kind, const doub
     hit->stamp = ++g_graph_clock;
     if (++hit->sightings < GRAPH_CAPTURE_AFTER)
         return mll_grad_enqueue(stream, kind, X, y, n, d, log_params, R, P, has_kv, fixed_kv, noise, val, grad, info, ws, ws_bytes);
-    // the key keeps coming: capture
-    if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    // the key keeps coming: capture -- on a stream of our own (the caller's may be the legacy default stream, which cannot
+    // be captured; torch's default stream is), the graph is then launched into the caller's stream
+    static cudaStream_t cap_streams[64] = {nullptr};
+    if (dev < 0 || dev >= 64 ||
+        (!cap_streams[dev] && cudaStreamCreateWithFlags(&cap_streams[dev], cudaStreamNonBlocking) != cudaSuccess) ||
+        cudaStreamBeginCapture(cap_streams[dev], cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
         cudaGetLastError();
+        hit->key.dev = -1;
         return mll_grad_enqueue(stream, kind, X, y, n, d, log_params, R, P, has_kv, fixed_kv, noise, val, grad, info, ws, ws_bytes);
     }
-    const int32_t rc = mll_grad_enqueue(stream, kind, X, y, n, d, log_params, R, P, has_kv, fixed_kv, noise, val, grad, info, ws, ws_bytes);
+    cudaStream_t cs = cap_streams[dev];
+    const int32_t rc = mll_grad_enqueue(cs, kind, X, y, n, d, log_params, R, P, has_kv, fixed_kv, noise, val, grad, info, ws, ws_bytes);
     cudaGraph_t graph = nullptr;
-    const cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+    const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
     cudaGraphExec_t exec = nullptr;
     if (rc == BOBE_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess &&
         cudaGraphLaunch(exec, stream) == cudaSuccess) {
         cudaGraphDestroy(graph);
         hit->exec = exec;
+        if (env_int("BOBE_MLL_GRAPH_DEBUG", 0)) fprintf(stderr, "bobe: mll_grad graph captured (R=%lld)\n", (long long)R);
         return BOBE_OK;
     }
+    if (env_int("BOBE_MLL_GRAPH_DEBUG", 0))
+        fprintf(stderr, "bobe: mll_grad graph capture FAILED rc=%d end=%s last=%s\n", rc, cudaGetErrorString(ce),
+                cudaGetErrorString(cudaPeekAtLastError()));
     cudaGetLastError();  // capture did not work out here: nothing was executed, so run the call plainly (and stop trying)
     if (exec) cudaGraphExecDestroy(exec);
     if (graph) cudaGraphDestroy(graph);
