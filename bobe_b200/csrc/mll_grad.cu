@@ -387,7 +387,7 @@ int32_t mll_grad_enqueue(cudaStream_t stream, int32_t kind, const double* X, con
     // BOBE_MLL_STREAMS / BOBE_MLL_MIN_PER_STREAM force S = min(streams, R / min_per_stream) instead (experiments).
     static const int64_t forced_streams = env_int("BOBE_MLL_STREAMS", 0);
     static const int64_t max_streams = std::min<int64_t>(MLL_MAX_STREAMS, forced_streams > 0 ? forced_streams : 4);
-    static const int64_t min_per_stream = std::max<int64_t>(1, env_int("BOBE_MLL_MIN_PER_STREAM", forced_streams > 0 ? 4 : 0));
+    static const int64_t min_per_stream = env_int("BOBE_MLL_MIN_PER_STREAM", forced_streams > 0 ? 4 : 0);  // 0: not forced
     static const int64_t scheme = env_int("BOBE_FACTOR", 1);
     int S;
     if (forced_streams > 0 || min_per_stream > 0)
@@ -472,11 +472,32 @@ int32_t mll_grad_enqueue(cudaStream_t stream, int32_t kind, const double* X, con
                 if (subs[si].rc == BOBE_OK) subs[si].rc = rc;
             }
     }
-    each([&](Sub& u, int) -> int32_t {
+    // alpha / log-det / quad (a dozen small, partly gated launches) and K^-1 = U U^T (the largest product of the call) only
+    // share their INPUTS (Linv, U): the vector work runs on a side stream of the lane beside the product, joined before
+    // the gradient kernel, which needs both
+    each([&](Sub& u, int si) -> int32_t {
+        static const bool use_side = env_int("BOBE_MLL_SIDE_VECTORS", 1) != 0;
+        if (!use_side) {
+            SolveArgs sa0{kind, X, u.ls_s, u.kv_s, d, noise, u.xs};
+            if (int32_t rc0 = launch_solve_vectors(u.st, u.fb, sa0, y, n, npad, (int)u.Rs, u.zws, u.alpha, u.logdet, u.quad, info + u.r0))
+                return rc0;
+            return launch_kinv(u.st, u.fb, npad, (int)u.Rs);
+        }
+        cudaStream_t side = pool->streams[POOL_LANE_STREAMS * si + 1];
+        cudaEvent_t e0 = pool->event(si, 0), e1 = pool->event(si, 1);  // (the factorisation's events of this lane are done with)
+        if (!e0 || !e1 || cudaEventRecord(e0, u.st) != cudaSuccess || cudaStreamWaitEvent(side, e0, 0) != cudaSuccess) {
+            set_error("mll_grad: fork failed");
+            return BOBE_E_CUDA;
+        }
         SolveArgs sa{kind, X, u.ls_s, u.kv_s, d, noise, u.xs};
-        return launch_solve_vectors(u.st, u.fb, sa, y, n, npad, (int)u.Rs, u.zws, u.alpha, u.logdet, u.quad, info + u.r0);
+        const int32_t rc = launch_solve_vectors(side, u.fb, sa, y, n, npad, (int)u.Rs, u.zws, u.alpha, u.logdet, u.quad, info + u.r0);
+        const int32_t rk = launch_kinv(u.st, u.fb, npad, (int)u.Rs);
+        if (cudaEventRecord(e1, side) != cudaSuccess || cudaStreamWaitEvent(u.st, e1, 0) != cudaSuccess) {
+            set_error("mll_grad: join failed");
+            return BOBE_E_CUDA;
+        }
+        return rc != BOBE_OK ? rc : rk;
     });
-    each([&](Sub& u, int) -> int32_t { return launch_kinv(u.st, u.fb, npad, (int)u.Rs); });
     each([&](Sub& u, int) -> int32_t {
         int smem = (int)((2 * d * GLD + 2 * GT + 8 * (d + 1)) * sizeof(double));
         dim3 grid((unsigned)l.ntile_pairs, (unsigned)u.Rs);
