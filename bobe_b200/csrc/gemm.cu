@@ -165,7 +165,9 @@ int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& a, int batch) {
     const int64_t nodes = a.node_count > 0 ? a.node_count : 1;
     int64_t tiles64 = (int64_t)((a.M + 63) / 64) * ((a.N + 63) / 64) * batch * nodes;
     if (a.flags & GEMM_C_LOWER) tiles64 = tiles64 / 2 + ((a.M < a.N ? a.M : a.N) + 63) / 64 * batch;
-    if (tile == 1 && !forced && tiles64 <= tiny_max && a.M > 32)
+    // ... and every 128-column product (measured at batches of 8 / 16 / 64 matrices: profiles/r02/gemm_bench*.txt)
+    static const int64_t tiny_narrow = env_int("BOBE_TINY_NARROW", 1);
+    if (tile == 1 && !forced && (tiles64 <= tiny_max || (tiny_narrow && a.N <= 128)) && a.M > 32)
         rc = mode == TRI_LOWER ? go(CfgTiny{}, M1{}) : (mode == TRI_UPPER ? go(CfgTiny{}, M2{}) : go(CfgTiny{}, M0{}));
     else if (tile == 1)
         rc = mode == TRI_LOWER ? go(CfgSmall{}, M1{}) : (mode == TRI_UPPER ? go(CfgSmall{}, M2{}) : go(CfgSmall{}, M0{}));

@@ -553,7 +553,7 @@ using CfgSmall = TileCfg<64, 64, 2, 2, 3, 16, true, 4>;  // 128 threads, warp ti
 using CfgMed = TileCfg<128, 64, 4, 2, 4, 16, true, 2>; // 256 threads, warp tile 32x32, 96 KB smem: two CTAs per SM
 // Launches whose 64x64 tiles cannot give every SM a tile (the k = 128 products on the critical path of the tile-column
 // factorisation: one 64x64x128 tile is 4.2 us of ONE SM's tensor pipe): half-height tiles, twice the CTAs
-using CfgTiny = TileCfg<32, 64, 1, 4, 3, 16, true, 4>;  // 128 threads, warp tile 32x16, 36 KB smem
+using CfgTiny = TileCfg<32, 64, 1, 4, 3, 16, true, 6>;  // 128 threads, warp tile 32x16, 36 KB smem: six CTAs per SM
 
 int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& args, int batch);
 

@@ -618,6 +618,27 @@ def test_factorisation_is_batch_invariant_and_deterministic():
         assert torch.equal(a[2], b[0])
 
 
+def test_graph_replay_of_repeated_mll_calls_is_bitwise_the_plain_call():
+    """bobe_mll_grad_batched replays a captured CUDA graph once a call repeats with the same arguments (the optimiser
+    loops: GP.neg_mll_and_grad_batched keeps its staging buffers, so the device pointers repeat).  The first two calls
+    run plainly, the third captures, later ones replay: all must give bitwise the same numbers, also when the
+    PARAMETER VALUES change between replays (the graph holds pointers, not values)."""
+    ref, X, y, _, x0, _, _ = make_case("M_matern_n300_d3")
+    gp = make_gp(ref)
+    first = gp.neg_mll_and_grad_batched(x0)
+    for rep in range(6):
+        again = gp.neg_mll_and_grad_batched(x0)
+        assert np.array_equal(first[0], again[0]) and np.array_equal(first[1], again[1]), rep
+    x1 = x0 + 0.05
+    v1, g1 = gp.neg_mll_and_grad_batched(x1)  # replay with other values in the same buffers
+    for r in range(x1.shape[0]):
+        vr, gr = ref.neg_mll_and_grad(x1[r])
+        assert abs(v1[r] - vr) <= TOL_MLL * max(abs(vr), X.shape[0])
+        check_grad(g1[r], gr, f"restart {r}")
+    back = gp.neg_mll_and_grad_batched(x0)
+    assert np.array_equal(first[0], back[0]) and np.array_equal(first[1], back[1])
+
+
 def test_nan_query_propagates():
     """A NaN query coordinate gives NaN kernel rows in the reference (jnp.exp(NaN)), hence a NaN mean; predict_var
     propagates the NaN through clip (BOBE/gp.py:465), predict_single floors it (BOBE/gp.py:487-488)."""
