@@ -242,13 +242,13 @@ extern "C" int64_t bobe_mll_grad_workspace_bytes(int64_t n, int64_t d, int64_t R
     return mll_layout(n, d, R).total * 8 + 256;
 }
 
-// One call is several hundred launches and event operations on up to sixteen streams: 1 - 2 ms of host time, more than
-// a third of the device time of a small batch, and exposed whenever the caller needs the result before it can issue the
-// next call (every optimiser step).  A call whose arguments (all pointers, sizes and scalars) repeat is therefore captured
-// ONCE into a CUDA graph -- the same launches, dependencies and programmatic-launch edges -- and replayed from then on:
-// one graph launch instead of the enqueue.  A key is captured at its third sighting (capture + instantiate cost several
-// plain enqueues; a caller whose output pointers cycle through a few allocator blocks must not pay that every call).
-// BOBE_MLL_GRAPH=0 turns this off; a caller that is itself capturing (XLA command buffers, torch.cuda.graph) is left alone.
+// Optional (BOBE_MLL_GRAPH=1, default off): a call whose arguments (all pointers, sizes and scalars) repeat is captured
+// into a CUDA graph at its third sighting -- the same launches, dependencies and programmatic-launch edges -- and
+// replayed from then on: one graph launch (~0.05 ms of host time) instead of 1 - 2 ms of enqueueing several hundred
+// launches and event operations on up to twelve streams.  Measured (profiles/r02/README.md): the enqueue already overlaps
+// the device work, so the round does not get shorter (8 restarts: 3.47 vs 3.49 ms call + fetch), while capture +
+// instantiation cost ~10 ms per key -- a loss for optimisers whose batch shrinks as restarts retire.  It pays only where
+// the host thread is the scarce resource.  A caller that is itself capturing is left alone.
 namespace {
 struct GraphKey {
     const void *X, *y, *lp, *val, *grad, *info, *ws;
@@ -284,7 +284,7 @@ extern "C" int32_t bobe_mll_grad_batched(void* stream_, int32_t kind, const doub
                                          double fixed_kv, double noise, double* val, double* grad, int32_t* info,
                                          void* ws, int64_t ws_bytes) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    static const bool graphs = env_int("BOBE_MLL_GRAPH", 1) != 0;
+    static const bool graphs = env_int("BOBE_MLL_GRAPH", 0) != 0;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     int dev = 0;
     if (!graphs || cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone ||

@@ -618,11 +618,11 @@ def test_factorisation_is_batch_invariant_and_deterministic():
         assert torch.equal(a[2], b[0])
 
 
-def test_graph_replay_of_repeated_mll_calls_is_bitwise_the_plain_call():
-    """bobe_mll_grad_batched replays a captured CUDA graph once a call repeats with the same arguments (the optimiser
-    loops: GP.neg_mll_and_grad_batched keeps its staging buffers, so the device pointers repeat).  The first two calls
-    run plainly, the third captures, later ones replay: all must give bitwise the same numbers, also when the
-    PARAMETER VALUES change between replays (the graph holds pointers, not values)."""
+def test_repeated_mll_calls_are_bitwise_reproducible():
+    """The optimiser loops call GP.neg_mll_and_grad_batched over and over through persistent staging buffers (the same
+    device pointers every time).  Every repetition must give bitwise the same numbers, also when other parameter values
+    pass through the same buffers in between.  With BOBE_MLL_GRAPH=1 the third call captures a CUDA graph and the later
+    ones replay it: the same assertions then cover the replay (the graph holds pointers, not values)."""
     ref, X, y, _, x0, _, _ = make_case("M_matern_n300_d3")
     gp = make_gp(ref)
     first = gp.neg_mll_and_grad_batched(x0)
