@@ -609,6 +609,21 @@ def test_factorisation_is_batch_invariant_and_deterministic():
     for lo, hi in [(0, 1), (1, 3), (3, 10), (10, 27), (27, 40)]:  # 1, 2, 7, 17, 13 matrices: every stream configuration
         part = [t.cpu().numpy() for t in ops.mll_grad_batched("rbf", gp._X_dev, gp._y_dev, T(lp[lo:hi]), True, 1.0, float(ref.noise))]
         assert np.array_equal(part[0], full[0][lo:hi]) and np.array_equal(part[1], full[1][lo:hi]), (lo, hi)
+    # a shape whose last tile column is 64 wide (npad = 320) and whose inverse tree is ragged, in both modes:
+    # 20 restarts -> two sub-batches of 10 (single stream) against 3 of the same rows (four-stream look-ahead)
+    ref3, X3, y3, *_ = make_case("M_matern_n300_d3")
+    gp3 = make_gp(ref3)
+    gp3._ensure_factor()
+    lp3 = O.synthetic_restarts(ref3, 20)
+    lp3[:, :3] = np.clip(lp3[:, :3], np.log(0.2), None)
+    f3 = [t.cpu().numpy() for t in ops.mll_grad_batched("matern", gp3._X_dev, gp3._y_dev, T(lp3), True, 1.0, float(ref3.noise))]
+    p3 = [t.cpu().numpy() for t in ops.mll_grad_batched("matern", gp3._X_dev, gp3._y_dev, T(lp3[4:7]), True, 1.0, float(ref3.noise))]
+    assert not np.isnan(f3[0]).any() and np.array_equal(p3[0], f3[0][4:7]) and np.array_equal(p3[1], f3[1][4:7])
+    for r in (0, 5, 19):  # and the values themselves against the oracle
+        vr, gr = ref3.neg_mll_and_grad(lp3[r])
+        pl, pg = ref3.log_prior_and_grad(lp3[r])
+        assert abs((-f3[0][r] - pl) - vr) <= TOL_MLL * max(abs(vr), 300)
+        check_grad(-f3[1][r] - pg, gr, f"n=300 restart {r}")
     # the factor handed to the caller, alone and as part of a batch
     ls = np.exp(lp[:5, :27])
     kv = np.exp(lp[:5, 27])
