@@ -68,6 +68,12 @@ def test_golden_parity(name):
               f" | cuda vs oracle: mean {mixed_err(ms, gold['mean_std'], 1.0):.1e}")
         # ... i.e. within the tolerance, or within twice the float64 oracle's own distance from the exact value
         assert e_cuda < max(TOL_MEAN, 2 * e_orac) and m_cuda < max(TOL_MLL, 2 * m_orac)
+        # the posterior variance against its exact value (kk - |L^-1 k*|^2 before the floor, standardised units)
+        tv = np.maximum(gold["truth_var_raw"], 1e-12)
+        v_cuda = mixed_err(vs.ravel()[:32], tv, 1.0)
+        v_orac = mixed_err(gold["var_std"][:32], tv, 1.0)
+        print(f"[{name}] vs exact: var cuda {v_cuda:.1e} oracle {v_orac:.1e}")
+        assert v_cuda < max(TOL_VAR, 2 * v_orac)
         assert mixed_err(ms, gold["mean_std"], 1.0) < 3 * TOL_MEAN  # and never far from the oracle either
     else:
         assert mixed_err(ms, gold["mean_std"], 1.0) < TOL_MEAN

@@ -263,6 +263,27 @@ def test_priors_logprob_values():
     assert math.isclose(float(O.uniform_logprob(0.3, 0.01, 5)), -math.log(4.99))
 
 
+@pytest.mark.parametrize("name", ["A_banana_rbf_n100_d2", "M_matern_n300_d3", "B_rbf_n500_d2", "B_rbf_n500_d4", "B_rbf_n500_d6"])
+def test_oracle_against_the_exact_values_in_the_fixtures(name):
+    """The float64 oracle against the 60-digit (mpmath) values stored beside its outputs: posterior mean, posterior variance
+    and the log marginal likelihood of EVERY restart row.  These gaps are the oracle's own rounding noise (SURVEY.md fact 5);
+    the GPU tests hold the CUDA path to max(tolerance, 2 x this gap) against the same exact values."""
+    gold = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    from oracle.gen_golden import make_case
+    gp, X, y, Xq, x0, mc, cand = make_case(name)
+    n = X.shape[0]
+    e_mean = mixed_err(gold["mean_std"][:32], gold["truth_mean_std"], 1.0)
+    e_var = mixed_err(gold["var_std"][:32], np.maximum(gold["truth_var_raw"], 1e-12), 1.0)
+    gaps = []
+    for r in range(x0.shape[0]):
+        pl = gp.log_prior_and_grad(x0[r])[0]
+        tr = float(gold["truth_mll_rows"][r])
+        gaps.append(abs((-gold["neg_mll"][r] - pl) - tr) / max(abs(tr), n))
+    print(f"\n[{name}] oracle vs exact: mean {e_mean:.1e} var {e_var:.1e} log-ML rows {[f'{g:.1e}' for g in gaps]}")
+    assert e_mean < 1e-9 and e_var < 1e-7 and max(gaps) < 5e-9
+    assert abs(float(gold["truth_mll_rows"][0]) - float(gold["truth_mll"])) <= 1e-12 * n  # row 0 = the current hyper-parameters
+
+
 @pytest.mark.parametrize("name", ["A_banana_rbf_n100_d2", "M_matern_n300_d3", "B_rbf_n500_d4"])
 def test_golden_fixtures_are_reproduced_by_the_oracle(name):
     from oracle.gen_golden import make_case
