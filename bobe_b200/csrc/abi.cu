@@ -258,7 +258,7 @@ extern "C" int32_t bobe_factorize(void* stream_, int32_t kind, const double* X, 
         return BOBE_E_ARG;
     }
     const int npad = (int)npad_of(n);
-    FactorBuffers fb{l.KB, L ? L : l.L, l.Lt, Linv ? Linv : l.Linv, l.U, l.Q, l.diag, l.stat, (int*)(l.stat + 2 * batch), 0, 0};
+    FactorBuffers fb{l.KB, L ? L : l.L, l.Lt, Linv ? Linv : l.Linv, l.U, l.Q, l.diag, l.stat, (int*)(l.stat + 2 * batch), 0, 0, factor_live_rows(n)};
     if (int32_t rc = launch_prescale(stream, X, n, d, ls, d, l.xs, npad, d * (int64_t)npad, (int)batch)) return rc;
     KmatArgs ka{};
     ka.xa = X; ka.xb = X; ka.ls = ls; ka.kv_ptr = kv; ka.out = fb.KB;
@@ -303,7 +303,7 @@ extern "C" int32_t bobe_cholesky_batched(void* stream_, const double* K, int64_t
         return BOBE_E_ARG;
     }
     const int npad = (int)npad_of(n);
-    FactorBuffers fb{l.KB, L ? L : l.L, l.Lt, Linv ? Linv : l.Linv, l.U, l.Q, l.diag, l.stat, (int*)(l.stat + 2 * batch), 0, 0};
+    FactorBuffers fb{l.KB, L ? L : l.L, l.Lt, Linv ? Linv : l.Linv, l.U, l.Q, l.diag, l.stat, (int*)(l.stat + 2 * batch), 0, 0, factor_live_rows(n)};
     if (int32_t rc = launch_pad_k(stream, K, ldk, n * ldk, (int)n, npad, (int)batch, fb.KB)) return rc;
     {
         StreamPool* pool = stream_pool();

@@ -24,6 +24,15 @@ __global__ void init_stat_kernel(double* dstat, int* gate, int batch, int force)
     }
 }
 
+int factor_live_rows(int64_t n) {
+    static const bool live = env_int("BOBE_FACTOR_LIVE", 1) != 0;  // 0: every product on the padded size (round-1 behaviour)
+    static const int gran = (env_int("BOBE_TILE", 0) > 2 || env_int("BOBE_GEMM_TMA", 0) != 0) ? 32 : 16;
+    const int64_t npad = npad_of(n);
+    if (!live) return (int)npad;
+    const int64_t nl = round_up(n, gran);
+    return (int)(nl < npad ? nl : npad);
+}
+
 int64_t factor_q_elems(int64_t npad) {  // >= npad^2 / 4 (inverse tree, phase 2) and >= 128 npad (panel correction)
     int64_t m = ((npad / NB + 1) / 2) * NB;
     return m * m > 128 * npad ? m * m : 128 * npad;
@@ -201,7 +210,9 @@ int32_t launch_kinv(cudaStream_t stream, const FactorBuffers& fb, int npad, int 
     g.A = fb.U; g.Bt = fb.U; g.C = fb.KB; g.Ct = nullptr;
     g.lda = g.ldb = g.ldc = g.ldct = npad;
     g.strideA = g.strideB = g.strideC = g.strideCt = (int64_t)npad * npad;
-    g.M = g.N = g.K = npad; g.alpha = 1.0;
+    static const int64_t scheme = env_int("BOBE_FACTOR", 1);
+    const int nl = (scheme != 0 && fb.n_live > 0 && fb.n_live <= npad) ? fb.n_live : npad;  // rows >= n_live of K^-1 are never read
+    g.M = g.N = g.K = nl; g.alpha = 1.0;
     g.flags = GEMM_A_UPPER | GEMM_B_UPPER | GEMM_C_LOWER;
     return launch_gemm_nt(stream, g, batch);
 }

@@ -127,6 +127,18 @@ cudaEvent_t StreamPool::event(int lane, int idx) {
 namespace {
 
 constexpr int TW = 128;  // tile-column width
+inline int off_last(int npad) { return ((npad + TW - 1) / TW - 1) * TW; }  // first column of the last tile column
+
+// L[r][c] = Linv[r][c] = 0 and U[c][r] = 0 for the padded rows r in [nl, npad) and the columns c < c_end left of the last
+// diagonal tile (which the leaf writes in full, identity part included).  grid = (ceil(c_end / 256), npad - nl, batch).
+__global__ void __launch_bounds__(256) pad_rows_zero_kernel(double* L, double* Linv, double* U, int npad, int nl, int c_end) {
+    const int c = blockIdx.x * 256 + threadIdx.x, r = nl + blockIdx.y;
+    if (c >= c_end) return;
+    const int64_t z = (int64_t)blockIdx.z * npad * npad;
+    L[z + (int64_t)r * npad + c] = 0.0;
+    Linv[z + (int64_t)r * npad + c] = 0.0;
+    U[z + (int64_t)c * npad + r] = 0.0;
+}
 
 struct Tiled {
     const FactorExec& ex;
@@ -135,6 +147,7 @@ struct Tiled {
     int64_t mstride, qstride;
     int32_t rc = BOBE_OK;
     int T;
+    int nl = 0;                      // live rows / columns (fb.n_live): products stop there, the padding is filled, not computed
     bool two;                        // look-ahead mode: chain / rest-of-column / trailing products / inverse on four streams
     int inv_waited = -1;             // highest column the inverse stream already waited for
     bool inv_used = false;
@@ -145,6 +158,8 @@ struct Tiled {
 
     int off(int j) const { return j * TW; }
     int width(int j) const { return npad - off(j) < TW ? npad - off(j) : TW; }
+    int live(int o) const { return nl > o ? nl - o : 0; }                      // live rows / columns from offset o on
+    int wlive(int j) const { return live(off(j)) < width(j) ? live(off(j)) : width(j); }  // live width of tile column j
 
     // events of lane ex.lane:  [j] top tile of panel j done (critical stream);  [T + j] leaf j done;
     // [2T + j] column j complete (mid stream);  [3T + j] rows of tile j+1 of column j updated (mid stream);
@@ -267,7 +282,7 @@ struct Tiled {
         return fb.Lt + o;
     }
     void node_p1(cudaStream_t st, int m, int o) {  // P^T = U11 L21^T
-        const int m2 = npad - o - m < m ? npad - o - m : m;
+        const int m2 = live(o + m) < m ? live(o + m) : m;
         if (m2 <= 0) return;
         GemmArgs g = base();
         g.A = fb.U + (int64_t)o * npad + o; g.Bt = fb.L + (int64_t)(o + m) * npad + o; g.C = pbuf(m); g.ldc = m2;
@@ -275,7 +290,7 @@ struct Tiled {
         gemm(st, g);
     }
     void node_p2(cudaStream_t st, int m, int o) {  // X21 = -X22 P
-        const int m2 = npad - o - m < m ? npad - o - m : m;
+        const int m2 = live(o + m) < m ? live(o + m) : m;
         if (m2 <= 0) return;
         GemmArgs g = base();
         g.A = fb.Linv + (int64_t)(o + m) * (npad + 1); g.Bt = pbuf(m); g.ldb = m2;
@@ -299,24 +314,24 @@ struct Tiled {
             return ex.inv;
         };
         // X21 of every node whose right half ends here (at a node boundary, or at the end of the matrix), small to large
-        for (int m = TW; m < npad; m *= 2) {
+        for (int m = TW; m < nl; m *= 2) {
             const int w = m / TW;  // tiles per half
             int t;
             if (done == T)
-                t = (npad - 1) / (2 * m);
+                t = (nl - 1) / (2 * m);
             else if (done % (2 * w) == 0)
                 t = done / (2 * w) - 1;
             else
                 continue;
             const int o = 2 * m * t;
-            if (o + m < npad && o + m < done * TW) node_p2(stream(), m, o);
+            if (o + m < nl && o + m < done * TW) node_p2(stream(), m, o);
         }
         // P^T of the node whose left half ends here
         if (done < T) {
             int w = 1;
             while (done % (2 * w) == 0) w *= 2;  // largest power of two dividing `done`
             const int m = w * TW, t = (done / w - 1) / 2, o = 2 * m * t;
-            if ((done / w) % 2 == 1 && o + m == done * TW && o + m < npad) node_p1(stream(), m, o);
+            if ((done / w) % 2 == 1 && o + m == done * TW && o + m < nl) node_p1(stream(), m, o);
         }
     }
 
@@ -329,8 +344,8 @@ struct Tiled {
     //              update of the rows below;  [after the leaf]  panel rows below tile j+1
     void step(int j, int PW) {
         const int s = (j / PW) * PW;  // first tile column of this outer panel
-        const int o = off(j), w = width(j), below = npad - o - w;
-        const int top = below < TW ? below : TW;  // rows of tile j+1
+        const int o = off(j), w = width(j), wl = wlive(j), below = live(o + w);
+        const int top = below < TW ? below : TW;  // (live) rows of tile j+1
         needs_col(ex.crit, crit_waited, j);
         if (below > 0) needs_col(s_mid(), mid_waited, j);
         if (j > 0) {
@@ -341,15 +356,15 @@ struct Tiled {
             if (j == s && j >= 2) wait(ex.crit, ev_col(j - 2));
             if (!two) {
                 // single stream: the three row ranges in ONE launch (same arithmetic per element; fewer, larger launches)
-                update(ex.crit, o, w + below, o, w, k0, k1);
+                update(ex.crit, o, wl + below, o, wl, k0, k1);
             } else {
-                update(ex.crit, o, w, o, w, k0, k1);
+                update(ex.crit, o, wl, o, wl, k0, k1);
             }
             if (two && below > 0) {
                 wait(s_mid(), ev_top(j - 1));  // the Bt operand L[tile j, k0:k1) includes the top of panel j-1
-                update(s_mid(), o + w, top, o, w, k0, k1);
+                update(s_mid(), o + w, top, o, wl, k0, k1);
                 record(ev_u1(j), s_mid());
-                update(s_mid(), o + w + top, below - top, o, w, k0, k1);
+                update(s_mid(), o + w + top, below - top, o, wl, k0, k1);
             }
         }
         // (the critical stream's panel below reads rows the mid stream's U1 updated; that finished about when the diagonal
@@ -387,13 +402,13 @@ struct Tiled {
             // bound by the throughput of these products, and the narrow pieces run less efficiently than the square.)
             if (j + 2 < T) {
                 bulk_needs_col(j);
-                update(s_bulk(), off(j + 2), npad - off(j + 2), off(j + 2), npad - off(j + 2), off(s), off(j + 1));
+                update(s_bulk(), off(j + 2), live(off(j + 2)), off(j + 2), live(off(j + 2)), off(s), off(j + 1));
                 bulk_wrote(j + 2, T);
             }
         } else if (j + 2 < T && j + 2 < s + PW) {
             // a1 of column j+2: the in-panel columns s .. j (column j+1 follows as a2)
             bulk_needs_col(j);
-            update(s_bulk(), off(j + 2), npad - off(j + 2), off(j + 2), width(j + 2), off(s), off(j + 1));
+            update(s_bulk(), off(j + 2), live(off(j + 2)), off(j + 2), wlive(j + 2), off(s), off(j + 1));
             bulk_wrote(j + 2, j + 3);
         }
     }
@@ -410,17 +425,17 @@ struct Tiled {
 
     void phase2() {
         if (two) return;  // done eagerly
-        for (int m = TW; m < npad && rc == BOBE_OK; m *= 2) {
-            const int nodes = (npad + 2 * m - 1) / (2 * m);
+        for (int m = TW; m < nl && rc == BOBE_OK; m *= 2) {
+            const int nodes = (nl + 2 * m - 1) / (2 * m);
             GemmArgs g = base();
             g.A = fb.U; g.Bt = fb.L; g.C = fb.Q; g.strideC = qstride;
             g.M = m; g.N = m; g.K = m; g.flags = GEMM_A_UPPER;
-            g.node_count = nodes; g.node_m = m; g.node_total = npad; g.node_kind = 1;
+            g.node_count = nodes; g.node_m = m; g.node_total = nl; g.node_kind = 1;
             gemm(ex.crit, g);
             g = base();
             g.A = fb.Linv; g.Bt = fb.Q; g.strideB = qstride; g.C = fb.Linv; g.Ct = fb.U;
             g.M = m; g.N = m; g.K = m; g.alpha = -1.0; g.flags = GEMM_A_LOWER;
-            g.node_count = nodes; g.node_m = m; g.node_total = npad; g.node_kind = 2;
+            g.node_count = nodes; g.node_m = m; g.node_total = nl; g.node_kind = 2;
             gemm(ex.crit, g);
         }
     }
@@ -461,10 +476,20 @@ TiledFactor* tiled_begin(const FactorExec& ex, const FactorBuffers& fb, int npad
     TiledFactor* f = new TiledFactor(ex, fb, npad, batch);
     Tiled& t = f->t;
     t.T = (npad + TW - 1) / TW;
+    t.nl = (fb.n_live > 0 && fb.n_live <= npad && fb.n_live > npad - NB && fb.n_live % 16 == 0) ? fb.n_live : npad;
     t.two = ex.bulk != nullptr && ex.mid != nullptr && ex.inv != nullptr && ex.pool != nullptr && t.T > 2 && fb.Lt != nullptr;
     t.last_writer.assign(t.T, -1);
     if (t.two) {  // make sure every event exists before the first record (creation failure -> single-stream fallback)
         if (!ex.pool->event(ex.lane, 7 * t.T + 5)) t.two = false;
+    }
+    if (t.nl < npad && t.T > 1) {
+        // the padded rows of L / Linv (columns of U) left of the last diagonal tile: no product computes them any more
+        pad_rows_zero_kernel<<<dim3((unsigned)((off_last(npad) + 255) / 256), npad - t.nl, batch), 256, 0, ex.crit>>>(
+            fb.L, fb.Linv, fb.U, npad, t.nl, off_last(npad));
+        if ((*rc_out = check_launch("pad_rows_zero_kernel")) != BOBE_OK) {
+            delete f;
+            return nullptr;
+        }
     }
     if (fb.zero_band == 0 && npad > NB) {
         // buffers handed to the caller: the whole other triangle must read as zero.  Nothing in the factorisation reads

@@ -92,8 +92,10 @@ bool pdl_enabled(int64_t ctas) {
 
 int32_t launch_gemm_nt(cudaStream_t stream, const GemmArgs& a, int batch) {
     if (a.M <= 0 || a.N <= 0 || batch <= 0) return BOBE_OK;
-    if ((a.K % 32) || (a.N % 2) || (a.lda % 2) || (a.ldb % 2) || (a.ldc % 2)) {
-        set_error("gemm_nt: K must be a multiple of 32 and N/ld even (M=%d N=%d K=%d)", a.M, a.N, a.K);
+    static const int64_t forced_tile = env_int("BOBE_TILE", 0);
+    const int kgran = (forced_tile > 2 || env_int("BOBE_GEMM_TMA", 0) != 0) ? 32 : 16;  // k-tile width of the tiles in use
+    if ((a.K % kgran) || (a.N % 2) || (a.lda % 2) || (a.ldb % 2) || (a.ldc % 2)) {
+        set_error("gemm_nt: K must be a multiple of %d and N/ld even (M=%d N=%d K=%d)", kgran, a.M, a.N, a.K);
         return BOBE_E_ARG;
     }
     // Tile choice (measured, profiles/r01/README.md "tile choice"): 64x64 tiles with FOUR CTAs per SM beat the 128x128 /

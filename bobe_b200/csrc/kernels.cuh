@@ -63,7 +63,12 @@ struct FactorBuffers {
                    // ratio), row j + 1 = snapshot after tile column j (factor_tiled.cuh)
     int force_refine;
     int zero_band;  // 0: zero the whole other triangle (L / Linv handed to the caller); 2: internal use only
+    // rows / columns >= n_live (a multiple of 16, n <= n_live <= npad; 0: npad) are pure padding -- identity on the diagonal,
+    // zero elsewhere: the tile-column scheme restricts every product to the live part ((npad / n)^3 = 7.4 % of the work at
+    // n = 2000) and fills the padded rows of L / Linv / U with zeros instead of computing them
+    int n_live = 0;
 };
+int factor_live_rows(int64_t n);  // n rounded up to the k granularity of the GEMM tiles in use (16; 32 with 128-wide tiles)
 int64_t factor_q_elems(int64_t npad);
 inline int64_t factor_gate_rows(int64_t npad) { return (npad + 127) / 128 + 2; }
 

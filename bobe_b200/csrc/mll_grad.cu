@@ -427,7 +427,7 @@ int32_t mll_grad_enqueue(cudaStream_t stream, int32_t kind, const double* X, con
         if (forked) cudaStreamWaitEvent(u.st, pool->fork, 0);
         u.fb = FactorBuffers{w + l.off_KB + r0 * m2, w + l.off_L + r0 * m2, w + l.off_Lt + r0 * m2,
                              w + l.off_Linv + r0 * m2, w + l.off_U + r0 * m2, w + l.off_Q + r0 * qel,
-                             w + l.off_diag + r0 * npad, w + l.off_stat + 2 * r0, (int*)(w + l.off_stat + 2 * R) + r0 * factor_gate_rows(npad), 0, 2};
+                             w + l.off_diag + r0 * npad, w + l.off_stat + 2 * r0, (int*)(w + l.off_stat + 2 * R) + r0 * factor_gate_rows(npad), 0, 2, factor_live_rows(n)};
         u.zws = w + l.off_z + (3 * r0 + si) * npad;  // each sub-batch: own padded y + 3 vectors per restart
         u.alpha = w + l.off_alpha + r0 * npad;
         u.logdet = w + l.off_logdet + r0;
