@@ -64,6 +64,12 @@ class SurrogatePool:
         self._fn = fn_batched
         self._tls = threading.local()
         self._ev: Optional[LockstepEvaluator] = None
+        self._threads: List[threading.Thread] = []
+        self._go: List[threading.Lock] = []
+        self._job = None
+        self._mu = threading.Lock()
+        self._done = threading.Lock()
+        self._done.acquire()
         self.n_device_calls = 0
         self.n_points = 0
 
@@ -85,37 +91,67 @@ class SurrogatePool:
     __call__ = loglike
 
     # ---- pool protocol ----------------------------------------------------------------------------------------
+    def _worker(self, i: int):
+        """Persistent task thread ``i`` (started on the first ``map``; 64 thread starts cost more than a whole round)."""
+        self._tls.wid = None
+        go = self._go[i]
+        while True:
+            go.acquire()
+            job = self._job
+            if job is None:
+                return
+            fn, items, s, out, errors, ev, state = job
+            self._tls.wid = i
+            try:
+                out[s + i] = fn(items[s + i])
+            except BaseException as e:  # noqa: BLE001 -- re-raised on the caller's thread by map()
+                errors.append(e)
+            finally:
+                self._tls.wid = None
+                ev.retire(i)
+                with self._mu:
+                    state[0] -= 1
+                    last = state[0] == 0
+                if last:
+                    self._done.release()
+
+    def _ensure_threads(self, count: int):
+        while len(self._threads) < count:
+            i = len(self._threads)
+            g = threading.Lock()
+            g.acquire()
+            self._go.append(g)
+            t = threading.Thread(target=self._worker, args=(i,), daemon=True, name=f"bobe-surrogate-{i}")
+            self._threads.append(t)
+            t.start()
+
     def map(self, fn: Callable, iterable: Iterable) -> List:
         """Run ``fn(item)`` for every item, ``size`` at a time on threads whose ``loglike`` calls are fused."""
         items = list(iterable)
         out: List = [None] * len(items)
         for s in range(0, len(items), self.size):
-            group = items[s:s + self.size]
-            ev = LockstepEvaluator(self._batched, len(group))
-            self._ev = ev
+            count = min(self.size, len(items) - s)
+            self._ensure_threads(count)
+            ev = LockstepEvaluator(self._batched, count)
             errors: List[BaseException] = []
-
-            def work(i, item):
-                self._tls.wid = i
-                try:
-                    out[s + i] = fn(item)
-                except BaseException as e:  # noqa: BLE001 -- re-raised on the caller's thread below
-                    errors.append(e)
-                finally:
-                    self._tls.wid = None
-                    ev.retire(i)
-            threads = [threading.Thread(target=work, args=(i, it), daemon=True) for i, it in enumerate(group)]
-            for t in threads:
-                t.start()
-            for t in threads:
-                t.join()
+            self._ev = ev
+            self._job = (fn, items, s, out, errors, ev, [count])
+            for i in range(count):
+                self._go[i].release()
+            self._done.acquire()
             self._ev = None
             if errors:
                 raise errors[0]
         return out
 
     def close(self):
-        pass
+        """Stop the task threads (the pool can be used again afterwards: they restart on the next ``map``)."""
+        self._job = None
+        for g in self._go:
+            g.release()
+        for t in self._threads:
+            t.join(timeout=1.0)
+        self._threads, self._go = [], []
 
     def join(self):
         pass
@@ -124,4 +160,5 @@ class SurrogatePool:
         return self
 
     def __exit__(self, *exc):
+        self.close()
         return False

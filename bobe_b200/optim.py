@@ -57,23 +57,32 @@ def _fd_value_and_grad(fun: Callable, h: float = 1e-6) -> Callable:
 
 
 class LockstepEvaluator:
-    """Gathers one pending evaluation per live worker thread into a single batched call."""
+    """Gathers one pending evaluation per live worker thread into a single batched call.
+
+    The rendezvous costs one short critical section per arrival and one private gate (a ``threading.Lock`` used as a binary
+    semaphore) per worker: the LAST arrival evaluates the batch outside the shared lock and opens the other workers' gates,
+    so a round of W workers is W uncontended futex wake-ups instead of W re-acquisitions of one condition variable.
+    """
 
     def __init__(self, batched_fn: Callable[[np.ndarray], Tuple[np.ndarray, np.ndarray]], n_workers: int):
         self.fn = batched_fn
-        self.cv = threading.Condition()
+        self.mu = threading.Lock()
         self.live = n_workers
-        self.pending = {}
-        self.results = {}
+        self.gates = [threading.Lock() for _ in range(n_workers)]
+        for g in self.gates:
+            g.acquire()
+        self.x = [None] * n_workers
+        self.results = [None] * n_workers
+        self.pending = []
         self.generation = 0
         self.n_batched_calls = 0
         self.error = None
 
-    def _flush_locked(self):
-        keys = sorted(self.pending)
-        xs = np.stack([self.pending[k] for k in keys])
+    def _flush(self, keys, me):
+        """Evaluate the pending set (called by exactly one thread, with every other live worker parked on its gate)."""
+        keys.sort()
         try:
-            vals, grads = self.fn(xs)
+            vals, grads = self.fn(np.stack([self.x[k] for k in keys]))
             vals, grads = np.asarray(vals, dtype=np.float64), np.asarray(grads, dtype=np.float64)
             for i, k in enumerate(keys):
                 self.results[k] = (float(vals[i]), grads[i].copy())
@@ -82,29 +91,35 @@ class LockstepEvaluator:
             for k in keys:
                 self.results[k] = e
         self.n_batched_calls += 1
-        self.pending.clear()
         self.generation += 1
-        self.cv.notify_all()
+        for k in keys:
+            if k != me:
+                self.gates[k].release()
 
     def evaluate(self, wid: int, x: np.ndarray):
-        with self.cv:
-            self.pending[wid] = np.array(x, dtype=np.float64)
+        self.x[wid] = np.array(x, dtype=np.float64)
+        keys = None
+        with self.mu:
+            self.pending.append(wid)
             if len(self.pending) == self.live:
-                self._flush_locked()
-            else:
-                gen = self.generation
-                while self.generation == gen:
-                    self.cv.wait()
-            r = self.results.pop(wid)
+                keys, self.pending = self.pending, []
+        if keys is not None:
+            self._flush(keys, wid)
+        else:
+            self.gates[wid].acquire()
+        r, self.results[wid] = self.results[wid], None
         if isinstance(r, Exception):
             raise r
         return r
 
     def retire(self, wid: int):
-        with self.cv:
+        keys = None
+        with self.mu:
             self.live -= 1
             if self.live > 0 and len(self.pending) == self.live:
-                self._flush_locked()
+                keys, self.pending = self.pending, []
+        if keys is not None:
+            self._flush(keys, -1)
 
 
 def optimize_scipy(fun: Callable = None, fun_args: Optional[Tuple] = (), fun_kwargs: Optional[dict] = {},
@@ -170,6 +185,10 @@ def optimize_scipy(fun: Callable = None, fun_args: Optional[Tuple] = (), fun_kwa
             results[i] = None
 
     if batched_value_and_grad is not None and len(x0) > 1:
+        # One lock-step group: splitting the restarts into groups that alternate on the device (so that one group's host-side
+        # L-BFGS-B bookkeeping hides behind the other's device round) was measured and is SLOWER -- restarts retire early, the
+        # average batch at 64 restarts is already ~31, and halving it costs more device efficiency than the overlap returns
+        # (profiles/r02/fit_lockstep_groups.txt: 2394 evals/s with one group, 1758 with two).
         ev = LockstepEvaluator(batched_value_and_grad, len(x0))
 
         def worker(i):

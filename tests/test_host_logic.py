@@ -291,6 +291,16 @@ def test_surrogate_pool_batches_concurrent_single_point_calls():
 
     with pytest.raises(RuntimeError, match="walk failed"):
         pool.map(boom, range(6))
+    # the task threads persist across map() calls, survive a failed map, and restart after close()
+    import threading
+    names = lambda: sorted(t.name for t in threading.enumerate() if t.name.startswith("bobe-surrogate-"))  # noqa: E731
+    assert len(names()) == 8
+    again = pool.map(walk, range(20))
+    assert [tuple(r[1]) for r in again] == [tuple(r[1]) for r in res] and names() == names()
+    pool.close()
+    assert names() == []
+    assert [r[2] for r in pool.map(walk, range(3))] == [r[2] for r in res[:3]] and len(names()) == 3
+    pool.close()
 
     class FakeGP:
         def predict_mean_batched(self, xs):
