@@ -434,6 +434,7 @@ extern "C" int64_t bobe_predict_workspace_bytes(int64_t n, int64_t d, int64_t M,
     if (mode & BOBE_PREDICT_VAR) {  // K* panel of up to KCHUNKS chunks + row-split partial sums of one chunk
         bytes += round_up(M < KCHUNKS * QCHUNK ? M : KCHUNKS * QCHUNK, 128) * npad_of(n) * 8;
         bytes += TRMM_MAX_SPLIT * round_up(M < QCHUNK ? M : QCHUNK, 128) * 8;
+        bytes += TRMM_COUNTERS * 4;  // tile counters of the shared-panel schedule
     }
     return bytes;
 }
@@ -464,6 +465,11 @@ extern "C" int32_t bobe_predict(void* stream_, int32_t kind, const double* X, in
     double* xs = align256(ws);  // (d, npad) = X^T / l, built once per call
     double* kstar = want_var ? xs + round_up(d * npad, 32) : nullptr;
     double* partial = want_var ? kstar + round_up(M < KCHUNKS * QCHUNK ? M : KCHUNKS * QCHUNK, 128) * npad : nullptr;
+    int* counters = want_var ? reinterpret_cast<int*>(partial + TRMM_MAX_SPLIT * round_up(M < QCHUNK ? M : QCHUNK, 128)) : nullptr;
+    if (counters && cudaMemsetAsync(counters, 0, TRMM_COUNTERS * sizeof(int), stream) != cudaSuccess) {
+        set_error("predict: cudaMemsetAsync failed");
+        return BOBE_E_CUDA;
+    }
     if (int32_t rc = launch_prescale(stream, X, n, d, ls, 0, xs, npad, 0, 1)) return rc;
     // mean only: no K* panel to bound, so the rows go out in launches as large as the grid allows (more CTAs per SM
     // for the kernel-matrix kernel); with the variance, the K* panel of KCHUNKS chunks is built by one launch and
@@ -472,7 +478,7 @@ extern "C" int32_t bobe_predict(void* stream_, int32_t kind, const double* X, in
     // kernel-matrix launch, so that the K* panels written by one launch are still in L2 when the next one reads them
     static const int64_t tsplit = std::max<int64_t>(1, std::min<int64_t>(TRMM_MAX_SPLIT, env_int("BOBE_TRMM_SPLIT", 1)));
     static const int64_t kchunks = std::max<int64_t>(1, std::min<int64_t>(KCHUNKS, env_int("BOBE_KCHUNKS", tsplit > 1 ? 1 : KCHUNKS)));
-    const int64_t qchunk = (148 / tsplit) * 128;
+    const int64_t qchunk = tsplit > 1 ? (148 / tsplit) * 128 : (int64_t)trmm_chunk_tiles((int)n, (int)npad) * 128;
     const int64_t step = want_var ? kchunks * qchunk : (int64_t)64 * 32768;
     for (int64_t q0 = 0; q0 < M; q0 += step) {
         int64_t rows = (M - q0 < step) ? M - q0 : step;
@@ -498,7 +504,7 @@ extern "C" int32_t bobe_predict(void* stream_, int32_t kind, const double* X, in
             for (int64_t c0 = 0; c0 < rows_pad; c0 += qchunk) {
                 const int64_t crows = (rows_pad - c0 < qchunk) ? rows_pad - c0 : qchunk;
                 if (int32_t rc = launch_trmm_sumsq(stream, Linv, (int)n, (int)npad, kstar + c0 * npad, npad, crows, q0 + c0, M,
-                                                   kv + noise, y_std * y_std, standardised, var_out, partial))
+                                                   kv + noise, y_std * y_std, standardised, var_out, partial, counters))
                     return rc;
             }
         }
@@ -722,6 +728,19 @@ extern "C" int32_t bobe_bench_trmm_sumsq(void* stream, const double* Linv, int64
         return BOBE_E_ARG;
     }
     const int64_t npad = npad_of(n);
+    // the scratch bobe_predict takes from its workspace (benchmark entry: allocated once, never freed), so that the launch
+    // timed here is the one the product makes
+    static double* scratch = nullptr;
+    static int* counters = nullptr;
+    if (!scratch && rows_pad <= QCHUNK) {
+        if (cudaMalloc(&scratch, 8 * QCHUNK * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&counters, TRMM_COUNTERS * sizeof(int)) != cudaSuccess ||
+            cudaMemset(counters, 0, TRMM_COUNTERS * sizeof(int)) != cudaSuccess) {
+            set_error("bench_trmm_sumsq: scratch allocation failed");
+            return BOBE_E_CUDA;
+        }
+    }
+    const bool fits = scratch && rows_pad <= QCHUNK && rows_pad >= 74 * 128;  // (below that the row split would engage)
     return launch_trmm_sumsq((cudaStream_t)stream, Linv, (int)n, (int)npad, kstar, npad, rows_pad, 0, rows_pad, kk, 1.0, 0,
-                             var_out);
+                             var_out, fits ? scratch : nullptr, fits ? counters : nullptr);
 }

@@ -221,9 +221,53 @@ __global__ void __launch_bounds__(256) trmm_finish_kernel(const double* __restri
     var_out[q] = var;
 }
 
+// Shared-panel schedule of trmm_sumsq_tma_kernel: S CTAs per K* panel.  The smallest S <= 4 for which the panels in flight
+// (148 / S panels of 128 x npad doubles) fit the L2 budget AND the row blocks deal out evenly; 1 = every CTA its own panel.
+// BOBE_TRMM_SHARE: 1 = off (default: the schedule is 2 % slower -- see profiles/r02/trmm_shared_panels.txt), 0 = auto,
+// S = forced (if it deals out evenly).
+static int trmm_share(int n, int npad) {
+    using Cfg = CfgTrmm;
+    static const int64_t forced = env_int("BOBE_TRMM_SHARE", 1);
+    static const int64_t budget_mb = env_int("BOBE_TRMM_L2_MB", 80);
+    if (forced == 1) return 1;
+    const int n8 = (n + 7) & ~7, nblk = (n8 + Cfg::BM - 1) / Cfg::BM;
+    const int r_first = n8 % Cfg::BM, first = r_first ? r_first : Cfg::BM;
+    const int kmax = ((n + Cfg::BK - 1) / Cfg::BK) * Cfg::BK;
+    auto weight = [&](int b) {  // k-tiles x live rows of row block b (the kernel's own sweep)
+        const int row0 = b == 0 ? 0 : first + (b - 1) * Cfg::BM, live = b == 0 ? first : Cfg::BM;
+        const int ke = std::min(kmax, ((row0 + live + Cfg::BK - 1) / Cfg::BK) * Cfg::BK);
+        return (double)(ke / Cfg::BK) * live;
+    };
+    const double panel_mb = 128.0 * npad * 8.0 / (1024.0 * 1024.0);
+    int s_min = 1;
+    while (s_min < 4 && (148 / s_min) * panel_mb > (double)budget_mb) ++s_min;
+    if (forced > 1) s_min = (int)std::min<int64_t>(forced, 8);
+    for (int S = s_min; S <= (forced > 1 ? s_min : 4); ++S) {
+        if (S == 1) return 1;
+        double w[8] = {0, 0, 0, 0, 0, 0, 0, 0}, total = 0.0, worst = 0.0;
+        for (int m = 0; m < S; ++m)
+            for (int i = 0;; ++i) {
+                const int b = nblk - 1 - ((i >> 1) * 2 * S + ((i & 1) ? 2 * S - 1 - m : m));
+                if (b < 0) break;
+                w[m] += weight(b);
+            }
+        for (int m = 0; m < S; ++m) {
+            total += w[m];
+            worst = std::max(worst, w[m]);
+        }
+        if (worst * S <= 1.03 * total) return S;
+    }
+    return 1;
+}
+
+int trmm_chunk_tiles(int n, int npad) {
+    const int S = trmm_share(n, npad);
+    return (148 / S) * S;
+}
+
 int32_t launch_trmm_sumsq(cudaStream_t stream, const double* Linv, int n, int npad, const double* Kstar, int64_t ldk,
                           int64_t rows_pad, int64_t q_begin, int64_t M, double kk, double scale, int standardised,
-                          double* var_out, double* partial) {
+                          double* var_out, double* partial, int* counters) {
     using Cfg = CfgTrmm;
     if (rows_pad % Cfg::BN) {
         set_error("trmm_sumsq: query chunk must be padded to %d", Cfg::BN);
@@ -252,8 +296,17 @@ int32_t launch_trmm_sumsq(cudaStream_t stream, const double* Linv, int n, int np
         if (make_panel_map(&mapA, Linv, npad, npad, npad, Cfg::BM) && make_panel_map(&mapB, Kstar, rows_pad, npad, ldk, Cfg::BN)) {
             constexpr int TMA_SMEM = Cfg::SMEM_BYTES + 128;  // room to align the stages to 128 bytes
             if (int32_t rc = ensure_smem<trmm_sumsq_tma_kernel<Cfg>>(TMA_SMEM)) return rc;
-            trmm_sumsq_tma_kernel<Cfg><<<grid, Cfg::THREADS, TMA_SMEM, stream>>>(mapA, mapB, n, npad, q_begin, M, kk, scale,
-                                                                                   standardised, var_out);
+            const int share = (partial && counters && qtiles <= TRMM_COUNTERS) ? trmm_share(n, npad) : 1;
+            if (share > 1) {
+                const int groups = std::min(148 / share, qtiles);
+                if (int32_t rc = ensure_smem<trmm_sumsq_tma_kernel<Cfg, false, true>>(TMA_SMEM)) return rc;
+                trmm_sumsq_tma_kernel<Cfg, false, true><<<groups * share, Cfg::THREADS, TMA_SMEM, stream>>>(
+                    mapA, mapB, n, npad, q_begin, M, kk, scale, standardised, var_out, nullptr, 0, share, qtiles, partial,
+                    rows_pad, counters);
+            } else {
+                trmm_sumsq_tma_kernel<Cfg><<<grid, Cfg::THREADS, TMA_SMEM, stream>>>(mapA, mapB, n, npad, q_begin, M, kk,
+                                                                                       scale, standardised, var_out);
+            }
             return check_launch("trmm_sumsq_tma_kernel");
         }
     }

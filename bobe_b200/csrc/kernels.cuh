@@ -43,7 +43,12 @@ constexpr int TRMM_MAX_SPLIT = 32;  // rows of the `partial` scratch (each as lo
 // partial: optional scratch of TRMM_MAX_SPLIT * rows_pad doubles; enables the row split for under-filled launches
 int32_t launch_trmm_sumsq(cudaStream_t stream, const double* Linv, int n, int npad, const double* Kstar, int64_t ldk,
                           int64_t rows_pad, int64_t q_begin, int64_t M, double kk, double scale, int standardised,
-                          double* var_out, double* partial = nullptr);
+                          double* var_out, double* partial = nullptr, int* counters = nullptr);
+// counters: optional TRMM_COUNTERS zeroed ints (with `partial`): enables the shared-panel schedule of the TMA kernel, in which
+// groups of S CTAs walk the query tiles together so that the K* panels in flight fit in L2 (see trmm_sumsq_tma_kernel).
+constexpr int TRMM_COUNTERS = 512;
+// query tiles one full-size launch should carry for this n (a multiple of the group count of the shared-panel schedule)
+int trmm_chunk_tiles(int n, int npad);
 
 // VT = (Linv Kin^T)^T through the TMA trmm pipeline; 1 = route not available (use launch_gemm_nt), 0 = done, < 0 = error
 int32_t launch_trmm_store(cudaStream_t stream, const double* Linv, int n, int npad, const double* Kin, int64_t ldk,

@@ -49,11 +49,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
 // STORE = true: the same sweep, but instead of squaring V = Linv K*^T into per-query sums the finished row blocks are written
 // out transposed, VT[q][i] (leading dimension ldv, rows i in [n8, npad) zeroed): the shared solve of the fantasy variance
 // (bobe_fantasy_var), whose K* panel is K(MC, X).  The values are bitwise those of gemm_nt_kernel for the same product.
-template <class Cfg, bool STORE = false>
+template <class Cfg, bool STORE = false, bool SHARED = false>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
     trmm_sumsq_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int n, int npad,
                           int64_t q_begin, int64_t M, double kk, double scale, int standardised,
-                          double* __restrict__ var_out, double* __restrict__ vt_out = nullptr, int64_t ldv = 0) {
+                          double* __restrict__ var_out, double* __restrict__ vt_out = nullptr, int64_t ldv = 0,
+                          int share = 1, int qtiles = 0, double* __restrict__ partial = nullptr, int64_t pstride = 0,
+                          int* __restrict__ counters = nullptr) {
     using ML = Mainloop<Cfg>;
     constexpr int STAGES = Cfg::STAGES, NWARPS = Cfg::THREADS / 32;
     constexpr uint32_t STAGE_BYTES = Cfg::STAGE_DOUBLES * 8;
@@ -63,7 +65,18 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
     __shared__ __align__(8) uint64_t full[STAGES];
     __shared__ int left[STAGES];  // warps that have not yet left the stage
     __shared__ double red[Cfg::WM][Cfg::BN];
-    const int j0 = blockIdx.x * Cfg::BN;
+    // SHARED (sum-of-squares mode only; share = S > 1): S consecutive CTAs form a group that walks the query tiles
+    // group, group + G, ... (G groups) TOGETHER, each member taking the row blocks m, 2S-1-m, 2S+m, 4S-1-m, ... (counted from the last
+    // one) of every tile (dealt out boustrophedon-wise: equal triangular work), so only G K* panels are in flight at a time and their re-reads
+    // (once per row block) hit L2 instead of DRAM.  The members' partial column sums meet in `partial`; the last member to
+    // finish a tile adds them in member order (fixed order: deterministic) and writes the variances.
+    constexpr bool shared_mode = SHARED && !STORE;
+    const int S = shared_mode ? share : 1;
+    const int member = shared_mode ? (int)blockIdx.x % S : 0;
+    const int group = shared_mode ? (int)blockIdx.x / S : (int)blockIdx.x;
+    const int G = shared_mode ? (int)gridDim.x / S : 1;
+    const int ntile_mine = shared_mode ? (group < qtiles ? (qtiles - group + G - 1) / G : 0) : 1;
+    __shared__ int last_flag;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp / Cfg::WN, wn = warp % Cfg::WN;
@@ -81,6 +94,18 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
         return ke / Cfg::BK;
     };
 
+    // the i-th row block of this CTA and how many it has (shared mode: dealt from the LAST, longest block downwards, so the
+    // incomplete final round consists of the shortest blocks and every member gets the same work for any n)
+    auto blk = [&](int i) {
+        return shared_mode ? nblk - 1 - ((i >> 1) * 2 * S + ((i & 1) ? 2 * S - 1 - member : member)) : i;
+    };
+    int nbm = nblk;
+    if (shared_mode) {
+        nbm = 0;
+        while (blk(nbm) >= 0) ++nbm;
+    }
+    const int tiles_run = nbm > 0 ? ntile_mine : 0;  // (a member without row blocks only joins the final sums)
+
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
@@ -91,35 +116,38 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
     }
     __syncthreads();
 
-    // issue the TMA loads of item (b, kt) into `stage` (one lane)
-    auto issue = [&](int b, int kt, int stage) {
+    // issue the TMA loads of item (tile u of this CTA, its row block i, k-tile kt) into `stage` (one lane)
+    auto issue = [&](int u, int i, int kt, int stage) {
         double* sA = smem + stage * Cfg::STAGE_DOUBLES;
         double* sB = sA + Cfg::BM * Cfg::BK;
         mbar_expect_tx(&full[stage], STAGE_BYTES);
-        const int i0 = row0(b), k0 = kt * Cfg::BK;
+        const int i0 = row0(blk(i)), k0 = kt * Cfg::BK, jq = (group + u * G) * Cfg::BN;
 #pragma unroll
         for (int p = 0; p < Cfg::PANELS; ++p) {
             tma_load_2d(sA + p * Cfg::BM * 8, &mapA, &full[stage], k0 + 8 * p, i0);
-            tma_load_2d(sB + p * Cfg::BN * 8, &mapB, &full[stage], k0 + 8 * p, j0);
+            tma_load_2d(sB + p * Cfg::BN * 8, &mapB, &full[stage], k0 + 8 * p, jq);
         }
     };
 
     // look-ahead iterator (item + STAGES), kept by every warp's lane 0
-    int lb = 0, lkt = 0;
-    auto advance = [&](int& b, int& kt) {
-        if (b >= nblk) return;
-        if (++kt == ktiles_of(b)) {
+    int lu = 0, lb = 0, lkt = 0;
+    auto advance = [&](int& u, int& i, int& kt) {
+        if (u >= tiles_run) return;
+        if (++kt == ktiles_of(blk(i))) {
             kt = 0;
-            ++b;
+            if (++i == nbm) {
+                i = 0;
+                ++u;
+            }
         }
     };
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            if (lb < nblk) issue(lb, lkt, s);
-            advance(lb, lkt);
+            if (lu < tiles_run) issue(lu, lb, lkt, s);
+            advance(lu, lb, lkt);
         }
     } else {
-        for (int s = 0; s < STAGES; ++s) advance(lb, lkt);
+        for (int s = 0; s < STAGES; ++s) advance(lu, lb, lkt);
     }
 
     double colsum[Cfg::NF][2];
@@ -131,7 +159,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
     const int fbase = Cfg::frag_row(wm, 0);
     int stage = 0;
     uint32_t parity = 0;
-    for (int b = 0; b < nblk; ++b) {
+    for (int u = 0; u < ntile_mine; ++u) {
+    const int j0 = (group + u * G) * Cfg::BN;
+    for (int bi = 0; bi < nbm; ++bi) {
+        const int b = blk(bi);
         const int i0 = row0(b);
         const int rows_live = b == 0 ? first : Cfg::BM;
         const int ktiles = ktiles_of(b);
@@ -182,12 +213,12 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
                 if (before == 1) {
                     left[stage] = NWARPS;  // nobody touches it again before the refill has landed
                     __threadfence_block();
-                    if (lb < nblk) {
+                    if (lu < tiles_run) {
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        issue(lb, lkt, stage);
+                        issue(lu, lb, lkt, stage);
                     }
                 }
-                advance(lb, lkt);
+                advance(lu, lb, lkt);
             }
             if (++stage == STAGES) {
                 stage = 0;
@@ -215,7 +246,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
                     colsum[nf][1] = fma(acc[mf][nf][1], acc[mf][nf][1], colsum[nf][1]);
                 }
         }
-    }
+    }  // row blocks of this CTA
     if (STORE) {  // identity rows of the padded Linv meet zero columns of K*: V is zero there
         const int tail = npad - n8;
         for (int idx = threadIdx.x; idx < tail * Cfg::BN; idx += Cfg::THREADS) {
@@ -234,10 +265,37 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
                 if (g == 0) red[wm][wn * Cfg::WTN + nf * 8 + 2 * t + c] = v;
             }
         __syncthreads();
+        if (shared_mode) {  // deposit this member's partial sums; the last member of the tile finishes it
+            for (int c = threadIdx.x; c < Cfg::BN; c += Cfg::THREADS) {
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < Cfg::WM; ++w) s += red[w][c];
+                partial[member * pstride + j0 + c] = s;
+                __threadfence();
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const int tile = group + u * G;
+                const int prev = atomicAdd(&counters[tile], 1);
+                last_flag = prev == S - 1;
+                if (prev == S - 1) counters[tile] = 0;  // ready for the next launch
+            }
+            __syncthreads();
+            if (!last_flag) {
+#pragma unroll
+                for (int nf = 0; nf < Cfg::NF; ++nf) colsum[nf][0] = colsum[nf][1] = 0.0;
+                continue;
+            }
+            __threadfence();
+        }
         for (int c = threadIdx.x; c < Cfg::BN; c += Cfg::THREADS) {
             double s = 0.0;
+            if (shared_mode) {
+                for (int m = 0; m < S; ++m) s += __ldcg(partial + m * pstride + j0 + c);
+            } else {
 #pragma unroll
-            for (int w = 0; w < Cfg::WM; ++w) s += red[w][c];
+                for (int w = 0; w < Cfg::WM; ++w) s += red[w][c];
+            }
             const int64_t q = q_begin + j0 + c;
             if (q < M) {
                 double var = kk - s;
@@ -251,7 +309,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
                 var_out[q] = var;
             }
         }
+#pragma unroll
+        for (int nf = 0; nf < Cfg::NF; ++nf) colsum[nf][0] = colsum[nf][1] = 0.0;
     }
+    }  // tiles of this CTA
 }
 
 // ---- persistent TMA-fed NT GEMM ------------------------------------------------------------------------------------------

@@ -897,6 +897,41 @@ def test_kernel_variants_agree_bitwise():
     assert _run_with_env({"BOBE_PDL": "0", "BOBE_MLL_STREAMS": "1"}, _KERNEL_VARIANT_SNIPPET) == default
 
 
+_SHARED_PANEL_SNIPPET = """
+import sys, numpy as np, torch
+from bobe_b200 import GP
+from oracle import gp_oracle as O
+out = {}
+for n, d in ((2000, 6), (1900, 5), (1500, 4), (1000, 3), (1203, 3), (500, 2)):
+    X, y = O.synthetic_training_set(n, d)
+    gp = GP(X, y, kernel="matern", lengthscales=np.full(d, 0.9))
+    Xq = torch.as_tensor(O.synthetic_queries(2 * 148 * 128 + 100 * 128 + 77, d, seed=n), device="cuda")
+    out[str(n)] = gp.predict_var_batched(Xq).cpu().numpy()
+    out["prior" + str(n)] = np.array([gp.y_std ** 2])
+np.savez(sys.argv[1] if len(sys.argv) > 1 else OUT, **out)
+print("ok")
+"""
+
+
+def test_shared_panel_schedule_matches_the_default(tmp_path):
+    """BOBE_TRMM_SHARE (opt-in: S CTAs walk the query tiles together and share each K* panel through L2, partial sums added in
+    member order by the last CTA of a tile): the same variances as the default schedule up to the order of the S partial
+    sums, for sizes that pick S = 4 / 3 / 2 / 1, ragged row-block counts, and launches with fewer tiles than groups x S."""
+    res = {}
+    for tag, env in (("default", {}), ("auto", {"BOBE_TRMM_SHARE": "0"}), ("forced4", {"BOBE_TRMM_SHARE": "4"})):
+        path = str(tmp_path / f"{tag}.npz")
+        assert _run_with_env(env, f"OUT = {path!r}\n" + _SHARED_PANEL_SNIPPET) == "ok"
+        res[tag] = np.load(path)
+    for tag in ("auto", "forced4"):
+        for k in res["default"].files:
+            if k.startswith("prior"):
+                continue
+            a, b, prior = res["default"][k], res[tag][k], float(res["default"]["prior" + k][0])
+            assert a.shape == b.shape and np.all(np.isfinite(b)) and np.all(b > 0), (tag, k)
+            # var = k** - sum of squares: the sums differ only in their last bits, i.e. by rounding noise of the PRIOR variance
+            assert float(np.max(np.abs(a - b))) < 64 * 2.3e-16 * prior, (tag, k, float(np.max(np.abs(a - b))), prior)
+
+
 @pytest.mark.parametrize("kernel", ["rbf", "matern"])
 @pytest.mark.parametrize("n,d", [(5, 2), (50, 2), (127, 3), (130, 3), (300, 5), (517, 4)])
 def test_small_training_sets_with_many_queries(kernel, n, d):
