@@ -487,8 +487,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
         if (SPLIT) {
             // Row block b costs ~(b + 1) k-blocks.  Dealing the blocks out boustrophedon-wise (0 1 2 3 3 2 1 0 0 1 ...)
             // gives every CTA of a query tile the same triangular work (a plain stride would leave the last CTA with
-            // up to 40 % more than the first).
-            const int S = gridDim.y, r = b % (2 * S);
+            // up to 40 % more than the first); counted from the LAST block, so that an incomplete final round consists
+            // of the shortest blocks (4 blocks over 3 CTAs: loads 4 / 3 / 2+1 instead of 1 / 2 / 3+4).
+            const int S = gridDim.y, r = (nblk - 1 - b) % (2 * S);
             if ((r < S ? r : 2 * S - 1 - r) != (int)blockIdx.y) continue;
         }
         const int i0 = b == 0 ? 0 : first + (b - 1) * Cfg::BM;

@@ -1,6 +1,6 @@
 """Kernel timeline (CUPTI through torch.profiler) of one factorisation / one log-ML+grad round: start offset, duration,
 stream and name of every kernel, so that gaps on the critical path and the overlap between streams can be read off.
-  python tools/timeline.py factor [n]      |     python tools/timeline.py mll R [n]
+  python tools/timeline.py factor [n]   |   python tools/timeline.py mll R [n]   |   python tools/timeline.py predict n d M [kernel]
 """
 import os, sys, re
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -26,6 +26,17 @@ lp = torch.log(torch.cat([torch.ones(R, d, dtype=torch.float64, device=dev) * (0
                           torch.ones(R, 1, dtype=torch.float64, device=dev)], 1))
 fn = (lambda: ops.factorize("matern", X, y, ls, kv, 1e-8)) if what == "factor" else \
      (lambda: ops.mll_grad_batched("matern", X, y, lp, True, 1.0, 1e-8))
+if what == "predict":  # python tools/timeline.py predict n d M [kernel]
+    import numpy as np
+    from bobe_b200 import GP
+    from oracle import gp_oracle as O
+    n, d, M = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+    kern = sys.argv[5] if len(sys.argv) > 5 else "rbf"
+    Xh, yh = O.synthetic_training_set(n, d)
+    gp = GP(Xh, yh, kernel=kern, lengthscales=np.full(d, 0.3 if kern == "rbf" else 1.0), device=dev)
+    Xq = torch.as_tensor(O.synthetic_queries(M, d), device=dev)
+    fn = lambda: gp.predict_mean_var_batched(Xq)  # noqa: E731
+    R = 0
 for _ in range(3):
     fn()
 torch.cuda.synchronize()
