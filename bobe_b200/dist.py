@@ -103,6 +103,8 @@ def mll_grad_sharded(gp, log_params: np.ndarray):
     rank, ws = world()
     lp = np.atleast_2d(np.asarray(log_params, dtype=np.float64))
     R = lp.shape[0]
+    if ws > 1 and _comm_device().type == "cuda" and hasattr(gp, "_mll_grad_device"):
+        return _mll_grad_sharded_device(gp, lp, rank, ws)
     lo, hi = shard_bounds(R, rank, ws)
     if hi > lo:
         v, g = gp.neg_mll_and_grad_batched(lp[lo:hi])
@@ -113,6 +115,32 @@ def mll_grad_sharded(gp, log_params: np.ndarray):
     both = torch.as_tensor(np.concatenate([v[:, None], g], axis=1))
     allr = allgather_rows(both, R).cpu().numpy()
     return allr[:, 0], allr[:, 1:]
+
+
+_gather_buffers: dict = {}
+
+
+def _mll_grad_sharded_device(gp, lp: np.ndarray, rank: int, ws: int):
+    """NCCL route of :func:`mll_grad_sharded`: the shard's [log-ML | gradient] rows never visit the host before the
+    collective -- device call (asynchronous), ONE ``all_gather_into_tensor`` on persistent buffers behind it, the prior terms
+    of all R rows on the host meanwhile, then a single device-to-host copy (the only synchronisation of the round)."""
+    R, P = lp.shape
+    sizes = [shard_bounds(R, r, ws)[1] - shard_bounds(R, r, ws)[0] for r in range(ws)]
+    maxrows = max(sizes)
+    lo, hi = shard_bounds(R, rank, ws)
+    dev = _comm_device()
+    key = (maxrows, P, ws, dev)
+    if key not in _gather_buffers:
+        _gather_buffers[key] = (torch.zeros((maxrows, P + 1), dtype=torch.float64, device=dev),
+                                torch.empty((ws * maxrows, P + 1), dtype=torch.float64, device=dev))
+    mine, out = _gather_buffers[key]
+    if hi > lo:
+        mine[: hi - lo].copy_(gp._mll_grad_device(np.ascontiguousarray(lp[lo:hi])))
+    tdist.all_gather_into_tensor(out, mine)
+    pv, pg = gp._prior_terms(lp)
+    allr = out.cpu().numpy().reshape(ws, maxrows, P + 1)
+    both = np.concatenate([allr[r, : sizes[r]] for r in range(ws)], axis=0)
+    return -(both[:, 0] + pv), -(both[:, 1:] + pg)
 
 
 def acquisition_sharded(eval_fn: Callable[[np.ndarray], np.ndarray], candidates: np.ndarray) -> np.ndarray:

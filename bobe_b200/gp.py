@@ -321,22 +321,32 @@ class GP:
         One lock-step device call for all rows; prior terms added on the host.
         """
         lp = np.ascontiguousarray(np.atleast_2d(np.asarray(log_params, dtype=np.float64)))
+        both_dev = self._mll_grad_device(lp)
+        # the device call above is asynchronous: the O(R d) prior terms are evaluated on the host WHILE it runs, and only
+        # then are the results fetched (the .cpu() below is the first synchronisation)
+        pv, pg = self._prior_terms(lp)
+        both = both_dev.cpu().numpy()  # one D2H copy
+        return -(both[:, 0] + pv), -(both[:, 1:] + pg)
+
+    def _mll_grad_device(self, lp: np.ndarray) -> torch.Tensor:
+        """(R, 1 + P) device tensor [log-ML | gradient] WITHOUT the prior terms, enqueued asynchronously (the sharded
+        evaluation all-gathers these rows on the device before anything is fetched: ``dist.mll_grad_sharded``)."""
         self._ensure_factor()
-        dev = self.device
         # (persistent staging buffers: the same device pointers on every optimiser step, so the native call replays its
         # captured CUDA graph instead of enqueueing several hundred launches)
         val, grad, _info = ops.mll_grad_batched(self.kernel_name, self._X_dev, self._y_dev, torch.from_numpy(lp),
                                                 not self.fixed_kernel_variance, float(self.kernel_variance),
                                                 float(self.noise), reuse_buffers=True)
-        # the device call above is asynchronous: the O(R d) prior terms are evaluated on the host WHILE it runs, and only
-        # then are the results fetched (the .cpu() below is the first synchronisation)
+        return torch.cat([val[:, None], grad], dim=1)
+
+    def _prior_terms(self, lp: np.ndarray):
+        """Log-prior values (R,) and gradients (R, P) of the rows of ``lp`` (host)."""
         pv, pg = np.empty(lp.shape[0]), np.empty_like(lp)
         for r in range(lp.shape[0]):
             ls, kv, tausq = self._parse_hyperparams(lp[r])
             pv[r] = self.prior_func(ls, kv, tausq)
             pg[r] = self._prior_grad(ls, kv, tausq)
-        both = torch.cat([val[:, None], grad], dim=1).cpu().numpy()  # one D2H copy
-        return -(both[:, 0] + pv), -(both[:, 1:] + pg)
+        return pv, pg
 
     def neg_mll_and_grad(self, log_params):
         v, g = self.neg_mll_and_grad_batched(np.asarray(log_params, dtype=np.float64)[None, :])
