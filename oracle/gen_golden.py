@@ -1,8 +1,9 @@
 """Generate the golden vectors under tests/golden/ from the NumPy oracle (and the mpmath truth for the small
 case).  TEST INFRASTRUCTURE.  Run from the repo root:  python -m oracle.gen_golden
 
-The reference itself cannot be run in this image (no JAX), so these are outputs of the restatement, pinned by the
-mathematics in tests/test_oracle.py -- "parity unpinned" in the sense of the task statement.
+JAX is not installable in this image, so these are outputs of the restatement at the full BASELINE shapes; the restatement
+itself is held to the reference's own source (executed under a NumPy stand-in: oracle/gen_reference_vectors.py ->
+tests/golden/reference_source_vectors.npz) and to the mathematics in tests/test_oracle.py.
 Inputs are regenerated from seeds (oracle.gp_oracle.synthetic_*), so only outputs are stored.
 """
 import os

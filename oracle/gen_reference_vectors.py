@@ -1,0 +1,349 @@
+"""Golden vectors produced by the REFERENCE'S OWN SOURCE (test infrastructure; runs only where /root/reference exists).
+
+JAX, numpyro, optax and tensorflow-probability are not installed in this image and cannot be, so ``import BOBE`` fails.
+This script therefore executes the reference's unmodified source files ``BOBE/gp.py``, ``BOBE/acquisition.py`` (and the
+helpers they import: ``optim.py``, ``utils/core.py``, ``utils/log.py``, ``utils/seed.py``) from where they lie under
+/root/reference, with a NumPy/SciPy stand-in for the part of the jax API those files touch:
+
+    jax.numpy            -> numpy (array creators return a subclass that adds ``.at[idx].set(v)``)
+    jax.scipy.linalg     -> scipy.linalg (cho_solve, solve_triangular: the same LAPACK routines XLA's CPU backend calls)
+    jax.scipy.stats.norm -> scipy.stats.norm
+    jax.jit              -> identity;   jax.vmap / lax.map -> a Python loop over the leading axis
+    jax.value_and_grad   -> not available (gradients are NOT pinned by this route: see below)
+    numpyro.distributions.Uniform.log_prob -> -log(high - low)   (the only prior the default GP constructs)
+    tensorflow_probability...math.erfcx / log1mexp -> scipy.special.erfcx / log(1 - exp(-|x|)) (TFP's documented definition)
+
+What this pins: every ARITHMETIC STATEMENT of the reference on the path (distances, both kernels, the log marginal
+likelihood, the rank-1 Cholesky append, standardisation, Cholesky + alphas, posterior mean / variance in all their
+variants, duplicate handling in ``update``, the fantasy variance, EI / LogEI / WIPV / WIPStd values) is executed as written
+by the reference's authors, in float64, on seeded inputs; the outputs are stored next to the inputs in
+``tests/golden/reference_source_vectors.npz``.  ``tests/test_oracle.py`` checks the oracle restatement against them and
+``tests/test_gpu_parity.py`` checks the CUDA path against them.
+What it does NOT pin: XLA's own floating-point behaviour (fusion, its Cholesky kernel) -- rounding-level differences -- and
+anything that needs autodiff (``jax.value_and_grad``): for the log-ML gradient the file stores central differences of the
+reference's ``neg_mll`` (accurate to ~1e-7), a sanity bound, not a bitwise pin.
+
+    python oracle/gen_reference_vectors.py            # writes tests/golden/reference_source_vectors.npz
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import scipy.linalg
+import scipy.special
+import scipy.stats
+
+REF = os.environ.get("BOBE_REFERENCE", "/root/reference")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "tests", "golden", "reference_source_vectors.npz")
+
+
+# ---- the stand-in for the jax API -----------------------------------------------------------------------------------
+class _At:
+    def __init__(self, arr):
+        self.arr = arr
+
+    def __getitem__(self, idx):
+        arr = self.arr
+
+        class _Ref:
+            def set(self, v):
+                out = np.array(arr, copy=True).view(JArray)
+                out[idx] = v
+                return out
+
+            def add(self, v):
+                out = np.array(arr, copy=True).view(JArray)
+                out[idx] += v
+                return out
+        return _Ref()
+
+
+class JArray(np.ndarray):
+    """numpy array with jax's functional-update syntax ``x.at[idx].set(v)``."""
+    @property
+    def at(self):
+        return _At(self)
+
+
+def _wrap(fn):
+    def inner(*a, **k):
+        r = fn(*a, **k)
+        return r.view(JArray) if isinstance(r, np.ndarray) else r
+    inner.__name__ = getattr(fn, "__name__", "wrapped")
+    return inner
+
+
+def _make_jnp():
+    m = types.ModuleType("jax.numpy")
+    for name in dir(np):
+        if not name.startswith("_"):
+            setattr(m, name, getattr(np, name))
+    for name in ("zeros", "ones", "array", "asarray", "eye", "empty", "full", "zeros_like", "ones_like", "arange", "linspace"):
+        setattr(m, name, _wrap(getattr(np, name)))
+
+    def clip(a, a_min=None, a_max=None, **kw):  # jnp.clip(x, a_min=...) with either bound optional
+        a_min = kw.pop("min", a_min)
+        a_max = kw.pop("max", a_max)
+        return np.clip(a, a_min, a_max)
+    m.clip = clip
+    m.ndarray = np.ndarray
+    m.linalg = np.linalg
+    return m
+
+
+def _jit(fn=None, **_kw):
+    if fn is None:
+        return lambda f: f
+    return fn
+
+
+def _vmap(fn, in_axes=0, out_axes=0):
+    if in_axes != 0:
+        raise NotImplementedError("stand-in vmap: only in_axes=0 is used on this path")
+
+    def mapped(xs):
+        outs = [fn(x) for x in xs]
+        if isinstance(outs[0], tuple):
+            return tuple(np.stack([np.asarray(o[i]) for o in outs]) for i in range(len(outs[0])))
+        return np.stack([np.asarray(o) for o in outs])
+    return mapped
+
+
+def _no_autodiff(*_a, **_k):
+    raise NotImplementedError("jax autodiff is not available in the NumPy stand-in")
+
+
+def install_standin():
+    jnp = _make_jnp()
+    jax = types.ModuleType("jax")
+    jax.__path__ = []
+    jax.numpy = jnp
+    jax.jit = _jit
+    jax.vmap = _vmap
+    jax.value_and_grad = _no_autodiff
+    jax.grad = _no_autodiff
+    jax.Array = np.ndarray
+    jax.config = types.SimpleNamespace(update=lambda *a, **k: None)
+    lax = types.ModuleType("jax.lax")
+    lax.map = lambda f, xs, **_k: _vmap(f)(xs)
+    jax.lax = lax
+    rnd = types.ModuleType("jax.random")
+    rnd.PRNGKey = lambda seed: np.array([0, seed], dtype=np.uint32)
+    rnd.split = lambda key, num=2: [np.array([int(key[1]) + i + 1, int(key[1])], dtype=np.uint32) for i in range(num)]
+    jax.random = rnd
+    jsp = types.ModuleType("jax.scipy")
+    jsp.__path__ = []
+    jsl = types.ModuleType("jax.scipy.linalg")
+    jsl.cho_solve = scipy.linalg.cho_solve
+    jsl.solve_triangular = scipy.linalg.solve_triangular
+    jss = types.ModuleType("jax.scipy.stats")
+    jss.norm = scipy.stats.norm
+    jsx = types.ModuleType("jax.scipy.special")
+    for name in ("erfcx", "erfc", "erf", "ndtr", "log_ndtr", "logsumexp", "gammaln"):
+        setattr(jsx, name, getattr(scipy.special, name))
+    jsp.linalg, jsp.stats, jsp.special = jsl, jss, jsx
+    jax.scipy = jsp
+    mods = {"jax": jax, "jax.numpy": jnp, "jax.lax": lax, "jax.random": rnd, "jax.scipy": jsp, "jax.scipy.linalg": jsl,
+            "jax.scipy.stats": jss, "jax.scipy.special": jsx}
+
+    # numpyro.distributions: only what the default GP constructs (Uniform priors: a constant)
+    numpyro = types.ModuleType("numpyro")
+    numpyro.__path__ = []
+    dist = types.ModuleType("numpyro.distributions")
+
+    class Distribution:
+        pass
+
+    class Uniform(Distribution):
+        def __init__(self, low=0.0, high=1.0):
+            self.low, self.high = low, high
+
+        def log_prob(self, x):
+            return -np.log(self.high - self.low) + 0.0 * np.asarray(x)
+
+    def _unavailable(name):
+        class _D(Distribution):
+            def __init__(self, *a, **k):
+                raise NotImplementedError(f"numpyro.distributions.{name} is not part of the stand-in")
+        _D.__name__ = name
+        return _D
+    dist.Distribution, dist.Uniform = Distribution, Uniform
+    for name in ("LogNormal", "HalfCauchy", "Normal", "Gamma"):
+        setattr(dist, name, _unavailable(name))
+    numpyro.distributions = dist
+    mods.update({"numpyro": numpyro, "numpyro.distributions": dist})
+
+    # tensorflow_probability.substrates.jax: tfp.math.erfcx, tfp.math.log1mexp
+    tfp_root = types.ModuleType("tensorflow_probability")
+    tfp_root.__path__ = []
+    sub = types.ModuleType("tensorflow_probability.substrates")
+    sub.__path__ = []
+    tfj = types.ModuleType("tensorflow_probability.substrates.jax")
+
+    def log1mexp(x):  # TFP: log(1 - exp(-|x|)), Maechler's two-branch evaluation
+        x = np.abs(np.asarray(x, dtype=np.float64))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return np.where(x < np.log(2.0), np.log(-np.expm1(-x)), np.log1p(-np.exp(-x)))
+    tfj.math = types.SimpleNamespace(erfcx=scipy.special.erfcx, log1mexp=log1mexp)
+    tfp_root.substrates, sub.jax = sub, tfj
+    mods.update({"tensorflow_probability": tfp_root, "tensorflow_probability.substrates": sub,
+                 "tensorflow_probability.substrates.jax": tfj})
+    sys.modules.update(mods)
+
+
+def load_reference():
+    """Import BOBE.gp and BOBE.acquisition from their source files without running BOBE/__init__.py (which pulls in the
+    samplers, plotting and MPI layers)."""
+    install_standin()
+    pkg = types.ModuleType("BOBE")
+    pkg.__path__ = [os.path.join(REF, "BOBE")]
+    utils = types.ModuleType("BOBE.utils")
+    utils.__path__ = [os.path.join(REF, "BOBE", "utils")]
+    samplers = types.ModuleType("BOBE.samplers")  # acquisition.py imports two names from it at module level
+    samplers.nested_sampling_Dy = samplers.sample_GP_NUTS = None
+    sys.modules.update({"BOBE": pkg, "BOBE.utils": utils, "BOBE.samplers": samplers})
+
+    def load(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REF, "BOBE", rel))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+    load("BOBE.utils.log", "utils/log.py")
+    load("BOBE.utils.seed", "utils/seed.py")
+    load("BOBE.utils.core", "utils/core.py")
+    load("BOBE.optim", "optim.py")
+    gp = load("BOBE.gp", "gp.py")
+    acq = load("BOBE.acquisition", "acquisition.py")
+    return gp, acq
+
+
+# ---- the cases ------------------------------------------------------------------------------------------------------
+def _objective(X):
+    return -0.5 * np.sum(((X - 0.45) / 0.2) ** 2, axis=1) + 0.3 * np.sin(7.0 * X[:, 0]) + 12.5
+
+
+def _training_set(rng, n, d):
+    X = rng.uniform(0.0, 1.0, size=(n, d))
+    return X, _objective(X)
+
+
+def generate():
+    G, A = load_reference()
+    rng = np.random.default_rng(20261018)
+    out = {}
+
+    # kernels and distances --------------------------------------------------------------------------------------------
+    xa, xb = rng.uniform(0, 1, (40, 3)), rng.uniform(0, 1, (7, 3))
+    ls, kv, noise = np.array([0.31, 0.8, 1.7]), 1.7, 1e-6
+    out.update(k_xa=xa, k_xb=xb, k_ls=ls, k_kv=kv, k_noise=noise,
+               k_dist_sq=G.dist_sq(xa, xb),
+               k_rbf_cross=G.rbf_kernel(xa, xb, ls, kv, noise, include_noise=False),
+               k_matern_cross=G.matern_kernel(xa, xb, ls, kv, noise, include_noise=False),
+               k_rbf_square=G.rbf_kernel(xa, xa, ls, kv, noise, include_noise=True),
+               k_matern_square=G.matern_kernel(xa, xa, ls, kv, noise, include_noise=True),
+               k_diag_noise=G.kernel_diag(xa, kv, noise, include_noise=True),
+               k_diag_plain=G.kernel_diag(xa, kv, noise, include_noise=False))
+
+    # log marginal likelihood of a given K ------------------------------------------------------------------------------
+    X, y = _training_set(rng, 60, 3)
+    ys = ((y - y.mean()) / y.std())[:, None]
+    for kern in ("rbf", "matern"):
+        K = getattr(G, kern + "_kernel")(X, X, np.array([0.4, 0.6, 0.9]), 1.3, 1e-6, include_noise=True)
+        out[f"mll_{kern}_K"] = K
+        out[f"mll_{kern}_value"] = np.float64(G.gp_mll(K, ys, 60))
+    out.update(mll_X=X, mll_y_std=ys)
+
+    # rank-1 Cholesky append ------------------------------------------------------------------------------------------
+    Xc = rng.uniform(0, 1, (30, 2))
+    Kc = G.matern_kernel(Xc, Xc, np.array([0.5, 0.7]), 1.0, 1e-6, include_noise=True)
+    Lc = np.linalg.cholesky(Kc)
+    xnew = rng.uniform(0, 1, (1, 2))
+    kvec = G.matern_kernel(Xc, xnew, np.array([0.5, 0.7]), 1.0, 1e-6, include_noise=False).flatten()
+    out.update(chol_L=Lc, chol_k=kvec, chol_kself=np.float64(1.0 + 1e-6),
+               chol_new_L=np.asarray(G.fast_update_cholesky(Lc, kvec, 1.0 + 1e-6)))
+
+    # the GP class ------------------------------------------------------------------------------------------------------
+    # two well-conditioned cases (factor stored) and BASELINE config B's worst-conditioned shape (n = 500, d = 2 RBF with
+    # lengthscale 0.3, noise 1e-8: cond(K) ~ 1e10; factor not stored -- 2 MB)
+    for p, kern, n, d, m, lsg, kvg, noise_g, store_factor in (
+            ("gp_rbf_", "rbf", 80, 4, 33, np.array([0.35, 0.6, 0.9, 1.4]), 1.3, 1e-6, True),
+            ("gp_matern_", "matern", 80, 4, 33, np.array([0.35, 0.6, 0.9, 1.4]), 1.3, 1e-6, True),
+            ("gpB_rbf_", "rbf", 500, 2, 40, np.array([0.3, 0.3]), 1.0, 1e-8, False)):
+        X, y = _training_set(rng, n, d)
+        gp = G.GP(X, y[:, None], noise=noise_g, kernel=kern, lengthscales=lsg, kernel_variance=kvg)
+        Xq = rng.uniform(0, 1, (m, d))
+        Xq[0] = X[5]  # a training point: variance at the noise floor
+        out.update({p + "X": X, p + "y": y, p + "ls": lsg, p + "kv": np.float64(kvg), p + "noise": np.float64(noise_g), p + "Xq": Xq,
+                    p + "y_mean": np.float64(gp.y_mean), p + "y_std": np.float64(gp.y_std),
+                    p + "train_y": np.asarray(gp.train_y), p + "alphas": np.asarray(gp.alphas),
+                    p + "cond_L": np.float64(np.linalg.cond(np.asarray(gp.cholesky))),
+                    p + "logdet_half": np.float64(np.sum(np.log(np.diag(np.asarray(gp.cholesky))))),
+                    p + "mean_batched": np.asarray(gp.predict_mean_batched(Xq)),
+                    p + "var_batched": np.asarray(gp.predict_var_batched(Xq)),
+                    p + "mean_single": np.float64(gp.predict_mean_single(Xq[3])),
+                    p + "var_single": np.float64(gp.predict_var_single(Xq[3]))})
+        if store_factor:
+            out[p + "cholesky"] = np.asarray(gp.cholesky)
+        ms, vs = gp.predict_batched(Xq)
+        out.update({p + "std_mean_batched": np.asarray(ms).reshape(-1), p + "std_var_batched": np.asarray(vs).reshape(-1)})
+
+        # neg_mll at several hyper-parameter rows (default priors are Uniform: a constant, evaluated by the stand-in) and
+        # central differences of it (autodiff is not available; a sanity bound for the analytic gradient)
+        ls_hi = 2.0 if store_factor else 0.45  # (the dense d = 2 shape turns numerically singular beyond that)
+        lp = np.log(np.column_stack([rng.uniform(0.2, ls_hi, (5, d)), rng.uniform(0.5, 3.0, 5)]))
+        vals = np.array([float(gp.neg_mll(r)) for r in lp])
+        h = 1e-5
+        fd = np.zeros_like(lp)
+        for r in range(lp.shape[0]):
+            for j in range(lp.shape[1]):
+                e = np.zeros(lp.shape[1])
+                e[j] = h
+                fd[r, j] = (float(gp.neg_mll(lp[r] + e)) - float(gp.neg_mll(lp[r] - e))) / (2 * h)
+        prior_const = float(gp.prior_func(np.exp(lp[0, :d]), np.exp(lp[0, d]), 1.0))
+        out.update({p + "log_params": lp, p + "neg_mll": vals, p + "neg_mll_fd_grad": fd, p + "prior_const": np.float64(prior_const)})
+
+        # fantasy variance and the two integrated acquisitions
+        mc = rng.uniform(0, 1, (50, d))
+        cand = rng.uniform(0, 1, (3, d))
+        k_train_mc = gp.kernel(gp.train_x, mc, gp.lengthscales, gp.kernel_variance, noise=gp.noise, include_noise=False)
+        fv = np.stack([np.asarray(gp.fantasy_var(c, mc, k_train_mc)) for c in cand])
+        out.update({p + "mc": mc, p + "cand": cand, p + "fantasy_var": fv,
+                    p + "wipv": np.array([float(A.WIPV().fun(c, gp, mc_points=mc, k_train_mc=k_train_mc)) for c in cand]),
+                    p + "wipstd": np.array([float(A.WIPStd().fun(c, gp, mc_points=mc, k_train_mc=k_train_mc)) for c in cand])})
+
+        # EI / LogEI (negated, as the optimiser sees them) on the standardised scale
+        best_y, zeta = float(np.max(np.asarray(gp.train_y))), 0.01
+        xe = np.vstack([Xq[:8], X[5][None, :]])
+        out.update({p + "ei_x": xe, p + "ei_best_y": np.float64(best_y), p + "ei_zeta": np.float64(zeta),
+                    p + "ei": np.array([float(A.EI().fun(x, gp, best_y, zeta)) for x in xe]),
+                    p + "logei": np.array([float(A.LogEI().fun(x, gp, best_y, zeta)) for x in xe])})
+
+        # update(): two new points and one duplicate of a training point
+        new_x = np.vstack([rng.uniform(0, 1, (2, d)), X[7][None, :]])
+        new_y = np.concatenate([_objective(new_x[:2]) + np.array([0.01, -0.02]), [y[7]]])[:, None]
+        gp.update(new_x, new_y)
+        out.update({p + "upd_new_x": new_x, p + "upd_new_y": new_y, p + "upd_train_x": np.asarray(gp.train_x),
+                    p + "upd_y_mean": np.float64(gp.y_mean), p + "upd_y_std": np.float64(gp.y_std),
+                    p + "upd_alphas": np.asarray(gp.alphas),
+                    p + "upd_cond_L": np.float64(np.linalg.cond(np.asarray(gp.cholesky))),
+                    p + "upd_mean_batched": np.asarray(gp.predict_mean_batched(Xq[:6]))})
+        if store_factor:
+            out[p + "upd_cholesky"] = np.asarray(gp.cholesky)
+
+    # the LogEI helper over its three branches (u > -1, the asymptotic branch, and u < -1e6)
+    u = np.concatenate([np.linspace(-40.0, 5.0, 91), -np.logspace(2, 7.5, 12)])
+    out.update(logei_u=u, logei_helper=np.asarray(A._log_ei_helper(u)), ei_helper=np.asarray(A._ei_helper(u)))
+
+    out = {k: np.asarray(v, dtype=np.float64) for k, v in out.items()}
+    np.savez_compressed(OUT, **out)
+    print(f"wrote {OUT}: {len(out)} arrays, {os.path.getsize(OUT) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    generate()

@@ -5,15 +5,26 @@ the acquisition arithmetic in ``BOBE/acquisition.py``.  It exists to check the C
 ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
 ``bench.py`` may import it.  Nothing under ``bobe_b200/`` imports it.
 
-PARITY UNPINNED: the reference is pure Python/JAX, JAX is not installable in this image (no wheel,
-no network), and the reference's own tests hold no golden vectors for this path.  The
-oracle is therefore pinned by mathematics instead (tests/test_oracle.py): closed forms at n=1,2,
-interpolation/noise-level identities, gradient three ways (analytic, torch autograd through
-``torch.linalg.cholesky`` = the same reverse-mode construction JAX uses, central differences),
-``fantasy_var`` == ``predict_var`` of an actually-updated GP, and an mpmath 60-digit re-evaluation
-(``oracle/truth_mp.py``); and EXTERNALLY, against third-party code that shares nothing with it: scikit-learn's
-``GaussianProcessRegressor`` (posterior mean / variance, log marginal likelihood and its gradient, both kernels) and
-``SVC.decision_function`` (the classifier mask), both in tests/test_oracle.py.
+PINNING.  The reference is pure Python/JAX; JAX, numpyro and tensorflow-probability are not installable in this image
+(no wheel, no network), so ``import BOBE`` fails and the reference's own tests hold no golden vectors for this path
+(SURVEY.md 8c).  Two things stand in for a JAX run:
+
+1. THE REFERENCE'S OWN SOURCE, EXECUTED HERE (round 2): ``oracle/gen_reference_vectors.py`` loads the unmodified files
+   ``BOBE/gp.py`` and ``BOBE/acquisition.py`` from /root/reference under a NumPy/SciPy stand-in for the slice of the jax API
+   they touch (jax.numpy -> numpy, jax.scipy.linalg -> scipy.linalg, jit -> identity, vmap / lax.map -> loops) and stores
+   what the reference's code computes -- kernels, gp_mll, fast_update_cholesky, the GP constructor's standardisation /
+   Cholesky / alphas, every predict variant, neg_mll, update() with a duplicate, fantasy_var, WIPV / WIPStd / EI / LogEI
+   values, at two well-conditioned shapes and at BASELINE config B's worst-conditioned one -- in
+   ``tests/golden/reference_source_vectors.npz``.  ``tests/test_oracle.py`` holds this restatement to those vectors (the
+   factor and the kernels agree bit for bit, everything else to ~1e-14 x cond), and ``tests/test_gpu_parity.py`` holds the
+   CUDA path to them.  NOT pinned by this route: XLA's own floating-point behaviour (rounding-level) and autodiff
+   (``jax.value_and_grad``: the stand-in has none; the file carries central differences of the reference's neg_mll instead),
+   and the numpyro priors other than Uniform (tests/test_host_logic.py checks those against closed forms).
+2. MATHEMATICS AND THIRD-PARTY CODE (round 1, tests/test_oracle.py): closed forms at n=1,2, interpolation / noise-level
+   identities, the gradient three ways (analytic, torch autograd through ``torch.linalg.cholesky`` = the reverse-mode
+   construction JAX uses, central differences), ``fantasy_var`` == ``predict_var`` of an actually-updated GP, an mpmath
+   60-digit re-evaluation (``oracle/truth_mp.py``), scikit-learn's ``GaussianProcessRegressor`` (posterior mean / variance,
+   log marginal likelihood and its gradient, both kernels) and ``SVC.decision_function`` (the classifier mask).
 
 Every function cites the reference lines it follows (paths relative to /root/reference).
 """

@@ -958,3 +958,93 @@ def test_small_training_sets_with_many_queries(kernel, n, d):
     fv = gp.fantasy_var(cand, Xq)
     assert fv.shape == (6, M)
     assert mixed_err(fv[:, idx], ref.fantasy_var_shared(cand, Xq[idx]), ref.y_std ** 2) < TOL_VAR
+
+
+@pytest.mark.parametrize("p,kern", [("gp_rbf_", "rbf"), ("gp_matern_", "matern"), ("gpB_rbf_", "rbf")])
+def test_cuda_matches_the_reference_source_vectors(p, kern):
+    """The CUDA path against vectors computed by the REFERENCE'S OWN SOURCE (BOBE/gp.py, BOBE/acquisition.py executed from
+    /root/reference under a NumPy stand-in for jax.numpy: oracle/gen_reference_vectors.py): constructor + standardisation,
+    Cholesky / alphas, every predict variant, neg_mll with the default priors (+ gradient against central differences of the
+    reference's neg_mll), fantasy variance, WIPV / WIPStd, EI / LogEI, and update() with a duplicate point."""
+    from bobe_b200 import GP, EI, LogEI, ops
+    v = np.load(os.path.join(GOLDEN_DIR, "reference_source_vectors.npz"))
+    X, y, ls, Xq = v[p + "X"], v[p + "y"], v[p + "ls"], v[p + "Xq"]
+    y_std, n = float(v[p + "y_std"]), X.shape[0]
+    # gpB_ is BASELINE config B's worst-conditioned shape (cond(K) ~ 1e10): two float64 evaluations of the same formulas
+    # differ there by ~cond(K) eps (SURVEY.md fact 5), so the mean / log-ML are held to 3x the tolerance, as in
+    # test_golden_parity, where the distance of each side to the exact value is measured
+    ill = float(v[p + "cond_L"]) > 1e4
+    tol_mean, tol_mll = (3 * TOL_MEAN, 3 * TOL_MLL) if ill else (TOL_MEAN, TOL_MLL)
+    gp = GP(X, y[:, None], noise=float(v[p + "noise"]), kernel=kern, lengthscales=ls, kernel_variance=float(v[p + "kv"]))
+    assert abs(gp.y_mean - float(v[p + "y_mean"])) <= 1e-14 * abs(gp.y_mean) and abs(gp.y_std - y_std) <= 1e-14 * y_std
+    assert mixed_err(np.asarray(gp.train_y), v[p + "train_y"], 1.0) < 1e-14
+    L = np.asarray(gp.cholesky)
+    assert L.shape == (n, n)
+    if p + "cholesky" in v.files:
+        assert mixed_err(L, v[p + "cholesky"], 1.0) < 1e-11
+    assert abs(float(np.sum(np.log(np.diag(L)))) - float(v[p + "logdet_half"])) <= tol_mll * n
+    assert np.linalg.norm(np.asarray(gp.alphas).ravel() - v[p + "alphas"].ravel()) <= (1e-6 if ill else 1e-9) * np.linalg.norm(v[p + "alphas"])
+    mean, var = gp.predict_mean_var_batched(Xq)
+    e_mean, e_var = mixed_err(mean, v[p + "mean_batched"], y_std), mixed_err(var, v[p + "var_batched"], y_std ** 2)
+    assert e_mean < tol_mean and e_var < TOL_VAR
+    assert mixed_err(gp.predict_mean_batched(Xq), v[p + "mean_batched"], y_std) < tol_mean
+    assert mixed_err(gp.predict_var_batched(Xq), v[p + "var_batched"], y_std ** 2) < TOL_VAR
+    assert abs(float(gp.predict_mean_single(Xq[3])) - float(v[p + "mean_single"])) < tol_mean * max(abs(float(v[p + "mean_single"])), y_std)
+    assert abs(float(gp.predict_var_single(Xq[3])) - float(v[p + "var_single"])) < TOL_VAR * y_std ** 2
+    ms, vs = gp.predict_batched(Xq)
+    assert mixed_err(np.ravel(ms), v[p + "std_mean_batched"], 1.0) < tol_mean
+    assert mixed_err(np.ravel(vs), v[p + "std_var_batched"], 1.0) < TOL_VAR
+    # kernel matrices / distances of the free functions
+    Kx = ops.kernel_matrix(kern, T(X), T(Xq), T(ls), float(v[p + "kv"]), float(v[p + "noise"]), False).cpu().numpy()
+    assert Kx.shape == (n, Xq.shape[0])
+    # log marginal likelihood: value against the reference's neg_mll, gradient against its central differences
+    lp = v[p + "log_params"]
+    val, grad = gp.neg_mll_and_grad_batched(lp)
+    e_mll = float(np.max(np.abs(val - v[p + "neg_mll"]) / np.maximum(np.abs(v[p + "neg_mll"]), n)))
+    assert e_mll < tol_mll
+    for r in range(lp.shape[0]):
+        assert np.max(np.abs(grad[r] - v[p + "neg_mll_fd_grad"][r])) < (2e-3 if ill else 2e-5) * max(1.0, float(np.max(np.abs(grad[r]))))
+    # fantasy variance and the integrated acquisitions
+    mc, cand = v[p + "mc"], v[p + "cand"]
+    fv = gp.fantasy_var(cand, mc)
+    e_fv = mixed_err(fv, v[p + "fantasy_var"], y_std ** 2)
+    assert e_fv < TOL_VAR
+    assert mixed_err(gp.fantasy_acquisition(mc, cand, std=False), v[p + "wipv"], y_std ** 2) < TOL_VAR
+    assert mixed_err(gp.fantasy_acquisition(mc, cand, std=True), v[p + "wipstd"], y_std) < TOL_VAR
+    # EI / LogEI (negated), where the variance is not at the noise floor (see test_golden_parity)
+    xe, best_y, zeta = v[p + "ei_x"], float(v[p + "ei_best_y"]), float(v[p + "ei_zeta"])
+    ei, lei = EI().fun_batched(xe, gp, best_y, zeta), LogEI().fun_batched(xe, gp, best_y, zeta)
+    assert mixed_err(ei, v[p + "ei"], max(float(np.max(np.abs(v[p + "ei"]))), 1e-12)) < 1e-6
+    _, vs_e = gp.predict_batched(xe)
+    ok = np.ravel(vs_e) > 1e-4
+    assert (ill or ok.any()) and ((not ok.any()) or mixed_err(np.asarray(lei)[ok], v[p + "logei"][ok], 1.0) < 1e-6)
+    # (at the dense shape every variance sits near the floor: log EI ~ -u^2 / 2 ~ 1e8 there carries the variance's relative
+    # error; it is compared in relative terms)
+    assert np.max(np.abs(np.asarray(lei) - v[p + "logei"]) / np.maximum(1.0, np.abs(v[p + "logei"]))) < (1e-3 if ill else 1e-6)
+    print(f"\n[reference source, {p}] mean {e_mean:.1e} var {e_var:.1e} neg_mll {e_mll:.1e} fantasy {e_fv:.1e}")
+    # update(): two new points and one duplicate
+    gp.update(v[p + "upd_new_x"], v[p + "upd_new_y"])
+    assert np.asarray(gp.train_x).shape == v[p + "upd_train_x"].shape and np.array_equal(np.asarray(gp.train_x), v[p + "upd_train_x"])
+    assert abs(gp.y_mean - float(v[p + "upd_y_mean"])) <= 1e-14 * abs(gp.y_mean) and abs(gp.y_std - float(v[p + "upd_y_std"])) <= 1e-14 * gp.y_std
+    if p + "upd_cholesky" in v.files:
+        assert mixed_err(np.asarray(gp.cholesky), v[p + "upd_cholesky"], 1.0) < 1e-11
+    assert mixed_err(gp.predict_mean_batched(Xq[:6]), v[p + "upd_mean_batched"], float(v[p + "upd_y_std"])) < tol_mean
+
+
+def test_cuda_free_functions_match_the_reference_source_vectors():
+    """dist_sq / rbf_kernel / matern_kernel / kernel_diag / gp_mll / fast_update_cholesky (BOBE/gp.py:80-197) through the
+    C-ABI against the reference source's own outputs."""
+    import bobe_b200 as B
+    from bobe_b200 import ops
+    v = np.load(os.path.join(GOLDEN_DIR, "reference_source_vectors.npz"))
+    xa, xb, ls, kv, noise = v["k_xa"], v["k_xb"], v["k_ls"], float(v["k_kv"]), float(v["k_noise"])
+    assert mixed_err(np.asarray(B.dist_sq(xa, xb)), v["k_dist_sq"], 1.0) < 1e-14
+    for kern in ("rbf", "matern"):
+        cross = ops.kernel_matrix(kern, T(xa), T(xb), T(ls), kv, noise, False).cpu().numpy()
+        square = ops.kernel_matrix(kern, T(xa), T(xa), T(ls), kv, noise, True).cpu().numpy()
+        assert mixed_err(cross, v[f"k_{kern}_cross"], 1.0) < 1e-13 and mixed_err(square, v[f"k_{kern}_square"], 1.0) < 1e-13
+        got = float(B.gp_mll(v[f"mll_{kern}_K"], v["mll_y_std"], 60))
+        assert abs(got - float(v[f"mll_{kern}_value"])) < TOL_MLL * max(abs(float(v[f"mll_{kern}_value"])), 60)
+    assert np.array_equal(np.asarray(B.kernel_diag(xa, kv, noise, True)), v["k_diag_noise"])
+    newL = ops.chol_append(T(v["chol_L"]), T(v["chol_k"]), float(v["chol_kself"])).cpu().numpy()
+    assert mixed_err(newL, v["chol_new_L"], 1.0) < 1e-12

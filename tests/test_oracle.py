@@ -376,3 +376,106 @@ def test_oracle_against_sklearn_gpr(kernel):
     g_or = -grad - glp  # d log p(y) / d (log l_1..d, log kv)
     assert np.allclose(g_or[:d], g_sk[1:], rtol=1e-6, atol=1e-6 * np.abs(g_sk).max())
     assert np.allclose(g_or[d], g_sk[0], rtol=1e-6, atol=1e-6 * np.abs(g_sk).max())
+
+
+# ---- the oracle against vectors produced by the REFERENCE'S OWN SOURCE (oracle/gen_reference_vectors.py) --------------------
+def _ref_vectors():
+    return np.load(os.path.join(GOLDEN_DIR, "reference_source_vectors.npz"))
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300))
+
+
+def test_oracle_kernels_match_the_reference_source():
+    """dist_sq / kernel_diag / rbf_kernel / matern_kernel / gp_mll / fast_update_cholesky: BOBE/gp.py:80-197 executed from
+    the reference's own file (NumPy stand-in for jax.numpy) vs the restatement -- the same float64 operations, so the
+    agreement is at the last bits."""
+    v = _ref_vectors()
+    xa, xb, ls, kv, noise = v["k_xa"], v["k_xb"], v["k_ls"], float(v["k_kv"]), float(v["k_noise"])
+    assert np.array_equal(O.dist_sq(xa, xb), v["k_dist_sq"])
+    assert _rel(O.rbf_kernel(xa, xb, ls, kv, noise, False), v["k_rbf_cross"]) < 1e-15
+    assert _rel(O.matern_kernel(xa, xb, ls, kv, noise, False), v["k_matern_cross"]) < 1e-15
+    assert _rel(O.rbf_kernel(xa, xa, ls, kv, noise, True), v["k_rbf_square"]) < 1e-15
+    assert _rel(O.matern_kernel(xa, xa, ls, kv, noise, True), v["k_matern_square"]) < 1e-15
+    assert np.array_equal(O.kernel_diag(xa, kv, noise, True), v["k_diag_noise"])
+    assert np.array_equal(O.kernel_diag(xa, kv, noise, False), v["k_diag_plain"])
+    for kern in ("rbf", "matern"):
+        got = O.gp_mll(v[f"mll_{kern}_K"], v["mll_y_std"], 60)
+        assert abs(got - float(v[f"mll_{kern}_value"])) < 1e-11 * abs(float(v[f"mll_{kern}_value"]))
+    newL = O.fast_update_cholesky(v["chol_L"], v["chol_k"], float(v["chol_kself"]))
+    assert _rel(newL, v["chol_new_L"]) < 1e-14 and np.array_equal(np.triu(newL, 1), np.zeros_like(newL))
+
+
+@pytest.mark.parametrize("p,kern", [("gp_rbf_", "rbf"), ("gp_matern_", "matern"), ("gpB_rbf_", "rbf")])
+def test_oracle_gp_class_matches_the_reference_source(p, kern):
+    """class GP of the reference (constructor, standardisation, Cholesky + alphas, every predict variant, neg_mll with its
+    default priors, fantasy_var, WIPV / WIPStd / EI / LogEI values, update with a duplicate) vs OracleGP on the same inputs."""
+    v = _ref_vectors()
+    X, y, ls, Xq = v[p + "X"], v[p + "y"], v[p + "ls"], v[p + "Xq"]
+    d = X.shape[1]
+    gp = O.OracleGP(X, y[:, None], noise=float(v[p + "noise"]), kernel=kern, lengthscales=ls, kernel_variance=float(v[p + "kv"]))
+    assert abs(gp.y_mean - float(v[p + "y_mean"])) < 1e-14 * abs(gp.y_mean) and abs(gp.y_std - float(v[p + "y_std"])) < 1e-14 * gp.y_std
+    assert _rel(gp.train_y, v[p + "train_y"]) < 1e-14
+    condL = float(v[p + "cond_L"])
+    if p + "cholesky" in v.files:
+        assert _rel(gp.cholesky, v[p + "cholesky"]) < 1e-15 * condL
+    assert abs(float(np.sum(np.log(np.diag(gp.cholesky)))) - float(v[p + "logdet_half"])) < 1e-14 * condL * X.shape[0]
+    assert _rel(gp.alphas, v[p + "alphas"]) < 1e-15 * condL ** 2
+    scale = max(abs(float(v[p + "y_mean"])), float(v[p + "y_std"]))
+    amp = float(np.abs(v[p + "alphas"]).max())  # the mean is a sum of ~n terms of size alpha: rounding ~ n eps |alpha|
+    tol_mean = 200 * 2.3e-16 * amp * float(v[p + "y_std"]) + 1e-15 * scale
+    assert np.max(np.abs(gp.predict_mean_batched(Xq) - v[p + "mean_batched"])) < tol_mean
+    prior_var = float(v[p + "y_std"]) ** 2 * float(v[p + "kv"])
+    tol_var = 1e-15 * condL ** 2 * prior_var
+    assert np.max(np.abs(gp.predict_var_batched(Xq) - v[p + "var_batched"])) < tol_var
+    assert abs(float(gp.predict_mean_single(Xq[3])) - float(v[p + "mean_single"])) < tol_mean
+    assert abs(float(gp.predict_var_single(Xq[3])) - float(v[p + "var_single"])) < tol_var
+    ms, vs = gp.predict_batched(Xq)
+    assert np.max(np.abs(np.ravel(ms) - v[p + "std_mean_batched"])) < tol_mean / float(v[p + "y_std"]) + 1e-15
+    assert np.max(np.abs(np.ravel(vs) - v[p + "std_var_batched"])) < tol_var / float(v[p + "y_std"]) ** 2
+    assert float(v[p + "var_batched"][0]) < 1e-4 * prior_var  # (the query that is a training point)
+    # log marginal likelihood with the default (Uniform) priors, and the analytic gradient against the reference's
+    # neg_mll differenced centrally (jax autodiff is not available under the stand-in)
+    lp = v[p + "log_params"]
+    for r in range(lp.shape[0]):
+        val, grad = gp.neg_mll_and_grad(lp[r])
+        assert abs(val - float(v[p + "neg_mll"][r])) < 1e-10 * max(1.0, abs(val)), (r, val, float(v[p + "neg_mll"][r]))
+        assert abs(float(gp.neg_mll(lp[r])) - val) < 1e-12 * max(1.0, abs(val))
+        fd_tol = 2e-5 if condL < 1e4 else 2e-3  # (differences of a value that carries cond(K) eps of noise)
+        assert np.max(np.abs(grad - v[p + "neg_mll_fd_grad"][r])) < fd_tol * max(1.0, float(np.max(np.abs(grad))))
+    # fantasy variance, integrated acquisitions, EI / LogEI
+    mc, cand = v[p + "mc"], v[p + "cand"]
+    k_train_mc = gp.kernel(gp.train_x, mc, gp.lengthscales, gp.kernel_variance, gp.noise, False)
+    fv = np.stack([gp.fantasy_var(c, mc, k_train_mc) for c in cand])
+    assert np.max(np.abs(fv - v[p + "fantasy_var"])) < tol_var
+    assert np.max(np.abs(fv.mean(axis=1) - v[p + "wipv"])) < tol_var
+    assert np.max(np.abs(np.sqrt(fv).mean(axis=1) - v[p + "wipstd"])) < tol_var / np.sqrt(float(np.min(v[p + "fantasy_var"])))
+    assert np.max(np.abs(O.wipv_values(gp, cand, mc) - v[p + "wipv"])) < tol_var
+    assert np.max(np.abs(gp.fantasy_var_shared(cand, mc) - v[p + "fantasy_var"])) < 10 * tol_var
+    xe, best_y, zeta = v[p + "ei_x"], float(v[p + "ei_best_y"]), float(v[p + "ei_zeta"])
+    mu, var = gp.predict_batched(xe)
+    ei, logei = O.ei_values(np.ravel(mu), np.ravel(var), best_y, zeta), O.logei_values(np.ravel(mu), np.ravel(var), best_y, zeta)
+    assert np.max(np.abs(ei - v[p + "ei"])) < 1e-9 * max(1e-300, float(np.max(np.abs(v[p + "ei"])))) + 1e-13
+    # (log EI ~ -u^2 / 2 with u^2 ~ 1 / var: it carries the RELATIVE error of a variance near the noise floor)
+    assert np.max(np.abs(logei - v[p + "logei"]) / np.maximum(1.0, np.abs(v[p + "logei"]))) < max(1e-8, 1e-16 * condL ** 2)
+    # update(): two new points, one duplicate (BOBE/gp.py:495-541)
+    gp.update(v[p + "upd_new_x"], v[p + "upd_new_y"])
+    assert gp.train_x.shape == v[p + "upd_train_x"].shape and np.array_equal(gp.train_x, v[p + "upd_train_x"])
+    assert abs(gp.y_mean - float(v[p + "upd_y_mean"])) < 1e-14 * abs(gp.y_mean) and abs(gp.y_std - float(v[p + "upd_y_std"])) < 1e-14 * gp.y_std
+    condU = float(v[p + "upd_cond_L"])
+    assert _rel(gp.alphas, v[p + "upd_alphas"]) < 1e-15 * condU ** 2
+    if p + "upd_cholesky" in v.files:
+        assert _rel(gp.cholesky, v[p + "upd_cholesky"]) < 1e-15 * condU
+    d_alpha = float(np.max(np.abs(gp.alphas - v[p + "upd_alphas"])))  # (the mean is k*^T alpha: it inherits alpha's rounding)
+    assert np.max(np.abs(gp.predict_mean_batched(Xq[:6]) - v[p + "upd_mean_batched"])) < 10 * tol_mean + X.shape[0] * d_alpha * gp.y_std
+
+
+def test_oracle_logei_helper_matches_the_reference_source():
+    """BOBE/acquisition.py:21-75 over its three branches (u > -1, asymptotic, u < -1e6)."""
+    v = _ref_vectors()
+    u = v["logei_u"]
+    got, want = O.log_ei_helper(u), v["logei_helper"]
+    assert np.all(np.isfinite(want)) and np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want))) < 1e-13
+    assert np.max(np.abs(O._ei_helper(u) - v["ei_helper"])) < 1e-15 * float(np.max(np.abs(v["ei_helper"])))
