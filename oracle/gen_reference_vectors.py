@@ -220,7 +220,10 @@ def load_reference():
     load("BOBE.optim", "optim.py")
     gp = load("BOBE.gp", "gp.py")
     acq = load("BOBE.acquisition", "acquisition.py")
-    return gp, acq
+    clf = load("BOBE.clf", "clf.py")  # (scikit-learn's SVC is installed; flax / optax are absent: SVM only, as in the product)
+    clf_gp = load("BOBE.clf_gp", "clf_gp.py")
+    clf_gp.svm_predict = clf.svm_predict
+    return gp, acq, clf_gp
 
 
 # ---- the cases ------------------------------------------------------------------------------------------------------
@@ -234,7 +237,7 @@ def _training_set(rng, n, d):
 
 
 def generate():
-    G, A = load_reference()
+    G, A, C = load_reference()
     rng = np.random.default_rng(20261018)
     out = {}
 
@@ -335,6 +338,29 @@ def generate():
                     p + "upd_mean_batched": np.asarray(gp.predict_mean_batched(Xq[:6]))})
         if store_factor:
             out[p + "upd_cholesky"] = np.asarray(gp.cholesky)
+
+    # GPwithClassifier with the SVM mask (BOBE/clf_gp.py, BOBE/clf.py:36-83,188-214): a target with a deep infeasible region
+    n, d, m = 120, 3, 60
+    X = rng.uniform(0, 1, (n, d))
+    y = -60.0 * np.sum((X - 0.5) ** 2, axis=1) + 0.5 * np.sin(5.0 * X[:, 1])
+    cgp = C.GPwithClassifier(X, y[:, None], clf_type="svm", clf_use_size=10, clf_threshold=8.0, gp_threshold=16.0, noise=1e-6,
+                             kernel="rbf", lengthscales=np.array([0.4, 0.5, 0.6]), kernel_variance=1.2,
+                             lengthscale_prior={"name": "Uniform", "low": 0.01, "high": 5.0})
+    Xq = rng.uniform(0, 1, (m, d))
+    assert cgp.use_clf and cgp._clf_predict_func is not None
+    cm, cv = cgp.predict_batched(Xq)
+    mask = np.array([float(cgp._clf_predict_func(x)) for x in Xq])
+    assert 0 < mask.sum() < m  # both sides of the mask are exercised
+    out.update(clf_X=X, clf_y=y, clf_Xq=Xq, clf_ls=np.array([0.4, 0.5, 0.6]), clf_kv=1.2, clf_noise=1e-6,
+               clf_threshold=8.0, clf_gp_threshold=16.0, clf_minus_inf=cgp.minus_inf,
+               clf_gp_train_x=np.asarray(cgp.train_x), clf_y_mean=np.float64(cgp.y_mean), clf_y_std=np.float64(cgp.y_std),
+               clf_support_vectors=np.asarray(cgp.clf_params["support_vectors"]), clf_dual_coef=np.asarray(cgp.clf_params["dual_coef"]),
+               clf_intercept=cgp.clf_params["intercept"], clf_gamma=cgp.clf_params["gamma_eff"],
+               clf_decision=np.array([float(C.svm_predict(x, cgp.clf_params["support_vectors"], cgp.clf_params["dual_coef"],
+                                                          cgp.clf_params["intercept"], cgp.clf_params["gamma_eff"])) for x in Xq]),
+               clf_mask=mask, clf_mean_batched=np.asarray(cgp.predict_mean_batched(Xq)),
+               clf_var_batched=np.asarray(cgp.predict_var_batched(Xq)),
+               clf_std_mean_batched=np.asarray(cm).reshape(-1), clf_std_var_batched=np.asarray(cv).reshape(-1))
 
     # the LogEI helper over its three branches (u > -1, the asymptotic branch, and u < -1e6)
     u = np.concatenate([np.linspace(-40.0, 5.0, 91), -np.logspace(2, 7.5, 12)])

@@ -1048,3 +1048,26 @@ def test_cuda_free_functions_match_the_reference_source_vectors():
     assert np.array_equal(np.asarray(B.kernel_diag(xa, kv, noise, True)), v["k_diag_noise"])
     newL = ops.chol_append(T(v["chol_L"]), T(v["chol_k"]), float(v["chol_kself"])).cpu().numpy()
     assert mixed_err(newL, v["chol_new_L"], 1.0) < 1e-12
+
+
+def test_cuda_svm_mask_matches_the_reference_source_vectors():
+    """GPwithClassifier(clf_type='svm') through the product's class (bobe_svm_mask + the predict kernels) against what the
+    reference's own BOBE/clf_gp.py computed for the same data and settings (oracle/gen_reference_vectors.py)."""
+    from bobe_b200 import GPwithClassifier
+    v = np.load(os.path.join(GOLDEN_DIR, "reference_source_vectors.npz"))
+    X, y, Xq = v["clf_X"], v["clf_y"], v["clf_Xq"]
+    gp = GPwithClassifier(X, y[:, None], clf_type="svm", clf_use_size=10, clf_threshold=float(v["clf_threshold"]),
+                          gp_threshold=float(v["clf_gp_threshold"]), noise=float(v["clf_noise"]), kernel="rbf",
+                          lengthscales=v["clf_ls"], kernel_variance=float(v["clf_kv"]),
+                          lengthscale_prior={"name": "Uniform", "low": 0.01, "high": 5.0})
+    assert gp.use_clf and np.array_equal(np.asarray(gp.train_x), v["clf_gp_train_x"])
+    assert np.allclose(np.asarray(gp.clf_params["support_vectors"]), v["clf_support_vectors"])
+    assert np.allclose(np.asarray(gp.clf_params["dual_coef"]), v["clf_dual_coef"], rtol=1e-9)
+    y_std = float(v["clf_y_std"])
+    mean, var = gp.predict_mean_batched(Xq), gp.predict_var_batched(Xq)
+    feasible = v["clf_mask"] > 0
+    assert np.array_equal(np.asarray(mean) == float(v["clf_minus_inf"]), ~feasible)  # the same points are masked
+    assert mixed_err(mean, v["clf_mean_batched"], y_std) < TOL_MEAN and mixed_err(var, v["clf_var_batched"], y_std ** 2) < TOL_VAR
+    ms, vs = gp.predict_batched(Xq)
+    assert mixed_err(np.ravel(ms), v["clf_std_mean_batched"], 1.0) < TOL_MEAN
+    assert mixed_err(np.ravel(vs), v["clf_std_var_batched"], 1.0) < TOL_VAR

@@ -479,3 +479,30 @@ def test_oracle_logei_helper_matches_the_reference_source():
     got, want = O.log_ei_helper(u), v["logei_helper"]
     assert np.all(np.isfinite(want)) and np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want))) < 1e-13
     assert np.max(np.abs(O._ei_helper(u) - v["ei_helper"])) < 1e-15 * float(np.max(np.abs(v["ei_helper"])))
+
+
+def test_oracle_svm_mask_matches_the_reference_source():
+    """GPwithClassifier(clf_type='svm') of the reference (BOBE/clf_gp.py:16-205, BOBE/clf.py:36-83,188-214): the SVM decision
+    function, the mask, and the masked mean / variance in both scalings vs the restatement, with the reference's own trained
+    classifier parameters."""
+    v = _ref_vectors()
+    X, y, Xq = v["clf_X"], v["clf_y"], v["clf_Xq"]
+    keep = y > y.max() - float(v["clf_gp_threshold"])  # BOBE/clf_gp.py:84-90
+    assert np.array_equal(X[keep], v["clf_gp_train_x"])
+    gp = O.OracleGP(X[keep], y[keep][:, None], noise=float(v["clf_noise"]), kernel="rbf", lengthscales=v["clf_ls"],
+                    kernel_variance=float(v["clf_kv"]))
+    assert abs(gp.y_mean - float(v["clf_y_mean"])) < 1e-13 * abs(gp.y_mean) and abs(gp.y_std - float(v["clf_y_std"])) < 1e-13 * gp.y_std
+    params = {"support_vectors": v["clf_support_vectors"], "dual_coef": v["clf_dual_coef"], "intercept": float(v["clf_intercept"]),
+              "gamma_eff": float(v["clf_gamma"])}
+    dec = O.svm_decision(Xq, params["support_vectors"], params["dual_coef"], params["intercept"], params["gamma_eff"])
+    assert np.max(np.abs(dec - v["clf_decision"])) < 1e-9 * max(1.0, float(np.max(np.abs(v["clf_decision"]))))
+    assert np.array_equal((dec >= 0).astype(float), v["clf_mask"]) and 0 < v["clf_mask"].sum() < Xq.shape[0]
+    m, var, _ = O.clf_masked_predict(gp, Xq, params, minus_inf=float(v["clf_minus_inf"]))
+    assert mixed_err(m, v["clf_mean_batched"], gp.y_std) < 1e-11 and mixed_err(var, v["clf_var_batched"], gp.y_std ** 2) < 1e-11
+    ms, vs, _ = O.clf_masked_predict(gp, Xq, params, minus_inf=float(v["clf_minus_inf"]), standardised=True)
+    assert mixed_err(np.ravel(ms), v["clf_std_mean_batched"], 1.0) < 1e-11 and mixed_err(vs, v["clf_std_var_batched"], 1.0) < 1e-11
+    # the same classifier comes out of scikit-learn when trained here on the reference's labels (BOBE/clf_gp.py:143-147)
+    from sklearn.svm import SVC
+    labels = np.where(y < y.max() - float(v["clf_threshold"]), 0, 1)
+    clf = SVC(kernel="rbf", gamma="scale", C=1e7).fit(X, labels)
+    assert np.allclose(clf.support_vectors_, v["clf_support_vectors"]) and np.allclose(clf.dual_coef_[0], v["clf_dual_coef"])
