@@ -9,7 +9,9 @@ helpers they import: ``optim.py``, ``utils/core.py``, ``utils/log.py``, ``utils/
     jax.scipy.linalg     -> scipy.linalg (cho_solve, solve_triangular: the same LAPACK routines XLA's CPU backend calls)
     jax.scipy.stats.norm -> scipy.stats.norm
     jax.jit              -> identity;   jax.vmap / lax.map -> a Python loop over the leading axis
-    jax.value_and_grad   -> not available (gradients are NOT pinned by this route: see below)
+    jax.value_and_grad   -> not available under NumPy; BOBE/gp.py is therefore loaded a SECOND time with jax.numpy ->
+                            torch float64 tensors (load_reference_autodiff), where jax.value_and_grad(gp.neg_mll) runs as
+                            reverse-mode autodiff through the reference's own statements
     numpyro.distributions.Uniform.log_prob -> -log(high - low)   (the only prior the default GP constructs)
     tensorflow_probability...math.erfcx / log1mexp -> scipy.special.erfcx / log(1 - exp(-|x|)) (TFP's documented definition)
 
@@ -19,9 +21,10 @@ variants, duplicate handling in ``update``, the fantasy variance, EI / LogEI / W
 by the reference's authors, in float64, on seeded inputs; the outputs are stored next to the inputs in
 ``tests/golden/reference_source_vectors.npz``.  ``tests/test_oracle.py`` checks the oracle restatement against them and
 ``tests/test_gpu_parity.py`` checks the CUDA path against them.
-What it does NOT pin: XLA's own floating-point behaviour (fusion, its Cholesky kernel) -- rounding-level differences -- and
-anything that needs autodiff (``jax.value_and_grad``): for the log-ML gradient the file stores central differences of the
-reference's ``neg_mll`` (accurate to ~1e-7), a sanity bound, not a bitwise pin.
+The log-ML gradient -- what ``jax.value_and_grad`` gives the optimisers at BOBE/optim.py:118,211,309 -- comes from the
+torch-backed load (``neg_mll_ad_grad``), with central differences of the NumPy-run ``neg_mll`` stored beside it.
+What it does NOT pin: XLA's own floating-point behaviour (fusion, its Cholesky kernel and that kernel's derivative rule) --
+rounding-level differences -- and the numpyro priors other than Uniform.
 
     python oracle/gen_reference_vectors.py            # writes tests/golden/reference_source_vectors.npz
 """
@@ -226,6 +229,114 @@ def load_reference():
     return gp, acq, clf_gp
 
 
+# ---- a second stand-in, backed by torch, for the one thing NumPy cannot do: jax.value_and_grad ------------------------
+def load_reference_autodiff():
+    """BOBE/gp.py loaded a second time (package name BOBE_ad) with jax.numpy -> torch float64 tensors, so that
+    ``jax.value_and_grad(gp.neg_mll)`` -- what BOBE/optim.py:118,211,309 differentiates -- runs as reverse-mode autodiff
+    through the reference's own statements (kernel, Cholesky, cho_solve, log-determinant)."""
+    import math
+
+    import torch
+
+    f64 = torch.float64
+
+    def as_t(x, dtype=None):
+        if isinstance(x, torch.Tensor):
+            return x
+        return torch.as_tensor(np.asarray(x, dtype=np.float64) if not isinstance(x, (int, float)) else x, dtype=f64)
+
+    jnp = types.ModuleType("jax.numpy")
+    jnp.ndarray, jnp.float64, jnp.float32, jnp.pi = torch.Tensor, f64, torch.float32, math.pi
+    jnp.array = jnp.asarray = as_t
+    jnp.ones = lambda *shape, **k: torch.ones(*shape, dtype=f64)
+    jnp.zeros = lambda *shape, **k: torch.zeros(*shape, dtype=f64)
+    jnp.eye = lambda n, **k: torch.eye(n, dtype=f64)
+    for name in ("exp", "log", "sqrt", "square", "abs", "isnan", "diag", "dot", "vstack", "hstack", "concatenate", "isclose"):
+        setattr(jnp, name, (lambda fn: (lambda *a, **k: fn(*[as_t(x) if not isinstance(x, (list, tuple)) else x for x in a], **k)))(
+            getattr(torch, name if name != "concatenate" else "cat")))
+    jnp.sum = lambda x, axis=None: torch.sum(as_t(x)) if axis is None else torch.sum(as_t(x), dim=axis)
+    # (standardisation constants of NumPy training data stay NumPy scalars: ``ndarray - Tensor`` is not defined)
+    jnp.mean = lambda x, axis=None: float(np.mean(x)) if isinstance(x, np.ndarray) else torch.mean(x)
+    jnp.std = lambda x, axis=None: float(np.std(x)) if isinstance(x, np.ndarray) else torch.std(x, correction=0)
+    jnp.any, jnp.all = (lambda x, axis=None: torch.any(x) if axis is None else torch.any(x, dim=axis)), \
+        (lambda x, axis=None: torch.all(x) if axis is None else torch.all(x, dim=axis))
+    jnp.where = lambda c, a, b: torch.where(c, as_t(a), as_t(b))
+    jnp.clip = lambda a, a_min=None, a_max=None: torch.clamp(a, min=a_min, max=a_max)
+    jnp.atleast_2d = lambda x: torch.atleast_2d(as_t(x))
+    jnp.einsum = lambda spec, *ops: torch.einsum(spec if "->" in spec else spec + "->", *[as_t(o) for o in ops])
+    jnp.linalg = types.SimpleNamespace(cholesky=torch.linalg.cholesky)
+
+    def cho_solve(c_and_lower, b):
+        L, lower = c_and_lower
+        b = as_t(b)
+        return torch.cholesky_solve(b if b.ndim == 2 else b[:, None], L, upper=not lower)
+
+    def solve_triangular(a, b, lower=False):
+        b2 = b if b.ndim == 2 else b[:, None]
+        out = torch.linalg.solve_triangular(a, b2, upper=not lower)
+        return out if b.ndim == 2 else out[:, 0]
+
+    def value_and_grad(fn):
+        def vg(x, *a, **k):
+            xt = torch.tensor(np.asarray(x, dtype=np.float64), dtype=f64, requires_grad=True)
+            val = fn(xt, *a, **k)
+            (g,) = torch.autograd.grad(val, xt)
+            return float(val.detach()), g.numpy().copy()
+        return vg
+
+    jax = types.ModuleType("jax")
+    jax.__path__ = []
+    jax.numpy, jax.jit, jax.vmap, jax.value_and_grad, jax.Array = jnp, _jit, _vmap, value_and_grad, torch.Tensor
+    jax.config = types.SimpleNamespace(update=lambda *a, **k: None)
+    rnd = types.ModuleType("jax.random")
+    rnd.PRNGKey = lambda seed: seed
+    jax.random = rnd
+    jsp, jsl = types.ModuleType("jax.scipy"), types.ModuleType("jax.scipy.linalg")
+    jsp.__path__ = []
+    jsl.cho_solve, jsl.solve_triangular = cho_solve, solve_triangular
+    jsp.linalg = jsl
+    jax.scipy = jsp
+    dist = types.ModuleType("numpyro.distributions")
+
+    class Distribution:
+        pass
+
+    class Uniform(Distribution):
+        def __init__(self, low=0.0, high=1.0):
+            self.low, self.high = low, high
+
+        def log_prob(self, x):
+            return -math.log(self.high - self.low) + 0.0 * x
+    dist.Distribution, dist.Uniform = Distribution, Uniform
+    numpyro = types.ModuleType("numpyro")
+    numpyro.__path__ = []
+    numpyro.distributions = dist
+    saved = {k: sys.modules.get(k) for k in ("jax", "jax.numpy", "jax.random", "jax.scipy", "jax.scipy.linalg", "numpyro",
+                                             "numpyro.distributions")}
+    sys.modules.update({"jax": jax, "jax.numpy": jnp, "jax.random": rnd, "jax.scipy": jsp, "jax.scipy.linalg": jsl,
+                        "numpyro": numpyro, "numpyro.distributions": dist})
+    try:
+        pkg = types.ModuleType("BOBE_ad")
+        pkg.__path__ = [os.path.join(REF, "BOBE")]
+        utils = types.ModuleType("BOBE_ad.utils")
+        utils.__path__ = [os.path.join(REF, "BOBE", "utils")]
+        optim = types.ModuleType("BOBE_ad.optim")  # gp.py only takes two names from it at import time
+        optim.optimize_optax = optim.optimize_scipy = None
+        sys.modules.update({"BOBE_ad": pkg, "BOBE_ad.utils": utils, "BOBE_ad.optim": optim})
+        mods = {}
+        for name, rel in (("BOBE_ad.utils.log", "utils/log.py"), ("BOBE_ad.utils.seed", "utils/seed.py"), ("BOBE_ad.gp", "gp.py")):
+            spec = importlib.util.spec_from_file_location(name, os.path.join(REF, "BOBE", rel))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[name] = mod
+            spec.loader.exec_module(mod)
+            mods[name] = mod
+    finally:
+        for k, m in saved.items():
+            if m is not None:
+                sys.modules[k] = m
+    return mods["BOBE_ad.gp"], jax
+
+
 # ---- the cases ------------------------------------------------------------------------------------------------------
 def _objective(X):
     return -0.5 * np.sum(((X - 0.45) / 0.2) ** 2, axis=1) + 0.3 * np.sin(7.0 * X[:, 0]) + 12.5
@@ -238,6 +349,7 @@ def _training_set(rng, n, d):
 
 def generate():
     G, A, C = load_reference()
+    G_ad, jax_ad = load_reference_autodiff()
     rng = np.random.default_rng(20261018)
     out = {}
 
@@ -310,6 +422,13 @@ def generate():
                 fd[r, j] = (float(gp.neg_mll(lp[r] + e)) - float(gp.neg_mll(lp[r] - e))) / (2 * h)
         prior_const = float(gp.prior_func(np.exp(lp[0, :d]), np.exp(lp[0, d]), 1.0))
         out.update({p + "log_params": lp, p + "neg_mll": vals, p + "neg_mll_fd_grad": fd, p + "prior_const": np.float64(prior_const)})
+        # ... and jax.value_and_grad(neg_mll) as BOBE/optim.py:307-309 builds it, run as reverse-mode autodiff through the
+        # reference's own statements (torch-backed stand-in)
+        import torch
+        gp_ad = G_ad.GP(X, y[:, None], noise=noise_g, kernel=kern, lengthscales=torch.as_tensor(lsg), kernel_variance=kvg)
+        vg = jax_ad.value_and_grad(gp_ad.neg_mll)
+        ad = [vg(r) for r in lp]
+        out.update({p + "neg_mll_ad": np.array([a[0] for a in ad]), p + "neg_mll_ad_grad": np.stack([a[1] for a in ad])})
 
         # fantasy variance and the two integrated acquisitions
         mc = rng.uniform(0, 1, (50, d))

@@ -17,9 +17,11 @@ PINNING.  The reference is pure Python/JAX; JAX, numpyro and tensorflow-probabil
    values, at two well-conditioned shapes and at BASELINE config B's worst-conditioned one -- in
    ``tests/golden/reference_source_vectors.npz``.  ``tests/test_oracle.py`` holds this restatement to those vectors (the
    factor and the kernels agree bit for bit, everything else to ~1e-14 x cond), and ``tests/test_gpu_parity.py`` holds the
-   CUDA path to them.  NOT pinned by this route: XLA's own floating-point behaviour (rounding-level) and autodiff
-   (``jax.value_and_grad``: the stand-in has none; the file carries central differences of the reference's neg_mll instead),
-   and the numpyro priors other than Uniform (tests/test_host_logic.py checks those against closed forms).
+   CUDA path to them.  The log-ML GRADIENT is pinned the same way: gp.py is loaded a second time with jax.numpy -> torch
+   float64 tensors, where ``jax.value_and_grad(gp.neg_mll)`` (BOBE/optim.py:307-309) runs as reverse-mode autodiff through
+   the reference's own statements; the analytic gradient below agrees with it to 1e-12 .. 3e-10 (9e-8 at cond(K) ~ 1e10).
+   NOT pinned by this route: XLA's own floating-point behaviour (rounding-level) and the numpyro priors other than Uniform
+   (tests/test_host_logic.py checks those against closed forms).
 2. MATHEMATICS AND THIRD-PARTY CODE (round 1, tests/test_oracle.py): closed forms at n=1,2, interpolation / noise-level
    identities, the gradient three ways (analytic, torch autograd through ``torch.linalg.cholesky`` = the reverse-mode
    construction JAX uses, central differences), ``fantasy_var`` == ``predict_var`` of an actually-updated GP, an mpmath

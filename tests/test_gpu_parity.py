@@ -1002,6 +1002,11 @@ def test_cuda_matches_the_reference_source_vectors(p, kern):
     val, grad = gp.neg_mll_and_grad_batched(lp)
     e_mll = float(np.max(np.abs(val - v[p + "neg_mll"]) / np.maximum(np.abs(v[p + "neg_mll"]), n)))
     assert e_mll < tol_mll
+    # gradient against jax.value_and_grad(neg_mll) of the reference run as reverse-mode autodiff through its own statements
+    e_grad = max(float(np.max(np.abs(grad[r] - v[p + "neg_mll_ad_grad"][r])) / max(1.0, float(np.max(np.abs(v[p + "neg_mll_ad_grad"][r])))))
+                 for r in range(lp.shape[0]))
+    print(f"\n[reference source, {p}] gradient vs the reference's autodiff: {e_grad:.1e}")
+    assert e_grad < (3 * TOL_GRAD if ill else TOL_GRAD)
     for r in range(lp.shape[0]):
         assert np.max(np.abs(grad[r] - v[p + "neg_mll_fd_grad"][r])) < (2e-3 if ill else 2e-5) * max(1.0, float(np.max(np.abs(grad[r]))))
     # fantasy variance and the integrated acquisitions

@@ -443,6 +443,12 @@ def test_oracle_gp_class_matches_the_reference_source(p, kern):
         val, grad = gp.neg_mll_and_grad(lp[r])
         assert abs(val - float(v[p + "neg_mll"][r])) < 1e-10 * max(1.0, abs(val)), (r, val, float(v[p + "neg_mll"][r]))
         assert abs(float(gp.neg_mll(lp[r])) - val) < 1e-12 * max(1.0, abs(val))
+        # jax.value_and_grad(neg_mll) of the reference (reverse-mode autodiff through its own statements, torch-backed
+        # stand-in) vs the analytic gradient: 1e-7 (scale max|grad|), three times that at the cond(K) ~ 1e10 shape where two
+        # float64 evaluations of the same gradient differ by ~1e-7 themselves
+        ad = v[p + "neg_mll_ad_grad"][r]
+        assert abs(val - float(v[p + "neg_mll_ad"][r])) < 3e-9 * max(abs(val), X.shape[0])
+        assert np.max(np.abs(grad - ad)) < (1e-7 if condL < 1e4 else 3e-7) * max(1.0, float(np.max(np.abs(ad)))), (r,)
         fd_tol = 2e-5 if condL < 1e4 else 2e-3  # (differences of a value that carries cond(K) eps of noise)
         assert np.max(np.abs(grad - v[p + "neg_mll_fd_grad"][r])) < fd_tol * max(1.0, float(np.max(np.abs(grad))))
     # fantasy variance, integrated acquisitions, EI / LogEI
