@@ -22,7 +22,9 @@ by the reference's authors, in float64, on seeded inputs; the outputs are stored
 ``tests/golden/reference_source_vectors.npz``.  ``tests/test_oracle.py`` checks the oracle restatement against them and
 ``tests/test_gpu_parity.py`` checks the CUDA path against them.
 The log-ML gradient -- what ``jax.value_and_grad`` gives the optimisers at BOBE/optim.py:118,211,309 -- comes from the
-torch-backed load (``neg_mll_ad_grad``), with central differences of the NumPy-run ``neg_mll`` stored beside it.
+torch-backed load (``neg_mll_ad_grad``), with central differences of the NumPy-run ``neg_mll`` stored beside it; the same
+load runs the reference's ``GP.fit`` -> ``optimize_scipy`` and differentiates ``predict_single``, ``EI.fun``, ``LogEI.fun``,
+``WIPV.fun`` and ``WIPStd.fun`` in the query / candidate point.
 What it does NOT pin: XLA's own floating-point behaviour (fusion, its Cholesky kernel and that kernel's derivative rule) --
 rounding-level differences -- and the numpyro priors other than Uniform.
 
@@ -248,8 +250,34 @@ def load_reference_autodiff():
     jnp = types.ModuleType("jax.numpy")
     jnp.ndarray, jnp.float64, jnp.float32, jnp.pi = torch.Tensor, f64, torch.float32, math.pi
     jnp.array = jnp.asarray = as_t
+    class TAt:
+        def __init__(self, t):
+            self.t = t
+
+        def __getitem__(self, idx):
+            t = self.t
+
+            class _Ref:
+                def set(self, v):
+                    out = t.clone()
+                    out[idx] = v
+                    return out.as_subclass(TArray)
+            return _Ref()
+
+    class TArray(torch.Tensor):
+        """torch tensor with jax's functional update ``x.at[idx].set(v)`` (differentiable: clone + index_put)."""
+        @property
+        def at(self):
+            return TAt(self)
+
     jnp.ones = lambda *shape, **k: torch.ones(*shape, dtype=f64)
-    jnp.zeros = lambda *shape, **k: torch.zeros(*shape, dtype=f64)
+    jnp.zeros = lambda *shape, **k: torch.zeros(*shape, dtype=f64).as_subclass(TArray)
+    jnp.full = lambda shape, v, **k: as_t(v).expand(shape).clone() if isinstance(v, torch.Tensor) else torch.full(shape, v, dtype=f64)
+    jnp.reshape = lambda x, shape: torch.reshape(x, shape)
+    jnp.argmax = lambda x, axis=None: torch.argmax(as_t(x))
+    jnp.argmin = lambda x, axis=None: torch.argmin(as_t(x))
+    jnp.min = lambda x, axis=None: torch.min(as_t(x))
+    jnp.max = lambda x, axis=None: torch.max(as_t(x))
     jnp.eye = lambda n, **k: torch.eye(n, dtype=f64)
     for name in ("exp", "log", "sqrt", "square", "abs", "isnan", "diag", "dot", "vstack", "hstack", "concatenate", "isclose"):
         setattr(jnp, name, (lambda fn: (lambda *a, **k: fn(*[as_t(x) if not isinstance(x, (list, tuple)) else x for x in a], **k)))(
@@ -284,17 +312,44 @@ def load_reference_autodiff():
             return float(val.detach()), g.numpy().copy()
         return vg
 
+    def tvmap(fn, in_axes=0, out_axes=0):
+        def mapped(xs):
+            outs = [fn(x) for x in xs]
+            if isinstance(outs[0], tuple):
+                return tuple(torch.stack([o[i] for o in outs]) for i in range(len(outs[0])))
+            return torch.stack(outs)
+        return mapped
+
     jax = types.ModuleType("jax")
     jax.__path__ = []
-    jax.numpy, jax.jit, jax.vmap, jax.value_and_grad, jax.Array = jnp, _jit, _vmap, value_and_grad, torch.Tensor
+    jax.numpy, jax.jit, jax.vmap, jax.value_and_grad, jax.Array = jnp, _jit, tvmap, value_and_grad, torch.Tensor
     jax.config = types.SimpleNamespace(update=lambda *a, **k: None)
+    jax.config_module = jax.config
+    lax = types.ModuleType("jax.lax")
+    lax.map = lambda f, xs, **_k: tvmap(f)(xs)
+    jax.lax = lax
+    jss = types.ModuleType("jax.scipy.stats")
+    inv_sqrt_2pi = 1.0 / math.sqrt(2.0 * math.pi)
+    jss.norm = types.SimpleNamespace(pdf=lambda u: inv_sqrt_2pi * torch.exp(-0.5 * u * u),
+                                     cdf=lambda u: 0.5 * torch.erfc(-u / math.sqrt(2.0)))
+    tfp_root = types.ModuleType("tensorflow_probability")
+    tfp_root.__path__ = []
+    tfp_sub = types.ModuleType("tensorflow_probability.substrates")
+    tfp_sub.__path__ = []
+    tfj = types.ModuleType("tensorflow_probability.substrates.jax")
+
+    def t_log1mexp(x):  # TFP: log(1 - exp(-|x|))
+        x = torch.abs(x)
+        return torch.where(x < math.log(2.0), torch.log(-torch.expm1(-x)), torch.log1p(-torch.exp(-x)))
+    tfj.math = types.SimpleNamespace(erfcx=torch.special.erfcx, log1mexp=t_log1mexp)
+    tfp_root.substrates, tfp_sub.jax = tfp_sub, tfj
     rnd = types.ModuleType("jax.random")
     rnd.PRNGKey = lambda seed: seed
     jax.random = rnd
     jsp, jsl = types.ModuleType("jax.scipy"), types.ModuleType("jax.scipy.linalg")
     jsp.__path__ = []
     jsl.cho_solve, jsl.solve_triangular = cho_solve, solve_triangular
-    jsp.linalg = jsl
+    jsp.linalg, jsp.stats = jsl, jss
     jax.scipy = jsp
     dist = types.ModuleType("numpyro.distributions")
 
@@ -311,19 +366,23 @@ def load_reference_autodiff():
     numpyro = types.ModuleType("numpyro")
     numpyro.__path__ = []
     numpyro.distributions = dist
-    saved = {k: sys.modules.get(k) for k in ("jax", "jax.numpy", "jax.random", "jax.scipy", "jax.scipy.linalg", "numpyro",
-                                             "numpyro.distributions")}
-    sys.modules.update({"jax": jax, "jax.numpy": jnp, "jax.random": rnd, "jax.scipy": jsp, "jax.scipy.linalg": jsl,
-                        "numpyro": numpyro, "numpyro.distributions": dist})
+    names = ("jax", "jax.numpy", "jax.random", "jax.lax", "jax.scipy", "jax.scipy.linalg", "jax.scipy.stats", "numpyro",
+             "numpyro.distributions", "tensorflow_probability", "tensorflow_probability.substrates",
+             "tensorflow_probability.substrates.jax")
+    saved = {k: sys.modules.get(k) for k in names}
+    sys.modules.update(dict(zip(names, (jax, jnp, rnd, lax, jsp, jsl, jss, numpyro, dist, tfp_root, tfp_sub, tfj))))
     try:
         pkg = types.ModuleType("BOBE_ad")
         pkg.__path__ = [os.path.join(REF, "BOBE")]
         utils = types.ModuleType("BOBE_ad.utils")
         utils.__path__ = [os.path.join(REF, "BOBE", "utils")]
-        sys.modules.update({"BOBE_ad": pkg, "BOBE_ad.utils": utils})
+        samplers = types.ModuleType("BOBE_ad.samplers")
+        samplers.nested_sampling_Dy = samplers.sample_GP_NUTS = None
+        sys.modules.update({"BOBE_ad": pkg, "BOBE_ad.utils": utils, "BOBE_ad.samplers": samplers})
         mods = {}
         for name, rel in (("BOBE_ad.utils.log", "utils/log.py"), ("BOBE_ad.utils.seed", "utils/seed.py"),
-                          ("BOBE_ad.utils.core", "utils/core.py"), ("BOBE_ad.optim", "optim.py"), ("BOBE_ad.gp", "gp.py")):
+                          ("BOBE_ad.utils.core", "utils/core.py"), ("BOBE_ad.optim", "optim.py"), ("BOBE_ad.gp", "gp.py"),
+                          ("BOBE_ad.acquisition", "acquisition.py")):
             spec = importlib.util.spec_from_file_location(name, os.path.join(REF, "BOBE", rel))
             mod = importlib.util.module_from_spec(spec)
             sys.modules[name] = mod
@@ -333,7 +392,7 @@ def load_reference_autodiff():
         for k, m in saved.items():
             if m is not None:
                 sys.modules[k] = m
-    return mods["BOBE_ad.gp"], jax
+    return mods["BOBE_ad.gp"], jax, mods["BOBE_ad.acquisition"]
 
 
 # ---- the cases ------------------------------------------------------------------------------------------------------
@@ -348,7 +407,7 @@ def _training_set(rng, n, d):
 
 def generate():
     G, A, C = load_reference()
-    G_ad, jax_ad = load_reference_autodiff()
+    G_ad, jax_ad, A_ad = load_reference_autodiff()
     rng = np.random.default_rng(20261018)
     out = {}
 
@@ -452,6 +511,28 @@ def generate():
                     p + "ei": np.array([float(A.EI().fun(x, gp, best_y, zeta)) for x in xe]),
                     p + "logei": np.array([float(A.LogEI().fun(x, gp, best_y, zeta)) for x in xe])})
 
+        # jax.value_and_grad of the acquisition functions in the candidate point (what BOBE/optim.py differentiates when it
+        # polishes EI / LogEI / WIPV / WIPStd): reverse mode through predict_single / fantasy_var of the reference
+        mc_t = torch.as_tensor(mc)
+        k_train_mc_t = gp_ad.kernel(gp_ad.train_x, mc_t, gp_ad.lengthscales, gp_ad.kernel_variance, noise=gp_ad.noise,
+                                    include_noise=False)
+        xg = np.vstack([Xq[1:6], cand])  # (query points away from the training set, and the WIPV candidates)
+        acq_grads = {}
+        for name, obj, args, kwargs in (("ei", A_ad.EI(), (gp_ad, best_y, zeta), {}), ("logei", A_ad.LogEI(), (gp_ad, best_y, zeta), {}),
+                                        ("wipv", A_ad.WIPV(), (gp_ad,), {"mc_points": mc_t, "k_train_mc": k_train_mc_t}),
+                                        ("wipstd", A_ad.WIPStd(), (gp_ad,), {"mc_points": mc_t, "k_train_mc": k_train_mc_t})):
+            vg_acq = jax_ad.value_and_grad(obj.fun)
+            res_acq = [vg_acq(x, *args, **kwargs) for x in xg]
+            acq_grads[p + name + "_ad_value"] = np.array([r[0] for r in res_acq])
+            acq_grads[p + name + "_ad_grad"] = np.stack([r[1] for r in res_acq])
+        # ... and of the standardised posterior mean / variance themselves (BOBE/gp.py:476-489)
+        for name, fn in (("pmean", lambda x: jax_ad.numpy.reshape(gp_ad.predict_single(x)[0], ())),
+                         ("pvar", lambda x: jax_ad.numpy.reshape(gp_ad.predict_single(x)[1], ()))):
+            res_p = [jax_ad.value_and_grad(fn)(x) for x in xg]
+            acq_grads[p + name + "_ad_value"] = np.array([r[0] for r in res_p])
+            acq_grads[p + name + "_ad_grad"] = np.stack([r[1] for r in res_p])
+        out.update(acq_grads)
+        out[p + "acq_grad_x"] = xg
         # update(): two new points and one duplicate of a training point
         new_x = np.vstack([rng.uniform(0, 1, (2, d)), X[7][None, :]])
         new_y = np.concatenate([_objective(new_x[:2]) + np.array([0.01, -0.02]), [y[7]]])[:, None]

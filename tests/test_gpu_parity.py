@@ -1100,3 +1100,36 @@ def test_fit_matches_the_reference_source_fit(p, kern):
     # same log-ML differ in the 7th digit there: the tolerance is 1e-6, not the 1e-9 of the well-conditioned rows.)
     val, _ = gp.neg_mll_and_grad_batched(ref_par[None, :])
     assert abs(-val[0] - ref_mll) < 1e-6 * max(abs(ref_mll), v[p + "X"].shape[0])
+
+
+@pytest.mark.parametrize("p,kern", [("gp_rbf_", "rbf"), ("gp_matern_", "matern"), ("gpB_rbf_", "rbf")])
+def test_input_gradients_match_the_reference_autodiff(p, kern):
+    """bobe_predict_grad / bobe_fantasy_var_grad and the EI / LogEI chain rule against jax.value_and_grad of the reference's
+    own predict_single, EI.fun, LogEI.fun, WIPV.fun and WIPStd.fun in the query / candidate point (reverse mode through the
+    reference's statements under the torch-backed stand-in: oracle/gen_reference_vectors.py)."""
+    from bobe_b200 import GP, EI, LogEI, WIPV, WIPStd
+    v = np.load(os.path.join(GOLDEN_DIR, "reference_source_vectors.npz"))
+    gp = GP(v[p + "X"], v[p + "y"][:, None], noise=float(v[p + "noise"]), kernel=kern, lengthscales=v[p + "ls"],
+            kernel_variance=float(v[p + "kv"]))
+    xg, mc = v[p + "acq_grad_x"], v[p + "mc"]
+    ill = float(v[p + "cond_L"]) > 1e4
+    tol = 1e-5 if ill else TOL_GRAD  # relative to the largest entry (cond(K) ~ 1e10: float64 itself gives ~1e-6 there)
+
+    def rel(got, want):
+        return float(np.max(np.abs(np.asarray(got) - want))) / max(float(np.max(np.abs(want))), 1e-300)
+    m, var, dm, dv = gp.predict_grad_batched(xg, standardised=True)
+    e = {"dmean": rel(dm, v[p + "pmean_ad_grad"]), "dvar": rel(dv, v[p + "pvar_ad_grad"])}
+    best_y, zeta = float(v[p + "ei_best_y"]), float(v[p + "ei_zeta"])
+    for name, acq in (("ei", EI()), ("logei", LogEI())):
+        val, grad = acq.value_and_grad_batched(xg, gp, best_y, zeta)
+        want_v, want_g = v[p + name + "_ad_value"], v[p + name + "_ad_grad"]
+        if float(np.max(np.abs(want_g))) > 0:
+            e["d" + name] = rel(grad, want_g)
+        assert np.max(np.abs(np.asarray(val) - want_v) / np.maximum(np.abs(want_v), 1e-12 if name == "ei" else 1.0)) < (1e-3 if ill else 1e-6)
+    for name, acq in (("wipv", WIPV()), ("wipstd", WIPStd())):
+        val, grad = acq.value_and_grad_batched(xg, gp, mc_points=mc)
+        y_std = float(v[p + "y_std"])
+        assert mixed_err(val, v[p + name + "_ad_value"], y_std ** 2 if name == "wipv" else y_std) < TOL_VAR
+        e["d" + name] = rel(grad, v[p + name + "_ad_grad"])
+    print(f"\n[reference autodiff, {p}] " + "  ".join(f"{k} {x:.1e}" for k, x in e.items()))
+    assert all(x < tol for x in e.values()), e

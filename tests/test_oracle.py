@@ -512,3 +512,26 @@ def test_oracle_svm_mask_matches_the_reference_source():
     labels = np.where(y < y.max() - float(v["clf_threshold"]), 0, 1)
     clf = SVC(kernel="rbf", gamma="scale", C=1e7).fit(X, labels)
     assert np.allclose(clf.support_vectors_, v["clf_support_vectors"]) and np.allclose(clf.dual_coef_[0], v["clf_dual_coef"])
+
+
+@pytest.mark.parametrize("p,kern", [("gp_rbf_", "rbf"), ("gp_matern_", "matern"), ("gpB_rbf_", "rbf")])
+def test_oracle_input_gradients_match_the_reference_autodiff(p, kern):
+    """d/dx of the standardised posterior mean / variance (BOBE/gp.py:476-489) and of WIPV / WIPStd
+    (BOBE/acquisition.py:438-440,463-465 through GP.fantasy_var) as jax.value_and_grad yields them -- reverse mode through the
+    reference's own statements (torch-backed stand-in) -- vs the analytic forms of the restatement."""
+    v = _ref_vectors()
+    gp = O.OracleGP(v[p + "X"], v[p + "y"][:, None], noise=float(v[p + "noise"]), kernel=kern, lengthscales=v[p + "ls"],
+                    kernel_variance=float(v[p + "kv"]))
+    xg, mc = v[p + "acq_grad_x"], v[p + "mc"]
+    ill = float(v[p + "cond_L"]) > 1e4
+    tol = 3e-6 if ill else 1e-9  # (relative to the largest gradient entry; at cond(K) ~ 1e10 float64 itself gives ~1e-6)
+    m, var, dm, dv = gp.predict_grad_batched(xg, standardised=True)
+    assert np.max(np.abs(np.ravel(m) - v[p + "pmean_ad_value"])) < 1e-9 * max(1.0, float(np.max(np.abs(v[p + "pmean_ad_value"]))))
+    for got, key in ((dm, "pmean_ad_grad"), (dv, "pvar_ad_grad")):
+        want = v[p + key]
+        assert np.max(np.abs(got - want)) < tol * float(np.max(np.abs(want))), key
+    for std, key in ((False, "wipv"), (True, "wipstd")):
+        vals, grads = O.wipv_values_and_grad(gp, xg, mc, std=std)
+        assert np.max(np.abs(vals - v[p + key + "_ad_value"]) / np.abs(v[p + key + "_ad_value"])) < (1e-7 if ill else 1e-11)
+        want = v[p + key + "_ad_grad"]
+        assert np.max(np.abs(grads - want)) < tol * float(np.max(np.abs(want))), key
