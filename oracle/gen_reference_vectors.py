@@ -409,7 +409,7 @@ def generate():
     G, A, C = load_reference()
     G_ad, jax_ad, A_ad = load_reference_autodiff()
     rng = np.random.default_rng(20261018)
-    out = {}
+    out, state_vals, state_keys, state_meta = {}, {}, [], {}
 
     # kernels and distances --------------------------------------------------------------------------------------------
     xa, xb = rng.uniform(0, 1, (40, 3)), rng.uniform(0, 1, (7, 3))
@@ -533,6 +533,14 @@ def generate():
             acq_grads[p + name + "_ad_grad"] = np.stack([r[1] for r in res_p])
         out.update(acq_grads)
         out[p + "acq_grad_x"] = xg
+        if p == "gp_matern_":  # the state dictionary the reference saves / loads / copies through (BOBE/gp.py:586-636)
+            st = gp.state_dict()
+            state_keys = sorted(st.keys())
+            for k, val in st.items():
+                if isinstance(val, np.ndarray) or isinstance(val, (int, float, bool)):
+                    state_vals[k] = np.asarray(val, dtype=np.float64)
+            state_meta = {k: (val if isinstance(val, (str, dict, list, bool, int, float)) or val is None else None)
+                          for k, val in st.items() if not isinstance(val, np.ndarray)}
         # update(): two new points and one duplicate of a training point
         new_x = np.vstack([rng.uniform(0, 1, (2, d)), X[7][None, :]])
         new_y = np.concatenate([_objective(new_x[:2]) + np.array([0.01, -0.02]), [y[7]]])[:, None]
@@ -573,6 +581,10 @@ def generate():
     out.update(logei_u=u, logei_helper=np.asarray(A._log_ei_helper(u)), ei_helper=np.asarray(A._ei_helper(u)))
 
     out = {k: np.asarray(v, dtype=np.float64) for k, v in out.items()}
+    out.update({"state_" + k: v for k, v in state_vals.items()})
+    import json
+    out["state_keys_json"] = np.array(json.dumps(state_keys))
+    out["state_meta_json"] = np.array(json.dumps(state_meta))
     np.savez_compressed(OUT, **out)
     print(f"wrote {OUT}: {len(out)} arrays, {os.path.getsize(OUT) / 1024:.0f} KiB")
 

@@ -1133,3 +1133,37 @@ def test_input_gradients_match_the_reference_autodiff(p, kern):
         e["d" + name] = rel(grad, v[p + name + "_ad_grad"])
     print(f"\n[reference autodiff, {p}] " + "  ".join(f"{k} {x:.1e}" for k, x in e.items()))
     assert all(x < tol for x in e.values()), e
+
+
+def test_state_dict_matches_the_reference_source_schema():
+    """GP.state_dict (BOBE/gp.py:586-636) of the product against the dictionary the reference's own class produced for the same
+    GP: the same keys, the same scalar / configuration entries, the same arrays; and a GP rebuilt by the product from the
+    REFERENCE's dictionary predicts like the original (save / load / copy interoperate across the two implementations)."""
+    import json
+    from bobe_b200 import GP
+    v = np.load(os.path.join(GOLDEN_DIR, "reference_source_vectors.npz"))
+    p = "gp_matern_"
+    gp = GP(v[p + "X"], v[p + "y"][:, None], noise=float(v[p + "noise"]), kernel="matern", lengthscales=v[p + "ls"],
+            kernel_variance=float(v[p + "kv"]))
+    st = gp.state_dict()
+    assert sorted(st.keys()) == json.loads(str(v["state_keys_json"]))
+    meta = json.loads(str(v["state_meta_json"]))
+    for k, want in meta.items():
+        got = st[k]
+        if isinstance(want, float):
+            assert abs(float(got) - want) <= 1e-14 * max(abs(want), 1.0), k
+        elif isinstance(want, list):
+            assert [float(a) for a in got] == [float(a) for a in want], k
+        else:
+            assert got == want, (k, got, want)
+    for k in ("train_x", "train_y", "lengthscales", "cholesky", "alphas"):
+        assert np.asarray(st[k]).shape == v["state_" + k].shape, k
+        assert mixed_err(np.asarray(st[k]), v["state_" + k], 1.0) < (1e-9 if k in ("cholesky", "alphas") else 1e-13), k
+    # the reference's dictionary -> the product's class
+    ref_state = dict(meta)
+    for k in ("train_x", "train_y", "lengthscales", "cholesky", "alphas"):
+        ref_state[k] = v["state_" + k]
+    gp2 = GP.from_state_dict(ref_state)
+    Xq = v[p + "Xq"]
+    assert mixed_err(gp2.predict_mean_batched(Xq), v[p + "mean_batched"], float(v[p + "y_std"])) < TOL_MEAN
+    assert mixed_err(gp2.predict_var_batched(Xq), v[p + "var_batched"], float(v[p + "y_std"]) ** 2) < TOL_VAR
