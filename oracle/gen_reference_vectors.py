@@ -171,15 +171,30 @@ def install_standin():
         def log_prob(self, x):
             return -np.log(self.high - self.low) + 0.0 * np.asarray(x)
 
-    def _unavailable(name):
-        class _D(Distribution):
-            def __init__(self, *a, **k):
-                raise NotImplementedError(f"numpyro.distributions.{name} is not part of the stand-in")
-        _D.__name__ = name
-        return _D
-    dist.Distribution, dist.Uniform = Distribution, Uniform
-    for name in ("LogNormal", "HalfCauchy", "Normal", "Gamma"):
-        setattr(dist, name, _unavailable(name))
+    # the other priors the reference names (DSLP, SAAS, user specs): the densities come from scipy.stats -- third-party
+    # code for the same named distributions -- so what these cases pin is the reference's COMPOSITION of them (which
+    # argument meets which density, 1 / (tausq l^2), the DSLP location sqrt2 + log(d) / 2, ...)
+    class LogNormal(Distribution):
+        def __init__(self, loc=0.0, scale=1.0):
+            self.loc, self.scale = float(loc), float(scale)
+
+        def log_prob(self, x):
+            return scipy.stats.lognorm.logpdf(np.asarray(x, dtype=np.float64), s=self.scale, scale=np.exp(self.loc))
+
+    class HalfCauchy(Distribution):
+        def __init__(self, scale=1.0):
+            self.scale = float(scale)
+
+        def log_prob(self, x):
+            return scipy.stats.halfcauchy.logpdf(np.asarray(x, dtype=np.float64), scale=self.scale)
+
+    class Normal(Distribution):
+        def __init__(self, loc=0.0, scale=1.0):
+            self.loc, self.scale = float(loc), float(scale)
+
+        def log_prob(self, x):
+            return scipy.stats.norm.logpdf(np.asarray(x, dtype=np.float64), loc=self.loc, scale=self.scale)
+    dist.Distribution, dist.Uniform, dist.LogNormal, dist.HalfCauchy, dist.Normal = Distribution, Uniform, LogNormal, HalfCauchy, Normal
     numpyro.distributions = dist
     mods.update({"numpyro": numpyro, "numpyro.distributions": dist})
 
@@ -362,7 +377,23 @@ def load_reference_autodiff():
 
         def log_prob(self, x):
             return -math.log(self.high - self.low) + 0.0 * x
-    dist.Distribution, dist.Uniform = Distribution, Uniform
+
+    class LogNormal(Distribution):  # textbook densities, differentiable (checked against scipy.stats by the NumPy-run values)
+        def __init__(self, loc=0.0, scale=1.0):
+            self.loc, self.scale = float(loc), float(scale)
+
+        def log_prob(self, x):
+            x = as_t(x)
+            return -torch.log(x) - math.log(self.scale) - 0.5 * math.log(2.0 * math.pi) - (torch.log(x) - self.loc) ** 2 / (2.0 * self.scale ** 2)
+
+    class HalfCauchy(Distribution):
+        def __init__(self, scale=1.0):
+            self.scale = float(scale)
+
+        def log_prob(self, x):
+            x = as_t(x)
+            return math.log(2.0 / math.pi) - math.log(self.scale) - torch.log1p((x / self.scale) ** 2)
+    dist.Distribution, dist.Uniform, dist.LogNormal, dist.HalfCauchy = Distribution, Uniform, LogNormal, HalfCauchy
     numpyro = types.ModuleType("numpyro")
     numpyro.__path__ = []
     numpyro.distributions = dist
@@ -552,6 +583,26 @@ def generate():
                     p + "upd_mean_batched": np.asarray(gp.predict_mean_batched(Xq[:6]))})
         if store_factor:
             out[p + "upd_cholesky"] = np.asarray(gp.cholesky)
+
+    # priors: DSLP lengthscales + LogNormal kernel variance, and SAAS (adds tausq as a hyper-parameter)
+    import torch
+    n, d = 60, 3
+    X, y = _training_set(rng, n, d)
+    for tag, kwargs in (("prior_dslp_", dict(lengthscale_prior="DSLP", kernel_variance_prior={"name": "LogNormal", "loc": 0.0, "scale": 1.0})),
+                        ("prior_saas_", dict(lengthscale_prior="SAAS", tausq=0.7)),
+                        ("prior_fixedkv_", dict(lengthscale_prior="DSLP", kernel_variance_prior="fixed"))):
+        gpp = G.GP(X, y[:, None], noise=1e-6, kernel="matern", lengthscales=np.array([0.5, 0.8, 1.1]), kernel_variance=1.4, **kwargs)
+        gpt = G_ad.GP(X, y[:, None], noise=1e-6, kernel="matern", lengthscales=torch.as_tensor(np.array([0.5, 0.8, 1.1])),
+                      kernel_variance=1.4, **kwargs)
+        P = int(gpp.num_hyperparams)
+        lp = np.log(rng.uniform(0.3, 2.0, (4, P)))
+        vg = jax_ad.value_and_grad(gpt.neg_mll)
+        ad = [vg(r) for r in lp]
+        out.update({tag + "X": X, tag + "y": y, tag + "log_params": lp, tag + "num_hyperparams": P,
+                    tag + "neg_mll": np.array([float(gpp.neg_mll(r)) for r in lp]),
+                    tag + "prior": np.array([float(np.sum(gpp.prior_func(*gpp._parse_hyperparams(r)))) for r in lp]),
+                    tag + "neg_mll_ad": np.array([a[0] for a in ad]), tag + "neg_mll_ad_grad": np.stack([a[1] for a in ad]),
+                    tag + "hyperparam_bounds": np.asarray(gpp.hyperparam_bounds)})
 
     # GPwithClassifier with the SVM mask (BOBE/clf_gp.py, BOBE/clf.py:36-83,188-214): a target with a deep infeasible region
     n, d, m = 120, 3, 60

@@ -20,8 +20,9 @@ PINNING.  The reference is pure Python/JAX; JAX, numpyro and tensorflow-probabil
    CUDA path to them.  The log-ML GRADIENT is pinned the same way: gp.py is loaded a second time with jax.numpy -> torch
    float64 tensors, where ``jax.value_and_grad(gp.neg_mll)`` (BOBE/optim.py:307-309) runs as reverse-mode autodiff through
    the reference's own statements; the analytic gradient below agrees with it to 1e-12 .. 3e-10 (9e-8 at cond(K) ~ 1e10).
-   NOT pinned by this route: XLA's own floating-point behaviour (rounding-level) and the numpyro priors other than Uniform
-   (tests/test_host_logic.py checks those against closed forms).
+   The same load runs the reference's GP.fit -> optimize_scipy, differentiates predict_single / EI / LogEI / WIPV / WIPStd in
+   the query point, and evaluates the DSLP / SAAS / fixed-kv prior compositions (scipy.stats densities standing in for
+   numpyro's).  NOT pinned by this route: XLA's own floating-point behaviour (rounding-level) and numpyro's density code.
 2. MATHEMATICS AND THIRD-PARTY CODE (round 1, tests/test_oracle.py): closed forms at n=1,2, interpolation / noise-level
    identities, the gradient three ways (analytic, torch autograd through ``torch.linalg.cholesky`` = the reverse-mode
    construction JAX uses, central differences), ``fantasy_var`` == ``predict_var`` of an actually-updated GP, an mpmath

@@ -1167,3 +1167,22 @@ def test_state_dict_matches_the_reference_source_schema():
     Xq = v[p + "Xq"]
     assert mixed_err(gp2.predict_mean_batched(Xq), v[p + "mean_batched"], float(v[p + "y_std"])) < TOL_MEAN
     assert mixed_err(gp2.predict_var_batched(Xq), v[p + "var_batched"], float(v[p + "y_std"]) ** 2) < TOL_VAR
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("prior_dslp_", dict(lengthscale_prior="DSLP", kernel_variance_prior={"name": "LogNormal", "loc": 0.0, "scale": 1.0})),
+    ("prior_saas_", dict(lengthscale_prior="SAAS", tausq=0.7)),
+    ("prior_fixedkv_", dict(lengthscale_prior="DSLP", kernel_variance_prior="fixed"))])
+def test_neg_mll_with_priors_matches_the_reference_source(tag, kw):
+    """The full fit objective (device log-ML + host priors) and its gradient for the DSLP / SAAS / fixed-kernel-variance
+    parameter layouts against the reference's own neg_mll and its jax.value_and_grad (reference_source_vectors.npz)."""
+    from bobe_b200 import GP
+    v = np.load(os.path.join(GOLDEN_DIR, "reference_source_vectors.npz"))
+    X, y, lp = v[tag + "X"], v[tag + "y"], v[tag + "log_params"]
+    gp = GP(X, y[:, None], noise=1e-6, kernel="matern", lengthscales=np.array([0.5, 0.8, 1.1]), kernel_variance=1.4, **kw)
+    assert gp.num_hyperparams == int(v[tag + "num_hyperparams"]) == lp.shape[1]
+    val, grad = gp.neg_mll_and_grad_batched(lp)
+    e_val = float(np.max(np.abs(val - v[tag + "neg_mll"]) / np.maximum(np.abs(v[tag + "neg_mll"]), X.shape[0])))
+    e_grad = float(np.max(np.abs(grad - v[tag + "neg_mll_ad_grad"])) / max(1.0, float(np.max(np.abs(v[tag + "neg_mll_ad_grad"])))))
+    print(f"\n[reference source, {tag}] neg_mll {e_val:.1e} gradient {e_grad:.1e}")
+    assert e_val < TOL_MLL and e_grad < TOL_GRAD

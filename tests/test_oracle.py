@@ -535,3 +535,37 @@ def test_oracle_input_gradients_match_the_reference_autodiff(p, kern):
         assert np.max(np.abs(vals - v[p + key + "_ad_value"]) / np.abs(v[p + key + "_ad_value"])) < (1e-7 if ill else 1e-11)
         want = v[p + key + "_ad_grad"]
         assert np.max(np.abs(grads - want)) < tol * float(np.max(np.abs(want))), key
+
+
+_PRIOR_CASES = (("prior_dslp_", dict(lengthscale_prior="DSLP", kernel_variance_prior={"name": "LogNormal", "loc": 0.0, "scale": 1.0})),
+                ("prior_saas_", dict(lengthscale_prior="SAAS", tausq=0.7)),
+                ("prior_fixedkv_", dict(lengthscale_prior="DSLP", kernel_variance_prior="fixed")))
+
+
+@pytest.mark.parametrize("tag,kw", _PRIOR_CASES)
+def test_priors_match_the_reference_source_composition(tag, kw):
+    """DSLP / SAAS / fixed-kernel-variance / LogNormal kernel-variance priors: the reference's own _standard_prior_logprob /
+    saas_prior_logprob (BOBE/gp.py:56-78,357-366) executed with scipy.stats densities standing in for numpyro's, and the
+    gradient of its full neg_mll by autodiff (torch-backed stand-in), vs the restatement AND the product's host-side priors."""
+    from bobe_b200 import GP
+    v = _ref_vectors()
+    X, y, lp = v[tag + "X"], v[tag + "y"], v[tag + "log_params"]
+    common = dict(noise=1e-6, kernel="matern", lengthscales=np.array([0.5, 0.8, 1.1]), kernel_variance=1.4)
+    ref = O.OracleGP(X, y[:, None], **common, **kw)
+    gp = GP(X, y[:, None], **common, **kw)  # host logic only: nothing here touches the device
+    assert ref.num_hyperparams == gp.num_hyperparams == int(v[tag + "num_hyperparams"])
+    assert np.allclose(ref.hyperparam_bounds, v[tag + "hyperparam_bounds"], rtol=1e-15)
+    assert np.allclose(np.asarray(gp.hyperparam_bounds), v[tag + "hyperparam_bounds"], rtol=1e-15)
+    for r in range(lp.shape[0]):
+        want_prior = float(v[tag + "prior"][r])
+        assert abs(ref.log_prior_and_grad(lp[r])[0] - want_prior) < 1e-13 * max(1.0, abs(want_prior))
+        assert abs(float(np.sum(gp.prior_func(*gp._parse_hyperparams(lp[r])))) - want_prior) < 1e-13 * max(1.0, abs(want_prior))
+        val, grad = ref.neg_mll_and_grad(lp[r])
+        assert abs(val - float(v[tag + "neg_mll"][r])) < 1e-12 * abs(val) and abs(val - float(v[tag + "neg_mll_ad"][r])) < 1e-10 * abs(val)
+        want = v[tag + "neg_mll_ad_grad"][r]
+        assert np.max(np.abs(grad - want)) < 1e-9 * max(1.0, float(np.max(np.abs(want))))
+        # the product's prior gradient = the reference's total gradient minus the restatement's data term
+        data_grad = grad + ref.log_prior_and_grad(lp[r])[1]  # neg_mll = -(data + prior)
+        prior_grad_ref = -(want) - (-data_grad)
+        got = gp._prior_grad(*gp._parse_hyperparams(lp[r]))
+        assert np.max(np.abs(np.asarray(got) - prior_grad_ref)) < 1e-8 * max(1.0, float(np.max(np.abs(want))))
