@@ -295,8 +295,10 @@ def load_reference_autodiff():
     jnp.max = lambda x, axis=None: torch.max(as_t(x))
     jnp.eye = lambda n, **k: torch.eye(n, dtype=f64)
     for name in ("exp", "log", "sqrt", "square", "abs", "isnan", "diag", "dot", "vstack", "hstack", "concatenate", "isclose"):
-        setattr(jnp, name, (lambda fn: (lambda *a, **k: fn(*[as_t(x) if not isinstance(x, (list, tuple)) else x for x in a], **k)))(
+        setattr(jnp, name, (lambda fn: (lambda *a, **k: fn(*[as_t(x) if not isinstance(x, (list, tuple)) else [as_t(e) for e in x]
+                                                             for x in a], **k)))(
             getattr(torch, name if name != "concatenate" else "cat")))
+    jnp.tile = lambda x, reps: torch.tile(as_t(x), reps)
     jnp.sum = lambda x, axis=None: torch.sum(as_t(x)) if axis is None else torch.sum(as_t(x), dim=axis)
     # (standardisation constants of NumPy training data stay NumPy scalars: ``ndarray - Tensor`` is not defined)
     jnp.mean = lambda x, axis=None: float(np.mean(x)) if isinstance(x, np.ndarray) else torch.mean(x)
@@ -304,7 +306,7 @@ def load_reference_autodiff():
     jnp.any, jnp.all = (lambda x, axis=None: torch.any(x) if axis is None else torch.any(x, dim=axis)), \
         (lambda x, axis=None: torch.all(x) if axis is None else torch.all(x, dim=axis))
     jnp.where = lambda c, a, b: torch.where(c, as_t(a), as_t(b))
-    jnp.clip = lambda a, a_min=None, a_max=None: torch.clamp(a, min=a_min, max=a_max)
+    jnp.clip = lambda a, a_min=None, a_max=None: torch.clamp(as_t(a), min=a_min, max=a_max)
     jnp.atleast_2d = lambda x: torch.atleast_2d(as_t(x))
     jnp.einsum = lambda spec, *ops: torch.einsum(spec if "->" in spec else spec + "->", *[as_t(o) for o in ops])
     jnp.linalg = types.SimpleNamespace(cholesky=torch.linalg.cholesky)
@@ -564,6 +566,17 @@ def generate():
             acq_grads[p + name + "_ad_grad"] = np.stack([r[1] for r in res_p])
         out.update(acq_grads)
         out[p + "acq_grad_x"] = xg
+        if store_factor:
+            # the acquisition optimisation flows themselves, with a seeded generator (BOBE/acquisition.py:255-291,350-412 ->
+            # BOBE/optim.py:249-359): starting points from the rng, L-BFGS-B on jax.value_and_grad of the reference's fun
+            for name, obj, kw_acq in (("ei", A_ad.EI(), {"zeta": zeta, "best_y": best_y}), ("logei", A_ad.LogEI(), {"zeta": zeta, "best_y": best_y})):
+                pt, val = obj.get_next_point(gp_ad, kw_acq, maxiter=100, n_restarts=6, verbose=False, rng=np.random.default_rng(7))
+                out.update({p + "flow_" + name + "_x": np.asarray(pt), p + "flow_" + name + "_val": np.float64(val)})
+            mc_samples = {"x": mc}
+            for name, obj in (("wipv", A_ad.WIPV()), ("wipstd", A_ad.WIPStd())):
+                pt, val = obj.get_next_point(gp_ad, {"mc_samples": {"x": torch.as_tensor(mc)}, "mc_points_size": 32}, maxiter=60,
+                                             n_restarts=1, verbose=False, rng=np.random.default_rng(11))
+                out.update({p + "flow_" + name + "_x": np.asarray(pt), p + "flow_" + name + "_val": np.float64(val)})
         if p == "gp_matern_":  # the state dictionary the reference saves / loads / copies through (BOBE/gp.py:586-636)
             st = gp.state_dict()
             state_keys = sorted(st.keys())

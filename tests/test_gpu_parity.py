@@ -1186,3 +1186,31 @@ def test_neg_mll_with_priors_matches_the_reference_source(tag, kw):
     e_grad = float(np.max(np.abs(grad - v[tag + "neg_mll_ad_grad"])) / max(1.0, float(np.max(np.abs(v[tag + "neg_mll_ad_grad"])))))
     print(f"\n[reference source, {tag}] neg_mll {e_val:.1e} gradient {e_grad:.1e}")
     assert e_val < TOL_MLL and e_grad < TOL_GRAD
+
+
+@pytest.mark.parametrize("p,kern", [("gp_rbf_", "rbf"), ("gp_matern_", "matern")])
+def test_acquisition_flows_match_the_reference_source(p, kern):
+    """EI / LogEI / WIPV / WIPStd ``get_next_point`` with a seeded generator against the reference's own flows
+    (BOBE/acquisition.py:255-291,350-412 -> BOBE/optim.py:249-359, run on jax.value_and_grad of the reference's ``fun`` under
+    the torch-backed stand-in): the same starting points come out of the generator, and L-BFGS-B on the CUDA value + analytic
+    gradient reaches the same next point and acquisition value."""
+    from bobe_b200 import GP, EI, LogEI, WIPV, WIPStd
+    v = np.load(os.path.join(GOLDEN_DIR, "reference_source_vectors.npz"))
+    gp = GP(v[p + "X"], v[p + "y"][:, None], noise=float(v[p + "noise"]), kernel=kern, lengthscales=v[p + "ls"],
+            kernel_variance=float(v[p + "kv"]))
+    kw = {"zeta": float(v[p + "ei_zeta"]), "best_y": float(v[p + "ei_best_y"])}
+    report = []
+    for name, acq in (("ei", EI()), ("logei", LogEI())):
+        pt, val = acq.get_next_point(gp, dict(kw), maxiter=100, n_restarts=6, verbose=False, rng=np.random.default_rng(7))
+        dx = float(np.max(np.abs(np.asarray(pt) - v[p + "flow_" + name + "_x"])))
+        dv = abs(float(val) - float(v[p + "flow_" + name + "_val"])) / max(abs(float(v[p + "flow_" + name + "_val"])), 1e-12)
+        report.append(f"{name} dx {dx:.1e} dval {dv:.1e}")
+        assert dx < 1e-4 and dv < 1e-6, (name, pt, v[p + "flow_" + name + "_x"], val)
+    for name, acq in (("wipv", WIPV()), ("wipstd", WIPStd())):
+        pt, val = acq.get_next_point(gp, {"mc_samples": {"x": v[p + "mc"]}, "mc_points_size": 32}, maxiter=60, n_restarts=1,
+                                     verbose=False, rng=np.random.default_rng(11))
+        dx = float(np.max(np.abs(np.asarray(pt) - v[p + "flow_" + name + "_x"])))
+        dv = abs(float(val) - float(v[p + "flow_" + name + "_val"])) / abs(float(v[p + "flow_" + name + "_val"]))
+        report.append(f"{name} dx {dx:.1e} dval {dv:.1e}")
+        assert dx < 1e-4 and dv < 1e-6, (name, pt, v[p + "flow_" + name + "_x"], val)
+    print(f"\n[reference flows, {p}] " + "  ".join(report))
