@@ -646,7 +646,39 @@ def generate():
 
     out = {k: np.asarray(v, dtype=np.float64) for k, v in out.items()}
     out.update({"state_" + k: v for k, v in state_vals.items()})
+    import inspect
     import json
+
+    # the public surface of the path: every public function / method with its parameter names and defaults, for the
+    # drop-in check of tests/test_host_logic.py (same names, same order, same defaults)
+    def sig(fn):
+        try:
+            ps = inspect.signature(fn).parameters.values()
+        except (TypeError, ValueError):
+            return None
+        return [[q.name, None if q.default is inspect.Parameter.empty else repr(q.default)] for q in ps]
+
+    surface = {"functions": {}, "classes": {}}
+    opt_mod = sys.modules["BOBE.optim"]
+    for mod, names in ((G, ("dist_sq", "kernel_diag", "rbf_kernel", "matern_kernel", "gp_mll", "fast_update_cholesky",
+                            "saas_prior_logprob", "make_distribution")),
+                       (opt_mod, ("optimize_scipy", "optimize_optax", "optimize_optax_vmap"))):
+        for name in names:
+            surface["functions"][name] = sig(getattr(mod, name))
+    for mod, names in ((G, ("GP",)), (C, ("GPwithClassifier",)), (A, ("AcquisitionFunction", "EI", "LogEI", "WIPV", "WIPStd"))):
+        for name in names:
+            cls = getattr(mod, name)
+            members = {}
+            for mname, member in inspect.getmembers(cls):
+                if mname.startswith("_") and mname != "__init__":
+                    continue
+                if isinstance(inspect.getattr_static(cls, mname), property):
+                    members[mname] = "property"
+                elif callable(member):
+                    members[mname] = sig(member)
+            surface["classes"][name] = members
+    with open(os.path.join(ROOT, "tests", "golden", "reference_public_surface.json"), "w") as f:
+        json.dump(surface, f, indent=1, sort_keys=True)
     out["state_keys_json"] = np.array(json.dumps(state_keys))
     out["state_meta_json"] = np.array(json.dumps(state_meta))
     np.savez_compressed(OUT, **out)

@@ -334,3 +334,52 @@ def test_optax_lockstep_equals_sequential_restarts():
                                 optimizer_options=dict(opts), batched_value_and_grad=vg_b)
     assert np.array_equal(seq[0], lock[0]) and seq[1] == lock[1]
     assert calls[0] == 6 and min(calls) < 6 and len(calls) <= 301  # restarts retire one by one; one call per step
+
+
+def test_public_surface_matches_the_reference_manifest():
+    """Drop-in check: every public function / method / property the reference exposes on this path -- recorded
+    from its own source by oracle/gen_reference_vectors.py into tests/golden/reference_public_surface.json -- exists here
+    with the same parameter names in the same order and the same defaults.  Extra TRAILING parameters with defaults are
+    allowed (``device=``, ``value_and_grad=`` ...: additions a reference caller never passes)."""
+    import inspect
+    import json
+    import bobe_b200 as B
+    from bobe_b200 import acquisition as A, optim as OPT, priors as PR
+    from conftest import GOLDEN_DIR
+    with open(os.path.join(GOLDEN_DIR, "reference_public_surface.json")) as f:
+        surface = json.load(f)
+
+    def check(name, fn, want):
+        got = [[q.name, None if q.default is inspect.Parameter.empty else repr(q.default)]
+               for q in inspect.signature(fn).parameters.values()]
+        assert len(got) >= len(want), (name, got, want)
+        for (gn, gd), (wn, wd) in zip(got, want):
+            assert gn == wn, (name, gn, wn)
+            if wd is not None and wd != gd:  # numerically equal defaults may print differently ([0.01, 5] vs [0.01, 5.0])
+                assert gd is not None and eval(gd) == eval(wd), (name, gn, gd, wd)  # noqa: S307 -- literals from our own fixture
+            # (a required parameter of the reference may have a default here -- ``fun=None`` beside the added
+            # ``value_and_grad=``: every reference call site still passes it)
+        for gn, gd in got[len(want):]:
+            assert gd is not None or gn in ("args", "kwargs"), (name, gn, "extra required parameter")
+
+    homes = {"optimize_scipy": OPT, "optimize_optax": OPT, "optimize_optax_vmap": OPT, "make_distribution": PR,
+             "saas_prior_logprob": PR}
+    for name, want in surface["functions"].items():
+        mod = homes.get(name, B)
+        assert hasattr(mod, name), f"missing function {name}"
+        check(name, getattr(mod, name), want)
+    classes = {"GP": B.GP, "GPwithClassifier": B.GPwithClassifier, "AcquisitionFunction": A.AcquisitionFunction, "EI": B.EI,
+               "LogEI": B.LogEI, "WIPV": B.WIPV, "WIPStd": B.WIPStd}
+    for cname, members in surface["classes"].items():
+        cls = classes[cname]
+        for mname, want in members.items():
+            if mname == "kernel":
+                # BOBE/clf_gp.py:248 defines a ``kernel`` METHOD that GP.__init__ (BOBE/gp.py:252) immediately shadows with
+                # the instance attribute ``self.kernel = rbf_kernel | matern_kernel``; here it is an instance attribute
+                # only, with that call signature (checked on the device in tests/test_gpu_api.py)
+                continue
+            assert hasattr(cls, mname), f"missing {cname}.{mname}"
+            if want == "property":
+                assert isinstance(inspect.getattr_static(cls, mname), property), f"{cname}.{mname} must be a property"
+            elif want is not None:
+                check(f"{cname}.{mname}", getattr(cls, mname), want)
