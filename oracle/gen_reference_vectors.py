@@ -597,6 +597,32 @@ def generate():
         if store_factor:
             out[p + "upd_cholesky"] = np.asarray(gp.cholesky)
 
+    # the HEADLINE shape (BASELINE config H: n = 2000, d = 16, Matern-5/2 ARD): inputs are the seeded synthetic set of
+    # oracle.gp_oracle (regenerated by the tests, not stored); outputs of the reference's own code only
+    sys.path.insert(0, ROOT)
+    from oracle import gp_oracle as O
+    nH, dH = 2000, 16
+    XH, yH = O.synthetic_training_set(nH, dH)
+    lsH = np.ones(dH)
+    gpH = G.GP(XH, np.asarray(yH).reshape(-1, 1), noise=1e-8, kernel="matern", lengthscales=lsH, kernel_variance=1.0)
+    XqH = O.synthetic_queries(48, dH, seed=21)
+    msH, vsH = gpH.predict_batched(XqH)
+    mcH, candH = O.synthetic_queries(64, dH, seed=22), O.synthetic_queries(2, dH, seed=23)
+    ktmH = gpH.kernel(gpH.train_x, mcH, gpH.lengthscales, gpH.kernel_variance, noise=gpH.noise, include_noise=False)
+    lpH = np.log(np.column_stack([rng.uniform(0.6, 1.8, (3, dH)), rng.uniform(0.6, 2.0, 3)]))
+    import torch
+    gpH_ad = G_ad.GP(XH, np.asarray(yH).reshape(-1, 1), noise=1e-8, kernel="matern", lengthscales=torch.as_tensor(lsH), kernel_variance=1.0)
+    adH = [jax_ad.value_and_grad(gpH_ad.neg_mll)(r) for r in lpH]
+    out.update(gpH_n=nH, gpH_d=dH, gpH_y_mean=np.float64(gpH.y_mean), gpH_y_std=np.float64(gpH.y_std),
+               gpH_cond_L=np.float64(np.linalg.cond(np.asarray(gpH.cholesky))),
+               gpH_logdet_half=np.float64(np.sum(np.log(np.diag(np.asarray(gpH.cholesky))))),
+               gpH_alphas=np.asarray(gpH.alphas), gpH_mean_batched=np.asarray(gpH.predict_mean_batched(XqH)),
+               gpH_var_batched=np.asarray(gpH.predict_var_batched(XqH)), gpH_std_mean_batched=np.asarray(msH).reshape(-1),
+               gpH_std_var_batched=np.asarray(vsH).reshape(-1),
+               gpH_fantasy_var=np.stack([np.asarray(gpH.fantasy_var(c, mcH, ktmH)) for c in candH]),
+               gpH_log_params=lpH, gpH_neg_mll=np.array([float(gpH.neg_mll(r)) for r in lpH]),
+               gpH_neg_mll_ad=np.array([a[0] for a in adH]), gpH_neg_mll_ad_grad=np.stack([a[1] for a in adH]))
+
     # priors: DSLP lengthscales + LogNormal kernel variance, and SAAS (adds tausq as a hyper-parameter)
     import torch
     n, d = 60, 3

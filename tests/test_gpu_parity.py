@@ -1214,3 +1214,32 @@ def test_acquisition_flows_match_the_reference_source(p, kern):
         report.append(f"{name} dx {dx:.1e} dval {dv:.1e}")
         assert dx < 1e-4 and dv < 1e-6, (name, pt, v[p + "flow_" + name + "_x"], val)
     print(f"\n[reference flows, {p}] " + "  ".join(report))
+
+
+def test_cuda_matches_the_reference_source_at_the_headline_shape():
+    """BASELINE config H (n = 2000, d = 16, Matern-5/2 ARD -- the shape the headline metric is quoted on): the CUDA path
+    against what the reference's OWN source computes there (oracle/gen_reference_vectors.py; inputs are the seeded synthetic
+    set): posterior mean / variance in both scalings, log-ML and its jax.value_and_grad gradient at three hyper-parameter rows,
+    and the fantasy variance."""
+    from bobe_b200 import GP
+    v = np.load(os.path.join(GOLDEN_DIR, "reference_source_vectors.npz"))
+    n, d = int(v["gpH_n"]), int(v["gpH_d"])
+    X, y = O.synthetic_training_set(n, d)
+    gp = GP(X, y, noise=1e-8, kernel="matern", lengthscales=np.ones(d), kernel_variance=1.0)
+    y_std = float(v["gpH_y_std"])
+    assert abs(gp.y_mean - float(v["gpH_y_mean"])) <= 1e-13 * abs(gp.y_mean) and abs(gp.y_std - y_std) <= 1e-13 * y_std
+    Xq = O.synthetic_queries(48, d, seed=21)
+    mean, var = gp.predict_mean_var_batched(Xq)
+    e_mean, e_var = mixed_err(mean, v["gpH_mean_batched"], y_std), mixed_err(var, v["gpH_var_batched"], y_std ** 2)
+    ms, vs = gp.predict_batched(Xq)
+    assert mixed_err(np.ravel(ms), v["gpH_std_mean_batched"], 1.0) < TOL_MEAN and mixed_err(np.ravel(vs), v["gpH_std_var_batched"], 1.0) < TOL_VAR
+    assert abs(float(gp._logdet.item()) - float(v["gpH_logdet_half"])) <= TOL_MLL * n
+    assert np.linalg.norm(np.asarray(gp.alphas).ravel() - v["gpH_alphas"].ravel()) <= 1e-9 * np.linalg.norm(v["gpH_alphas"])
+    val, grad = gp.neg_mll_and_grad_batched(v["gpH_log_params"])
+    e_mll = float(np.max(np.abs(val - v["gpH_neg_mll"]) / np.maximum(np.abs(v["gpH_neg_mll"]), n)))
+    e_grad = float(np.max(np.abs(grad - v["gpH_neg_mll_ad_grad"])) / max(1.0, float(np.max(np.abs(v["gpH_neg_mll_ad_grad"])))))
+    mc, cand = O.synthetic_queries(64, d, seed=22), O.synthetic_queries(2, d, seed=23)
+    e_fv = mixed_err(gp.fantasy_var(cand, mc), v["gpH_fantasy_var"], y_std ** 2)
+    print(f"\n[reference source, headline shape n={n} d={d}] mean {e_mean:.1e} var {e_var:.1e} neg_mll {e_mll:.1e} "
+          f"gradient {e_grad:.1e} fantasy {e_fv:.1e}")
+    assert e_mean < TOL_MEAN and e_var < TOL_VAR and e_mll < TOL_MLL and e_grad < TOL_GRAD and e_fv < TOL_VAR

@@ -569,3 +569,27 @@ def test_priors_match_the_reference_source_composition(tag, kw):
         prior_grad_ref = -(want) - (-data_grad)
         got = gp._prior_grad(*gp._parse_hyperparams(lp[r]))
         assert np.max(np.abs(np.asarray(got) - prior_grad_ref)) < 1e-8 * max(1.0, float(np.max(np.abs(want))))
+
+
+def test_oracle_matches_the_reference_source_at_the_headline_shape():
+    """BASELINE config H (n = 2000, d = 16, Matern-5/2 ARD): what the reference's own source computes for the seeded
+    synthetic set -- posterior mean / variance, log-ML at three hyper-parameter rows with the autodiff gradient, fantasy
+    variance -- vs the restatement."""
+    v = _ref_vectors()
+    n, d = int(v["gpH_n"]), int(v["gpH_d"])
+    X, y = O.synthetic_training_set(n, d)
+    gp = O.OracleGP(X, y, noise=1e-8, kernel="matern", lengthscales=np.ones(d), kernel_variance=1.0)
+    assert abs(gp.y_mean - float(v["gpH_y_mean"])) < 1e-13 * abs(gp.y_mean) and abs(gp.y_std - float(v["gpH_y_std"])) < 1e-13 * gp.y_std
+    condL = float(v["gpH_cond_L"])
+    assert abs(float(np.sum(np.log(np.diag(gp.cholesky)))) - float(v["gpH_logdet_half"])) < 1e-14 * condL * n
+    assert _rel(gp.alphas, v["gpH_alphas"]) < 1e-15 * condL ** 2
+    Xq = O.synthetic_queries(48, d, seed=21)
+    assert mixed_err(gp.predict_mean_batched(Xq), v["gpH_mean_batched"], gp.y_std) < 1e-11
+    assert mixed_err(gp.predict_var_batched(Xq), v["gpH_var_batched"], gp.y_std ** 2) < 1e-11
+    ms, vs = gp.predict_batched(Xq)
+    assert mixed_err(np.ravel(ms), v["gpH_std_mean_batched"], 1.0) < 1e-11 and mixed_err(np.ravel(vs), v["gpH_std_var_batched"], 1.0) < 1e-11
+    mc, cand = O.synthetic_queries(64, d, seed=22), O.synthetic_queries(2, d, seed=23)
+    assert mixed_err(gp.fantasy_var_shared(cand, mc), v["gpH_fantasy_var"], gp.y_std ** 2) < 1e-10
+    val, grad = gp.neg_mll_and_grad(v["gpH_log_params"][0])
+    assert abs(val - float(v["gpH_neg_mll"][0])) < 1e-11 * max(abs(val), n)
+    assert np.max(np.abs(grad - v["gpH_neg_mll_ad_grad"][0])) < 1e-8 * max(1.0, float(np.max(np.abs(grad))))
