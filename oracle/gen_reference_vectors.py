@@ -623,6 +623,22 @@ def generate():
                gpH_log_params=lpH, gpH_neg_mll=np.array([float(gpH.neg_mll(r)) for r in lpH]),
                gpH_neg_mll_ad=np.array([a[0] for a in adH]), gpH_neg_mll_ad_grad=np.stack([a[1] for a in adH]))
 
+    # BASELINE config D (n = 1500, d = 27, RBF, lengthscale 2) and config E (n = 4000, d = 12, RBF: the WIPV shape), same
+    # convention: seeded inputs regenerated by the tests, the reference's outputs stored
+    for tag, nS, dS, ellS in (("gpD_", 1500, 27, 2.0), ("gpE_", 4000, 12, 1.0)):
+        XS, yS = O.synthetic_training_set(nS, dS)
+        gpS = G.GP(XS, np.asarray(yS).reshape(-1, 1), noise=1e-8, kernel="rbf", lengthscales=np.full(dS, ellS), kernel_variance=1.0)
+        XqS = O.synthetic_queries(32, dS, seed=31)
+        mcS, candS = O.synthetic_queries(48, dS, seed=32), O.synthetic_queries(2, dS, seed=33)
+        ktmS = gpS.kernel(gpS.train_x, mcS, gpS.lengthscales, gpS.kernel_variance, noise=gpS.noise, include_noise=False)
+        fvS = np.stack([np.asarray(gpS.fantasy_var(c, mcS, ktmS)) for c in candS])
+        out.update({tag + "n": nS, tag + "d": dS, tag + "ell": ellS, tag + "y_std": np.float64(gpS.y_std),
+                    tag + "cond_L": np.float64(np.linalg.cond(np.asarray(gpS.cholesky))),
+                    tag + "logdet_half": np.float64(np.sum(np.log(np.diag(np.asarray(gpS.cholesky))))),
+                    tag + "mean_batched": np.asarray(gpS.predict_mean_batched(XqS)),
+                    tag + "var_batched": np.asarray(gpS.predict_var_batched(XqS)),
+                    tag + "fantasy_var": fvS, tag + "wipv": fvS.mean(axis=1), tag + "wipstd": np.sqrt(fvS).mean(axis=1)})
+
     # priors: DSLP lengthscales + LogNormal kernel variance, and SAAS (adds tausq as a hyper-parameter)
     import torch
     n, d = 60, 3

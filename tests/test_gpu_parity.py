@@ -1243,3 +1243,25 @@ def test_cuda_matches_the_reference_source_at_the_headline_shape():
     print(f"\n[reference source, headline shape n={n} d={d}] mean {e_mean:.1e} var {e_var:.1e} neg_mll {e_mll:.1e} "
           f"gradient {e_grad:.1e} fantasy {e_fv:.1e}")
     assert e_mean < TOL_MEAN and e_var < TOL_VAR and e_mll < TOL_MLL and e_grad < TOL_GRAD and e_fv < TOL_VAR
+
+
+@pytest.mark.parametrize("tag", ["gpD_", "gpE_"])
+def test_cuda_matches_the_reference_source_at_configs_d_and_e(tag):
+    """BASELINE config D (n = 1500, d = 27 RBF) and config E (n = 4000, d = 12 RBF, the WIPV shape): posterior mean / variance,
+    log-determinant, fantasy variance and WIPV / WIPStd against the reference's own source on the seeded synthetic sets."""
+    from bobe_b200 import GP
+    v = np.load(os.path.join(GOLDEN_DIR, "reference_source_vectors.npz"))
+    n, d, ell = int(v[tag + "n"]), int(v[tag + "d"]), float(v[tag + "ell"])
+    X, y = O.synthetic_training_set(n, d)
+    gp = GP(X, y, noise=1e-8, kernel="rbf", lengthscales=np.full(d, ell), kernel_variance=1.0)
+    y_std = float(v[tag + "y_std"])
+    Xq = O.synthetic_queries(32, d, seed=31)
+    mc, cand = O.synthetic_queries(48, d, seed=32), O.synthetic_queries(2, d, seed=33)
+    mean, var = gp.predict_mean_var_batched(Xq)
+    e = {"mean": mixed_err(mean, v[tag + "mean_batched"], y_std), "var": mixed_err(var, v[tag + "var_batched"], y_std ** 2),
+         "logdet": abs(float(gp._logdet.item()) - float(v[tag + "logdet_half"])) / n,
+         "fantasy": mixed_err(gp.fantasy_var(cand, mc), v[tag + "fantasy_var"], y_std ** 2),
+         "wipv": mixed_err(gp.fantasy_acquisition(mc, cand, std=False), v[tag + "wipv"], y_std ** 2),
+         "wipstd": mixed_err(gp.fantasy_acquisition(mc, cand, std=True), v[tag + "wipstd"], y_std)}
+    print(f"\n[reference source, {tag} n={n} d={d}] " + "  ".join(f"{k} {x:.1e}" for k, x in e.items()))
+    assert e["mean"] < TOL_MEAN and e["logdet"] < TOL_MLL and max(e["var"], e["fantasy"], e["wipv"], e["wipstd"]) < TOL_VAR

@@ -593,3 +593,20 @@ def test_oracle_matches_the_reference_source_at_the_headline_shape():
     val, grad = gp.neg_mll_and_grad(v["gpH_log_params"][0])
     assert abs(val - float(v["gpH_neg_mll"][0])) < 1e-11 * max(abs(val), n)
     assert np.max(np.abs(grad - v["gpH_neg_mll_ad_grad"][0])) < 1e-8 * max(1.0, float(np.max(np.abs(grad))))
+
+
+@pytest.mark.parametrize("tag", ["gpD_", "gpE_"])
+def test_oracle_matches_the_reference_source_at_configs_d_and_e(tag):
+    """BASELINE configs D (n = 1500, d = 27) and E (n = 4000, d = 12), RBF: the restatement vs the reference's own source."""
+    v = _ref_vectors()
+    n, d, ell = int(v[tag + "n"]), int(v[tag + "d"]), float(v[tag + "ell"])
+    X, y = O.synthetic_training_set(n, d)
+    gp = O.OracleGP(X, y, noise=1e-8, kernel="rbf", lengthscales=np.full(d, ell), kernel_variance=1.0)
+    Xq = O.synthetic_queries(32, d, seed=31)
+    mc, cand = O.synthetic_queries(48, d, seed=32), O.synthetic_queries(2, d, seed=33)
+    assert abs(float(np.sum(np.log(np.diag(gp.cholesky)))) - float(v[tag + "logdet_half"])) < 1e-12 * n
+    assert mixed_err(gp.predict_mean_batched(Xq), v[tag + "mean_batched"], gp.y_std) < 1e-11
+    assert mixed_err(gp.predict_var_batched(Xq), v[tag + "var_batched"], gp.y_std ** 2) < 1e-11
+    fv = gp.fantasy_var_shared(cand, mc)
+    assert mixed_err(fv, v[tag + "fantasy_var"], gp.y_std ** 2) < 1e-10
+    assert mixed_err(fv.mean(axis=1), v[tag + "wipv"], gp.y_std ** 2) < 1e-10
