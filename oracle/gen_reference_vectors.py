@@ -639,6 +639,17 @@ def generate():
                     tag + "var_batched": np.asarray(gpS.predict_var_batched(XqS)),
                     tag + "fantasy_var": fvS, tag + "wipv": fvS.mean(axis=1), tag + "wipstd": np.sqrt(fvS).mean(axis=1)})
 
+    # BASELINE config A (n = 100, d = 2, RBF with lengthscale 0.3: cond(K) ~ 3e9): WIPV / WIPStd with the 512 MC points as
+    # their own candidates, exactly the sweep of BOBE/acquisition.py:385-397 (lax.map of fun over mc_points)
+    XA, yA = O.synthetic_training_set(100, 2)
+    gpA = G.GP(XA, np.asarray(yA).reshape(-1, 1), noise=1e-8, kernel="rbf", lengthscales=np.full(2, 0.3), kernel_variance=1.0)
+    mcA = O.synthetic_queries(512, 2, seed=5)
+    ktmA = gpA.kernel(gpA.train_x, mcA, gpA.lengthscales, gpA.kernel_variance, noise=gpA.noise, include_noise=False)
+    out.update(gpA_y_std=np.float64(gpA.y_std), gpA_cond_L=np.float64(np.linalg.cond(np.asarray(gpA.cholesky))),
+               gpA_wipv_self=np.array([float(A.WIPV().fun(x, gpA, mc_points=mcA, k_train_mc=ktmA)) for x in mcA]),
+               gpA_wipstd_self=np.array([float(A.WIPStd().fun(x, gpA, mc_points=mcA, k_train_mc=ktmA)) for x in mcA]),
+               gpA_mean_batched=np.asarray(gpA.predict_mean_batched(mcA[:64])), gpA_var_batched=np.asarray(gpA.predict_var_batched(mcA[:64])))
+
     # priors: DSLP lengthscales + LogNormal kernel variance, and SAAS (adds tausq as a hyper-parameter)
     import torch
     n, d = 60, 3

@@ -610,3 +610,14 @@ def test_oracle_matches_the_reference_source_at_configs_d_and_e(tag):
     fv = gp.fantasy_var_shared(cand, mc)
     assert mixed_err(fv, v[tag + "fantasy_var"], gp.y_std ** 2) < 1e-10
     assert mixed_err(fv.mean(axis=1), v[tag + "wipv"], gp.y_std ** 2) < 1e-10
+
+
+def test_oracle_matches_the_reference_source_at_config_a():
+    """BASELINE config A: the 512-candidate WIPV / WIPStd sweep (BOBE/acquisition.py:385-397) of the reference's own source."""
+    v = _ref_vectors()
+    X, y = O.synthetic_training_set(100, 2)
+    gp = O.OracleGP(X, y, noise=1e-8, kernel="rbf", lengthscales=np.full(2, 0.3), kernel_variance=1.0)
+    mc = O.synthetic_queries(512, 2, seed=5)
+    assert mixed_err(O.wipv_values(gp, mc, mc), v["gpA_wipv_self"], gp.y_std ** 2) < 1e-9
+    assert mixed_err(O.wipv_values(gp, mc, mc, std=True), v["gpA_wipstd_self"], gp.y_std) < 1e-9
+    assert mixed_err(gp.predict_mean_batched(mc[:64]), v["gpA_mean_batched"], gp.y_std) < 1e-9
